@@ -1,0 +1,177 @@
+/* liburso_b200.so -- C-ABI of the B200-native UrsoNet hot path.
+ *
+ * The reference (pedropro/UrsoNet) has NO native/FFI boundary: its hot path is the Keras graph built in
+ * net.py:85-352,639-643, the losses net.py:705-762 and the optimizer wired in net.py:973-1017, all executed by
+ * TensorFlow library kernels.  Each entry point below replaces the TF op family named in its comment.  The
+ * Python host (ursonet_b200/net.py, mirroring net.UrsoNet) binds them with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions: every pointer is a caller-owned DEVICE pointer unless stated; activations are NHWC; every launch
+ * takes a cudaStream_t (passed as void*), never synchronises, never allocates device memory and is CUDA-graph
+ * capturable.  Return value: 0 = ok, non-zero = error, message via urso_last_error() (thread-local).
+ */
+#ifndef URSO_B200_H
+#define URSO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URSO_MAX_AMAPS 8
+#define URSO_MAX_SEGS 32
+
+int urso_version(void);
+const char* urso_last_error(void);
+int urso_num_sms(void);
+
+/* A 4-D NHWC bf16 view (possibly strided): element (n,h,w,c) at base + n*stride_n + h*stride_h + w*stride_w + c.
+ * C must be a multiple of 64 for MMA operands; strides are in ELEMENTS and must be multiples of 8. */
+typedef struct {
+  const void* base;
+  int32_t C, W, H, N;
+  int64_t stride_w, stride_h, stride_n;
+} urso_view4;
+
+/* One K-segment of an implicit GEMM: `c_chunks` 64-channel chunks read from view `map_id`, shifted by (dh,dw)
+ * pixels relative to the output pixel (out-of-bounds pixels read as zero: this IS the conv padding). */
+typedef struct {
+  int32_t map_id, dh, dw, c_chunks;
+} urso_seg;
+
+/* Output / addend / mask pixel addressing: element (n,h,w,c) at ptr + n*sn + h*sh + w*sw + c. */
+typedef struct {
+  void* ptr;
+  int64_t sn, sh, sw;
+} urso_pix;
+
+/* ---- Engine F: implicit-GEMM convolution on tcgen05 (replaces Conv2D fprop and dgrad: net.py:101-111,138-152,
+ * 171,225-235,639 and their TF autodiff input-gradients) fused with the BatchNorm/bias/ReLU/residual epilogue
+ * (net.py:103-116) or, for dgrad, with the ReLU-mask and gradient fan-in add.
+ *   D[pixel, n] = sum_seg sum_chunk A_seg[pixel + (dh,dw), 64-ch chunk] . Bmat[n, k]      (fp32 accumulate in TMEM)
+ *   out = mask( relu( D + shift[n] + addend[pixel, n] ) )                                 (each stage optional)
+ * Bmat is bf16 [b_rows, b_k] row-major (K contiguous), k enumerating (segment, chunk, channel) in order. */
+typedef struct {
+  urso_view4 a[URSO_MAX_AMAPS];
+  int32_t n_a;
+  const void* b;
+  int32_t b_rows, b_k;
+  urso_seg seg[URSO_MAX_SEGS];
+  int32_t n_seg;
+  int32_t OW, OH, NB; /* output pixel grid the tiles cover */
+  int32_t TW, TH;     /* pixel patch per 128-row tile, TW*TH == 128, powers of two */
+  urso_pix out;
+  int32_t out_fp32;   /* 0: bf16 output, 1: fp32 output */
+  const float* shift; /* [b_rows] or NULL */
+  urso_pix addend;    /* bf16, ptr NULL = none */
+  urso_pix mask;      /* bf16, ptr NULL = none: output forced to 0 where mask <= 0 */
+  int32_t relu;
+  float* colsum;      /* [b_rows] fp32 or NULL: atomically accumulates per-channel sums of the stored output */
+  int32_t block_n;    /* N tile: 0 = auto, else 32 / 64 / 128 / 256 */
+} urso_convgemm_desc;
+
+typedef struct urso_convgemm urso_convgemm_t;
+int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t** out);
+int urso_convgemm_launch(urso_convgemm_t* h, void* stream);
+void urso_convgemm_destroy(urso_convgemm_t* h);
+
+/* ---- Engine W: weight-gradient GEMM on tcgen05 (replaces Conv2DBackpropFilter of TF autodiff).
+ *   G[t][p, q] (+)= sum_pixels  P_t[pixel + (dh_t,dw_t), p] * Q[pixel, q]        t = 0..n_seg-1
+ * P views are the layer inputs (tap-shifted), Q is the output gradient.  fp32 result accumulated with atomics
+ * into g + t*g_seg_stride + p*g_sp + q*g_sq (caller zeroes g). */
+typedef struct {
+  urso_view4 p[URSO_MAX_AMAPS];
+  int32_t n_p;
+  urso_view4 q;
+  urso_seg seg[URSO_MAX_SEGS]; /* c_chunks unused */
+  int32_t n_seg;
+  int32_t PC, QC;     /* valid channels of P (rows of G) and Q (cols of G) */
+  int32_t OW, OH, NB; /* pixel grid of Q */
+  int32_t TW, TH;     /* pixel patch per K block, TW*TH == 64 */
+  float* g;
+  int64_t g_seg_stride, g_sp, g_sq;
+  int32_t split_k;    /* 0 = auto */
+  int32_t block_q;    /* Q (N) tile: 0 = auto, else 64 / 128 / 256 */
+} urso_wgrad_desc;
+
+typedef struct urso_wgrad urso_wgrad_t;
+int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out);
+int urso_wgrad_launch(urso_wgrad_t* h, void* stream);
+void urso_wgrad_destroy(urso_wgrad_t* h);
+
+/* ---- Stem input staging (replaces mold_image net.py:1337-1348 + ZeroPadding2D(3) net.py:170,254 + the im2col TF does
+ * internally): uint8 or fp32 RGB [B,H,W,3] -> bf16 E[B, H/2+3, W/2, 64], E[b,h2,wo,(s2,ph,pw,c)] =
+ * (img[2*h2+ph-3, 2*(wo+s2)+pw-3, c] - mean[c]) or 0 outside the image / for c==3. */
+int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, const float* mean3, void* e_out,
+                    int32_t B, int32_t H, int32_t W, void* stream);
+
+/* ---- MaxPooling2D 3x3/s2 'same' on even maps (net.py:176,258): TF pads bottom/right only. bf16 NHWC.
+ * argmax (uint8 [B,H/2,W/2,C], may be NULL for inference) records the FIRST maximum of each window (dr*3+ds). */
+int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* dx = (x>0) * scatter(dy to the recorded argmax): TF MaxPoolGrad fused with the stem's ReLU mask. */
+int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
+                     int32_t C, void* stream);
+
+/* ---- Dense layers of the two heads (net.py:302,316,336,345,350): fp32, small batch, weight-bandwidth bound.
+ * y[B,N] = act(x[B,K] @ w[K,N] + bias).  act: 0 linear, 1 relu. y must be zeroed by the caller (split-K atomics);
+ * urso_dense_bias_act finishes it. */
+int urso_dense_fwd(const float* x, const float* w, float* y, int32_t B, int32_t K, int32_t N, void* stream);
+int urso_dense_bias_act(float* y, const float* bias, int32_t B, int32_t N, int32_t act, void* stream);
+/* dy is masked in place by (y>0) when act==1; dw[K,N] = x^T dy (overwrites), db[N] = colsum(dy), dx[B,K] = dy w^T. */
+int urso_dense_bwd(const float* x, const float* w, const float* y, float* dy, float* dx, float* dw, float* db,
+                   int32_t B, int32_t K, int32_t N, int32_t act, void* stream);
+
+/* ---- Losses (net.py:705-762) with their gradients; scalars are written to loss_out[0] (already weighted). */
+/* softmax_loss_graph on ReLU'd logits: loss = w/B * sum_b -sum_k y_k log_softmax(z)_k ; dz = w/B (softmax(z)*sum_k y - y) */
+int urso_softmax_xent(const float* z, const float* y, float* dz, float* loss_out, int32_t B, int32_t N, float weight,
+                      void* stream);
+/* rel_loss_graph: ||y-p||_F / ||y||_F over the whole [B,3] tensor. */
+int urso_rel_loss(const float* pred, const float* gt, float* dpred, float* loss_out, int32_t B, int32_t N, float weight,
+                  void* stream);
+/* ori_q head: q = l2_normalize(raw) (net.py:346), loss = mean_b(1-|<gt,q>|) (net.py:724-733); draw = d loss / d raw. */
+int urso_quat_head(const float* raw, const float* gt, float* q_out, float* draw, float* loss_out, int32_t B,
+                   float weight, void* stream);
+
+/* ---- Parameter plumbing --------------------------------------------------------------------------------- */
+/* scale[c] = gamma/sqrt(var+eps), shift[c] = (bias-mean)*scale+beta  (BatchNorm(training=False), net.py:60-76).
+ * gamma == NULL: layer without BN (scale = 1, shift = bias or 0). */
+int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
+                 float eps, float* scale, float* shift, int32_t C, void* stream);
+/* Conv weight staging, Keras HWIO fp32 kernel viewed as w[R = KH*KW*CI][CO] -> bf16 K-major GEMM operands with the
+ * frozen-BN scale folded in:
+ *   rows (fprop):  out[row, k] = w[idx[k], row] * scale[row]                 row < rows_out (zero rows beyond CO)
+ *   cols (dgrad):  out[ci, slot*COp + co] = w[tap[slot]*CI + ci, co] * scale[co]
+ * idx / tap are device int32 arrays; -1 selects zero padding. */
+int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
+                           int32_t rows_out, void* stream);
+int urso_stage_weight_cols(const float* w, const float* scale, void* out, const int32_t* tap_dev, int32_t n_slots,
+                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, void* stream);
+/* From the raw wgrad G[R'][CO] (fp32; row r of the HWIO kernel lives at G row g_row_map[r], identity if NULL) and
+ * colsum[c] = sum_pixels du: dW = scale*G, dbias = scale*colsum, dbeta = colsum,
+ * dgamma = rstd*(sum_r W[r,c]*G[r,c] + (bias-mean)*colsum).  gamma == NULL: no BN; dbias == NULL: no bias. */
+int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const float* w, const float* colsum,
+                          const float* scale, const float* gamma, const float* mean, const float* var,
+                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta, int32_t R,
+                          int32_t CO, void* stream);
+
+/* ---- Optimizer (net.py:979-983,1008-1012; Keras-2 SGD / Adam(amsgrad) with global-norm clipnorm) over flat arenas.
+ * chunk_coef[i] applies to elements [256 i, 256 i + 256): reg gradient 2*wd/size(w) (0 for gamma/beta);
+ * chunk_lr[i] is 1 for trainable chunks, 0 for frozen ones (their gradient is zeroed and excluded from the norm).
+ * hyper_dev (device fp32[8]): [0]=lr (Adam: lr_t), [1]=momentum|beta1, [2]=beta2, [3]=eps, [4]=clipnorm.        */
+int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef, const float* chunk_lr,
+                       float grad_scale, float* sumsq_out, int64_t n, void* stream);
+int urso_sgd_step(float* param, float* vel, const float* grad, const float* chunk_lr, const float* sumsq,
+                  const float* hyper_dev, int64_t n, void* stream);
+int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float* grad, const float* chunk_lr,
+                      const float* sumsq, const float* hyper_dev, int64_t n, void* stream);
+
+/* ---- small elementwise helpers */
+int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+/* dst[b, 0:Cpad] (bf16) = src[b, 0:C] (fp32), zero padded: stages head gradients as an Engine-F operand. */
+int urso_pad_cast_rows(const float* src, void* dst, int64_t rows, int32_t C, int32_t Cpad, void* stream);
+int urso_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

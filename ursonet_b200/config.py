@@ -1,0 +1,80 @@
+"""Configuration object for the B200 UrsoNet path.
+
+API mirror of the reference `config.Config` (/root/reference/config.py:13-196): same attribute
+names, defaults, `update()`-derived fields, `display()` and `write_to_file()` so that
+`pose_estimator.py`-style callers work unchanged.  Additions for this build are grouped at the
+bottom (`COMPUTE_DTYPE`, `GPU_COUNT` wiring, `PARITY_MODE`).
+"""
+import json
+import os
+
+import numpy as np
+
+_DEFAULTS = dict(
+    GPU_COUNT=1, IMAGES_PER_GPU=2,
+    STEPS_PER_EPOCH=1000, VALIDATION_STEPS=50,
+    BACKBONE="resnet101", BOTTLENECK_WIDTH=128, BRANCH_SIZE=1024,
+    IMAGE_RESIZE_MODE="pad64", IMAGE_MIN_DIM=480, IMAGE_MAX_DIM=512, IMAGE_MIN_SCALE=0,
+    NR_IMAGE_CHANNELS=3,
+    LEARNING_RATE=0.001, LEARNING_MOMENTUM=0.9,
+    CLR=False, MAX_LEARNING_RATE=0.0005, BASE_LEARNING_RATE=0.0001, CLR_STEP_SIZE=4000,
+    REGRESS_ORI=True, REGRESS_LOC=True, REGRESS_KEYPOINTS=False,
+    ROT_AUG=True, SIM2REAL_AUG=False, ROT_IMAGE_AUG=False,
+    ORIENTATION_PARAM="quaternion", DECOUPLE_ORIENTATION=False,
+    LOC_BINS_PER_DIM=16, ORI_BINS_PER_DIM=32, BETA=6.0,
+    OPTIMIZER="SGD", WEIGHT_DECAY=0.0001, F16=False,
+    LEARNABLE_LOSS_WEIGHTS=False,
+    TRAIN_BN=False, GRADIENT_CLIP_NORM=5.0,
+    # --- additions of this build (not in the reference) ---
+    COMPUTE_DTYPE="bf16",   # activation / MMA operand type of the tcgen05 conv stack ("bf16")
+    PARITY_MODE=False,      # forward-only split-bf16 (hi+lo) operands: ~fp32 accuracy at 3x MMA cost
+)
+
+
+class Config:
+    """Class-attribute defaults like the reference; instances may override any of them and
+    must call update() afterwards (config.py:151-166)."""
+
+    MEAN_PIXEL = np.array([123.7, 116.8, 103.9])       # RGB mean subtracted by mold_image
+    LOSS_WEIGHTS = {"loc_loss": 1.0, "ori_loss": 1.0, "k2_loss": 1.0, "k3_loss": 1.0}
+
+    def __init__(self):
+        # per-instance copy so CLI mutation of LOSS_WEIGHTS does not leak between instances
+        self.LOSS_WEIGHTS = dict(type(self).LOSS_WEIGHTS)
+        self.update()
+
+    def update(self):
+        """Derived fields: BATCH_SIZE, IMAGE_SHAPE, IMAGE_META_SIZE."""
+        self.BATCH_SIZE = self.IMAGES_PER_GPU * self.GPU_COUNT
+        mode = self.IMAGE_RESIZE_MODE
+        if mode == "crop":
+            hw = (self.IMAGE_MIN_DIM, self.IMAGE_MIN_DIM)
+        elif mode == "pad64":
+            hw = (self.IMAGE_MIN_DIM, self.IMAGE_MAX_DIM)          # wide images assumed
+        else:
+            hw = (self.IMAGE_MAX_DIM, self.IMAGE_MAX_DIM)
+        self.IMAGE_SHAPE = np.array([hw[0], hw[1], self.NR_IMAGE_CHANNELS])
+        self.IMAGE_META_SIZE = 1 + self.NR_IMAGE_CHANNELS + 3 + 4 + 1
+
+    def _public(self):
+        for a in dir(self):
+            if not a.startswith("__") and not a.startswith("_") and not callable(getattr(self, a)):
+                yield a, getattr(self, a)
+
+    def display(self):
+        print("\nConfigurations:")
+        for k, v in self._public():
+            print("{:30} {}".format(k, v))
+        print("\n")
+
+    def write_to_file(self, filepath):
+        d = {k: v for k, v in self._public() if not isinstance(v, np.ndarray)}
+        directory = os.path.dirname(filepath)
+        if directory and not os.path.isdir(directory):
+            os.makedirs(directory)
+        with open(filepath, "w+") as f:
+            f.write(json.dumps(d))
+
+
+for _k, _v in _DEFAULTS.items():
+    setattr(Config, _k, _v)

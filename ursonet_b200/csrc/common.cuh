@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/urso_b200.h"
+
+namespace urso {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency, so the
+// library loads -- and its symbols can be checked -- on a machine without a driver).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled();
+
+// bf16 NHWC (possibly strided) view -> 4-D tensor map {C, W, H, N}, box {64, bw, bh, 1}, SWIZZLE_128B, zero OOB fill.
+int make_view_map(CUtensorMap* out, const urso_view4& v, int box_w, int box_h);
+// bf16 row-major [rows, k] -> 2-D tensor map {k, rows}, box {64, box_rows}, SWIZZLE_128B.
+int make_mat_map(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int box_rows);
+
+#define URSO_CUDA_OK(expr)                                                                 \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      urso::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+#define URSO_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      urso::set_error(__VA_ARGS__);  \
+      return 2;                      \
+    }                                \
+  } while (0)
+
+}  // namespace urso

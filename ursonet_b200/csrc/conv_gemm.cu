@@ -1,0 +1,404 @@
+// Engine F: persistent, warp-specialised implicit-GEMM convolution on tcgen05 tensor cores.
+//
+//   D[pixel, n] = sum over K-segments (filter taps / concatenated inputs) of  A_seg[pixel + shift, c] * B[n, k]
+//
+//  * A tiles: 128 output pixels (a TH x TW patch of one image) x 64 channels, fetched by ONE 4-D TMA box per
+//    K-step straight from the NHWC activation tensor.  The tap shift is added to the box coordinates and TMA's
+//    out-of-bounds zero fill implements the convolution padding -- no im2col buffer ever exists.
+//  * B tiles: BLOCK_N x 64 slices of the staged (BN-folded, K-major) weight matrix, 2-D TMA.
+//  * both land in 128B-swizzled shared memory and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued by
+//    one thread; fp32 accumulators live in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
+//    tile i+1.
+//  * epilogue warps: tcgen05.ld -> (+shift, +addend, ReLU, mask) -> bf16/fp32 vector stores, optional per-channel
+//    sums (d beta) -- the BatchNorm / bias / ReLU / residual of net.py:103-116 never touch HBM on their own.
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace urso {
+
+struct SegDev {
+  int16_t map_id, dh, dw, c_chunks;
+};
+
+struct PixDev {
+  void* ptr;
+  long long sn, sh, sw;
+};
+
+struct ConvGemmParams {
+  CUtensorMap a_maps[URSO_MAX_AMAPS];
+  CUtensorMap b_map;
+  SegDev seg[URSO_MAX_SEGS];
+  int n_seg;
+  int OW, OH, NB;
+  int TW, TH, tw_shift;
+  int tiles_w, tiles_h, n_tiles_n, total_tiles;
+  int ncols;
+  PixDev out, addend, mask;
+  int out_fp32, relu;
+  const float* shift;
+  float* colsum;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+
+template <int BLOCK_N>
+struct ConvGemmCfg {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
+                                            int& w0) {
+  n_tile = tile % p.n_tiles_n;
+  int m_tile = tile / p.n_tiles_n;
+  int twi = m_tile % p.tiles_w;
+  int rest = m_tile / p.tiles_w;
+  int thi = rest % p.tiles_h;
+  img = rest / p.tiles_h;
+  h0 = thi * p.TH;
+  w0 = twi * p.TW;
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kATileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.a_maps[i]);
+    tma_prefetch_desc(&p.b_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n_tile, img, h0, w0;
+        decode_tile(p, tile, n_tile, img, h0, w0);
+        int kcol = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const SegDev sg = p.seg[s];
+          for (int c = 0; c < sg.c_chunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + Cfg::kBTileBytes);
+            tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
+                        h0 + sg.dh, img);
+            tma_load_2d(sB + stage * Cfg::kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+            kcol += kBlockK;
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int ksteps = 0;
+      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kATileBytes);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // K-major SW128: advancing 16 elements = 32 bytes inside the 128B swizzle row
+            uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (128 threads <-> 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      int n_tile, img, h0, w0;
+      decode_tile(p, tile, n_tile, img, h0, w0);
+      const int h = h0 + (row >> p.tw_shift);
+      const int w = w0 + (row & (p.TW - 1));
+      const bool valid = (h < p.OH) && (w < p.OW);
+      const long long o_off = (long long)img * p.out.sn + (long long)h * p.out.sh + (long long)w * p.out.sw;
+      const long long a_off = (long long)img * p.addend.sn + (long long)h * p.addend.sh + (long long)w * p.addend.sw;
+      const long long m_off = (long long)img * p.mask.sn + (long long)h * p.mask.sh + (long long)w * p.mask.sw;
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        const int col0 = n_tile * BLOCK_N + j * 32;
+        if (col0 >= p.ncols) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+        if (p.shift != nullptr) {
+          const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 s4 = __ldg(sp + i);
+            v[4 * i + 0] += s4.x;
+            v[4 * i + 1] += s4.y;
+            v[4 * i + 2] += s4.z;
+            v[4 * i + 3] += s4.w;
+          }
+        }
+        if (p.addend.ptr != nullptr && valid) {
+          const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.addend.ptr) + a_off + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u = ap[i];
+            v[8 * i + 0] += bf16_lo(u.x);
+            v[8 * i + 1] += bf16_hi(u.x);
+            v[8 * i + 2] += bf16_lo(u.y);
+            v[8 * i + 3] += bf16_hi(u.y);
+            v[8 * i + 4] += bf16_lo(u.z);
+            v[8 * i + 5] += bf16_hi(u.z);
+            v[8 * i + 6] += bf16_lo(u.w);
+            v[8 * i + 7] += bf16_hi(u.w);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (p.mask.ptr != nullptr && valid) {
+          const uint4* mp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask.ptr) + m_off + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u = mp[i];
+            v[8 * i + 0] = bf16_lo(u.x) > 0.0f ? v[8 * i + 0] : 0.0f;
+            v[8 * i + 1] = bf16_hi(u.x) > 0.0f ? v[8 * i + 1] : 0.0f;
+            v[8 * i + 2] = bf16_lo(u.y) > 0.0f ? v[8 * i + 2] : 0.0f;
+            v[8 * i + 3] = bf16_hi(u.y) > 0.0f ? v[8 * i + 3] : 0.0f;
+            v[8 * i + 4] = bf16_lo(u.z) > 0.0f ? v[8 * i + 4] : 0.0f;
+            v[8 * i + 5] = bf16_hi(u.z) > 0.0f ? v[8 * i + 5] : 0.0f;
+            v[8 * i + 6] = bf16_lo(u.w) > 0.0f ? v[8 * i + 6] : 0.0f;
+            v[8 * i + 7] = bf16_hi(u.w) > 0.0f ? v[8 * i + 7] : 0.0f;
+          }
+        }
+        if (valid) {
+          if (p.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out.ptr) + o_off + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out.ptr) + o_off + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+        if (p.colsum != nullptr) {
+          // per-channel sum over the 32 rows of this warp (butterfly), one atomic per channel per warp
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = valid ? v[i] : 0.0f;
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (lane == i) atomicAdd(p.colsum + col0 + i, s);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace urso
+
+// ====================================================================================== host side
+struct urso_convgemm {
+  urso::ConvGemmParams params;
+  int block_n;
+  int grid;
+};
+
+template <int BLOCK_N>
+static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
+  using Cfg = urso::ConvGemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 256, Cfg::kSmemBytes, stream>>>(h->params);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t** out) {
+  using namespace urso;
+  URSO_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  URSO_REQUIRE(d->n_a >= 1 && d->n_a <= URSO_MAX_AMAPS, "n_a=%d out of range", d->n_a);
+  URSO_REQUIRE(d->n_seg >= 1 && d->n_seg <= URSO_MAX_SEGS, "n_seg=%d out of range", d->n_seg);
+  URSO_REQUIRE(d->TW * d->TH == 128 && (d->TW & (d->TW - 1)) == 0, "TW*TH must be 128 with TW a power of two (got %dx%d)",
+               d->TW, d->TH);
+  URSO_REQUIRE(d->b_rows % 32 == 0, "b_rows=%d must be a multiple of 32", d->b_rows);
+  URSO_REQUIRE(d->out.ptr != nullptr, "null output");
+  auto* h = new urso_convgemm();
+  ConvGemmParams& p = h->params;
+  memset(&p, 0, sizeof(p));
+  int ktot = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const urso_seg& sg = d->seg[s];
+    if (sg.map_id < 0 || sg.map_id >= d->n_a || sg.c_chunks < 1 || sg.c_chunks * 64 > ((d->a[sg.map_id].C + 63) / 64) * 64) {
+      set_error("segment %d invalid (map %d, chunks %d)", s, sg.map_id, sg.c_chunks);
+      delete h;
+      return 2;
+    }
+    p.seg[s] = SegDev{(int16_t)sg.map_id, (int16_t)sg.dh, (int16_t)sg.dw, (int16_t)sg.c_chunks};
+    ktot += sg.c_chunks * 64;
+  }
+  if (ktot != d->b_k) {
+    set_error("segments cover K=%d but b_k=%d", ktot, d->b_k);
+    delete h;
+    return 2;
+  }
+  for (int i = 0; i < URSO_MAX_AMAPS; ++i) {
+    const urso_view4& v = d->a[i < d->n_a ? i : 0];
+    if (int rc = make_view_map(&p.a_maps[i], v, d->TW, d->TH)) {
+      delete h;
+      return rc;
+    }
+  }
+  int bn = d->block_n;
+  if (bn == 0) bn = d->b_rows >= 256 && d->b_rows % 256 == 0 ? 256 : (d->b_rows >= 128 ? 128 : (d->b_rows >= 64 ? 64 : 32));
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
+    set_error("block_n=%d unsupported", bn);
+    delete h;
+    return 2;
+  }
+  h->block_n = bn;
+  if (int rc = make_mat_map(&p.b_map, d->b, d->b_rows, d->b_k, bn)) {
+    delete h;
+    return rc;
+  }
+  p.n_seg = d->n_seg;
+  p.OW = d->OW; p.OH = d->OH; p.NB = d->NB;
+  p.TW = d->TW; p.TH = d->TH;
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < d->TW) ++p.tw_shift;
+  p.tiles_w = (d->OW + d->TW - 1) / d->TW;
+  p.tiles_h = (d->OH + d->TH - 1) / d->TH;
+  p.n_tiles_n = (d->b_rows + bn - 1) / bn;
+  long long total = (long long)p.tiles_w * p.tiles_h * d->NB * p.n_tiles_n;
+  if (total <= 0 || total > 0x7fffffffLL) {
+    set_error("bad tile count %lld", total);
+    delete h;
+    return 2;
+  }
+  p.total_tiles = (int)total;
+  p.ncols = d->b_rows;
+  p.out = PixDev{d->out.ptr, d->out.sn, d->out.sh, d->out.sw};
+  p.addend = PixDev{d->addend.ptr, d->addend.sn, d->addend.sh, d->addend.sw};
+  p.mask = PixDev{d->mask.ptr, d->mask.sn, d->mask.sh, d->mask.sw};
+  p.out_fp32 = d->out_fp32;
+  p.relu = d->relu;
+  p.shift = d->shift;
+  p.colsum = d->colsum;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  h->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  *out = h;
+  return 0;
+}
+
+extern "C" int urso_convgemm_launch(urso_convgemm_t* h, void* stream) {
+  URSO_REQUIRE(h != nullptr, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (h->block_n) {
+    case 32: return launch_conv_gemm<32>(h, s);
+    case 64: return launch_conv_gemm<64>(h, s);
+    case 128: return launch_conv_gemm<128>(h, s);
+    case 256: return launch_conv_gemm<256>(h, s);
+  }
+  urso::set_error("unsupported BLOCK_N %d", h->block_n);
+  return 2;
+}
+
+extern "C" void urso_convgemm_destroy(urso_convgemm_t* h) { delete h; }

@@ -1,0 +1,491 @@
+// Bandwidth-bound layers of the path: stem input staging, max-pool, the fp32 Dense heads and the losses.
+// All are HBM/L2-bound: 16-byte vector accesses, coalesced along the channel (innermost NHWC) axis, grids sized in
+// multiples of the SM count where the problem allows.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace urso {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum, result valid in every thread; blockDim.x multiple of 32, <= 1024
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? sh[l] : 0.0f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? sh[l] : -INFINITY;
+  return warp_max(t);
+}
+
+// ------------------------------------------------------------------------------------------ stem staging
+// E[b, h2, wo, k]  k = s2*16 + ph*8 + pw*4 + c ; one thread writes one 16-byte group (fixed s2,ph: 8 values).
+template <bool U8>
+__global__ void stem_stage_kernel(const void* __restrict__ img, int subtract_mean, const float* __restrict__ mean3,
+                                  __nv_bfloat16* __restrict__ e, int B, int H, int W) {
+  const int H2 = H / 2 + 3, WO = W / 2;
+  const long long total = (long long)B * H2 * WO * 8;
+  const float m0 = subtract_mean ? mean3[0] : 0.f, m1 = subtract_mean ? mean3[1] : 0.f, m2 = subtract_mean ? mean3[2] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);  // group: s2 = g>>1, ph = g&1
+    long long r = i >> 3;
+    const int wo = (int)(r % WO); r /= WO;
+    const int h2 = (int)(r % H2);
+    const int b = (int)(r / H2);
+    const int s2 = g >> 1, ph = g & 1;
+    const int y = 2 * h2 + ph - 3;
+    float v[8];
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw) {
+      const int x = 2 * (wo + s2) + pw - 3;
+      const bool in = (y >= 0) && (y < H) && (x >= 0) && (x < W);
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (in) {
+        const long long off = (((long long)b * H + y) * W + x) * 3;
+        if (U8) {
+          const uint8_t* p = static_cast<const uint8_t*>(img) + off;
+          c0 = (float)p[0] - m0; c1 = (float)p[1] - m1; c2 = (float)p[2] - m2;
+        } else {
+          const float* p = static_cast<const float*>(img) + off;
+          c0 = p[0] - m0; c1 = p[1] - m1; c2 = p[2] - m2;
+        }
+      }
+      v[pw * 4 + 0] = c0; v[pw * 4 + 1] = c1; v[pw * 4 + 2] = c2; v[pw * 4 + 3] = 0.f;
+    }
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(e + i * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ max-pool 3x3 / s2 'same'
+// Even H, W: TF pads only bottom/right, so window (ho,wo) covers rows 2ho..2ho+2, cols 2wo..2wo+2 clipped to the map.
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ argmax, int B, int H, int W, int C) {
+  const int HO = H / 2, WO = W / 2, C8 = C / 8;
+  const long long total = (long long)B * HO * WO * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % WO); r /= WO;
+    const int ho = (int)(r % HO);
+    const int b = (int)(r / HO);
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr) {
+      const int h = 2 * ho + dr;
+      if (h >= H) continue;
+#pragma unroll
+      for (int ds = 0; ds < 3; ++ds) {
+        const int w = 2 * wo + ds;
+        if (w >= W) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + c8 * 8);
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = __bfloat162float(e[j]);
+          if (f > best[j]) { best[j] = f; arg[j] = dr * 3 + ds; }   // strict > keeps the FIRST maximum
+        }
+      }
+    }
+    __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(best[j]);
+    *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<uint4*>(o);
+    if (argmax != nullptr) {
+      uint8_t a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = (uint8_t)arg[j];
+      *reinterpret_cast<uint2*>(argmax + i * 8) = *reinterpret_cast<uint2*>(a);
+    }
+  }
+}
+
+// dx[h,w,c] = (x>0) * sum over windows whose recorded argmax is (h,w) of dy.  One thread: one pixel x 8 channels.
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ argmax,
+                                   const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int B, int H,
+                                   int W, int C) {
+  const int HO = H / 2, WO = W / 2, C8 = C / 8;
+  const long long total = (long long)B * H * W * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long r = i / C8;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows containing row h: ho in {h/2 (dr = h - 2ho in {0,1}), h/2 - 1 (dr = 2, only when h even)}
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ho = h / 2 - a;
+      const int dr = h - 2 * ho;
+      if (ho < 0 || ho >= HO || dr > 2) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int wo = w / 2 - c;
+        const int ds = w - 2 * wo;
+        if (wo < 0 || wo >= WO || ds > 2) continue;
+        const long long o = ((((long long)b * HO + ho) * WO + wo) * C8 + c8) * 8;
+        const uint2 av = *reinterpret_cast<const uint2*>(argmax + o);
+        const uint4 gv = *reinterpret_cast<const uint4*>(dy + o);
+        const uint8_t* ai = reinterpret_cast<const uint8_t*>(&av);
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gv);
+        const int code = dr * 3 + ds;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (ai[j] == code) acc[j] += __bfloat162float(g[j]);
+      }
+    }
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + i * 8);
+    const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
+    __nv_bfloat16 o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(__bfloat162float(xe[j]) > 0.f ? acc[j] : 0.f);
+    *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<uint4*>(o8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Dense heads (fp32)
+// y[b, n] += sum_{k in chunk} x[b,k] * w[k,n].  Block: 128 threads = 128 output columns, 32 batch rows in registers,
+// one K chunk of 64 per block (split-K over gridDim.y, combined with atomics; y pre-zeroed).
+constexpr int kDenseKC = 64;
+__global__ void __launch_bounds__(128) dense_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        float* __restrict__ y, int B, int K, int N) {
+  __shared__ float4 xs[kDenseKC][8];  // [k][b/4] : 32 batch rows
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * kDenseKC;
+  const int b0 = blockIdx.z * 32;
+  for (int i = threadIdx.x; i < kDenseKC * 32; i += 128) {
+    const int kk = i % kDenseKC, bb = i / kDenseKC;  // consecutive threads read consecutive k: coalesced
+    float v = 0.f;
+    if (k0 + kk < K && b0 + bb < B) v = x[(long long)(b0 + bb) * K + k0 + kk];
+    reinterpret_cast<float*>(&xs[kk][0])[bb] = v;
+  }
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+  if (n < N) {
+    const int kend = min(kDenseKC, K - k0);
+    for (int kk = 0; kk < kend; ++kk) {
+      const float wv = __ldg(w + (long long)(k0 + kk) * N + n);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 xv = xs[kk][q];
+        acc[4 * q + 0] += xv.x * wv;
+        acc[4 * q + 1] += xv.y * wv;
+        acc[4 * q + 2] += xv.z * wv;
+        acc[4 * q + 3] += xv.w * wv;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+      if (b0 + b < B) atomicAdd(y + (long long)(b0 + b) * N + n, acc[b]);
+  }
+}
+
+__global__ void dense_bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int B, int N, int act) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = y[i] + bias[i % N];
+    if (act == 1) v = fmaxf(v, 0.f);
+    y[i] = v;
+  }
+}
+
+// dy <- dy * (y>0) (if relu) ; db[n] = sum_b dy[b,n].  One thread per column.
+__global__ void dense_mask_bias_grad_kernel(const float* __restrict__ y, float* __restrict__ dy, float* __restrict__ db,
+                                            int B, int N, int act) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float g = dy[(long long)b * N + n];
+    if (act == 1 && !(y[(long long)b * N + n] > 0.f)) {
+      g = 0.f;
+      dy[(long long)b * N + n] = 0.f;
+    }
+    s += g;
+  }
+  if (db != nullptr) db[n] = s;
+}
+
+// dw[k, n] = sum_b x[b,k] dy[b,n].  Block = 128 columns x 8 k-rows; batch staged through shared memory in tiles of 32.
+__global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dw, int B, int K, int N) {
+  __shared__ float xs[32][8];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += 128) {
+      const int kk = i & 7, bb = i >> 3;
+      xs[bb][kk] = (b0 + bb < B && k0 + kk < K) ? x[(long long)(b0 + bb) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+    if (n < N) {
+      const int bend = min(32, B - b0);
+      for (int bb = 0; bb < bend; ++bb) {
+        const float g = __ldg(dy + (long long)(b0 + bb) * N + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xs[bb][j] * g;
+      }
+    }
+  }
+  if (n < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (k0 + j < K) dw[(long long)(k0 + j) * N + n] = acc[j];
+  }
+}
+
+// dx[b, k] = sum_n dy[b,n] w[k,n].  One warp per k row, 32 batch rows at a time.
+__global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                          float* __restrict__ dx, int B, int K, int N) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= K) return;
+  const float* wr = w + (long long)warp * N;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+    const int bend = min(32, B - b0);
+    for (int n = lane; n < N; n += 32) {
+      const float wv = __ldg(wr + n);
+#pragma unroll
+      for (int b = 0; b < 32; ++b)
+        if (b < bend) acc[b] += wv * __ldg(dy + (long long)(b0 + b) * N + n);
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const float s = warp_sum(acc[b]);
+      if (lane == 0 && b < bend) dx[(long long)(b0 + b) * K + warp] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ losses
+// tf.losses.softmax_cross_entropy(onehot_labels=y, logits=z): mean over batch.  One block per row.
+__global__ void __launch_bounds__(256) softmax_xent_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                                           float* __restrict__ dz, float* __restrict__ loss_out, int B,
+                                                           int N, float weight) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* zr = z + (long long)b * N;
+  const float* yr = y + (long long)b * N;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, zr[i]);
+  m = block_max(m, sh);
+  float se = 0.f, sy = 0.f, syz = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    se += expf(zr[i] - m);
+    sy += yr[i];
+    syz += yr[i] * zr[i];
+  }
+  se = block_sum(se, sh);
+  sy = block_sum(sy, sh);
+  syz = block_sum(syz, sh);
+  const float lse = m + logf(se);
+  const float scale = weight / (float)B;
+  if (dz != nullptr) {
+    const float inv = 1.0f / se;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) dz[(long long)b * N + i] = scale * (expf(zr[i] - m) * inv * sy - yr[i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(loss_out, scale * (lse * sy - syz));
+}
+
+// tf.norm((gt - pred) / tf.norm(gt)) over the whole tensor (net.py:757).  Single block.
+__global__ void __launch_bounds__(256) rel_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                       float* __restrict__ dpred, float* __restrict__ loss_out, int n,
+                                                       float weight) {
+  __shared__ float sh[32];
+  float sd = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = gt[i] - pred[i];
+    sd += d * d;
+    sg += gt[i] * gt[i];
+  }
+  sd = block_sum(sd, sh);
+  sg = block_sum(sg, sh);
+  const float nd = sqrtf(sd), ng = sqrtf(sg);
+  if (dpred != nullptr) {
+    const float k = nd > 0.f ? weight / (nd * ng) : 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dpred[i] = -(gt[i] - pred[i]) * k;
+  }
+  if (threadIdx.x == 0) loss_out[0] = weight * nd / ng;
+}
+
+// q = l2_normalize(raw) ; loss = mean_b (1 - |<gt, q>|).  One thread per row (B is small), single block reduce.
+__global__ void __launch_bounds__(256) quat_head_kernel(const float* __restrict__ raw, const float* __restrict__ gt,
+                                                        float* __restrict__ q_out, float* __restrict__ draw,
+                                                        float* __restrict__ loss_out, int B, float weight) {
+  __shared__ float sh[32];
+  float part = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float r[4], g[4], q[4];
+    float n2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[j] = raw[b * 4 + j];
+      g[j] = gt != nullptr ? gt[b * 4 + j] : 0.f;
+      n2 += r[j] * r[j];
+    }
+    const float inv = rsqrtf(fmaxf(n2, 1e-12f));
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j] = r[j] * inv;
+      d += g[j] * q[j];
+      q_out[b * 4 + j] = q[j];
+    }
+    part += 1.0f - fabsf(d);
+    if (draw != nullptr) {
+      const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      const float k = -sgn * weight / (float)B;
+      float dq[4], qdq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dq[j] = k * g[j]; qdq += q[j] * dq[j]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) draw[b * 4 + j] = n2 > 1e-12f ? inv * (dq[j] - q[j] * qdq) : inv * dq[j];
+    }
+  }
+  part = block_sum(part, sh);
+  if (threadIdx.x == 0 && loss_out != nullptr) loss_out[0] = weight * part / (float)B;
+}
+
+static inline int grid_for(long long n, int block, int max_blocks) {
+  long long g = (n + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace urso
+
+using namespace urso;
+
+extern "C" {
+
+int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, const float* mean3, void* e_out,
+                    int32_t B, int32_t H, int32_t W, void* stream) {
+  URSO_REQUIRE(img && e_out && (!subtract_mean || mean3), "null pointer");
+  URSO_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem input must have even H, W");
+  const long long total = (long long)B * (H / 2 + 3) * (W / 2) * 8;
+  const int grid = grid_for(total, 256, num_sms() * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (img_is_u8)
+    stem_stage_kernel<true><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W);
+  else
+    stem_stage_kernel<false><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  URSO_REQUIRE(x && y, "null pointer");
+  URSO_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool needs even H, W and C %% 8 == 0");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), static_cast<uint8_t*>(argmax), B, H, W, C);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
+                     int32_t C, void* stream) {
+  URSO_REQUIRE(x && argmax && dy && dx, "null pointer");
+  const long long total = (long long)B * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(argmax), static_cast<const __nv_bfloat16*>(dy),
+      static_cast<__nv_bfloat16*>(dx), B, H, W, C);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_dense_fwd(const float* x, const float* w, float* y, int32_t B, int32_t K, int32_t N, void* stream) {
+  URSO_REQUIRE(x && w && y, "null pointer");
+  dim3 grid((N + 127) / 128, (K + kDenseKC - 1) / kDenseKC, (B + 31) / 32);
+  dense_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, w, y, B, K, N);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_dense_bias_act(float* y, const float* bias, int32_t B, int32_t N, int32_t act, void* stream) {
+  URSO_REQUIRE(y && bias, "null pointer");
+  dense_bias_act_kernel<<<grid_for((long long)B * N, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, bias, B, N, act);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_dense_bwd(const float* x, const float* w, const float* y, float* dy, float* dx, float* dw, float* db,
+                   int32_t B, int32_t K, int32_t N, int32_t act, void* stream) {
+  URSO_REQUIRE(x && w && dy, "null pointer");
+  URSO_REQUIRE(act == 0 || y != nullptr, "relu backward needs the forward output");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dense_mask_bias_grad_kernel<<<(N + 127) / 128, 128, 0, s>>>(y, dy, db, B, N, act);
+  if (dw != nullptr) {
+    dim3 grid((N + 127) / 128, (K + 7) / 8);
+    dense_wgrad_kernel<<<grid, 128, 0, s>>>(x, dy, dw, B, K, N);
+  }
+  if (dx != nullptr) dense_dgrad_kernel<<<(K + 7) / 8, 256, 0, s>>>(dy, w, dx, B, K, N);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_softmax_xent(const float* z, const float* y, float* dz, float* loss_out, int32_t B, int32_t N, float weight,
+                      void* stream) {
+  URSO_REQUIRE(z && y && loss_out, "null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  URSO_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
+  softmax_xent_kernel<<<B, 256, 0, s>>>(z, y, dz, loss_out, B, N, weight);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_rel_loss(const float* pred, const float* gt, float* dpred, float* loss_out, int32_t B, int32_t N, float weight,
+                  void* stream) {
+  URSO_REQUIRE(pred && gt && loss_out, "null pointer");
+  rel_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, gt, dpred, loss_out, B * N, weight);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_quat_head(const float* raw, const float* gt, float* q_out, float* draw, float* loss_out, int32_t B,
+                   float weight, void* stream) {
+  URSO_REQUIRE(raw && q_out, "null pointer");
+  quat_head_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(raw, gt, q_out, draw, loss_out, B, weight);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// Parameter plumbing: BN folding, bf16 weight staging for the GEMM engines, conv parameter gradients from the
+// raw wgrad, and the fused regulariser + global-norm clip + SGD / AMSGrad update over the flat fp32 arenas.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace urso {
+
+__device__ __forceinline__ float warp_sum_p(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// scale = gamma * rsqrt(var + eps) ; shift = (bias - mean) * scale + beta.  NULL gamma => no BN (scale 1, shift bias).
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var,
+                               const float* bias, float eps, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float b = bias != nullptr ? bias[c] : 0.f;
+  if (gamma != nullptr) {
+    const float s = gamma[c] * rsqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = (b - mean[c]) * s + beta[c];
+  } else {
+    scale[c] = 1.f;
+    shift[c] = b;
+  }
+}
+
+// Forward operand: out[row, k] = w[idx[k] * CO + row] * scale[row]  (idx[k] = flat (tap, ci) of the HWIO kernel or -1).
+// Threads run along k (contiguous in out); the strided read of w is served by L2 (weights are small).
+__global__ void stage_weight_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                         __nv_bfloat16* __restrict__ out, const int* __restrict__ idx, int K, int CO,
+                                         int rows_out) {
+  const long long total = (long long)rows_out * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int row = (int)(i / K);
+    float v = 0.f;
+    const int src = idx[k];
+    if (src >= 0 && row < CO) v = w[(long long)src * CO + row] * (scale != nullptr ? scale[row] : 1.f);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// Dgrad operand: out[ci, slot*COp + co] = w[(tap[slot]*CI + ci)*CO + co] * scale[co]   (tap[slot] = -1 => zeros).
+__global__ void stage_weight_cols_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                         __nv_bfloat16* __restrict__ out, const int* __restrict__ tap, int n_slots,
+                                         int CI, int CO, int COp, int rows_out) {
+  const int K = n_slots * COp;
+  const long long total = (long long)rows_out * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int ci = (int)(i / K);
+    const int slot = k / COp, co = k % COp;
+    float v = 0.f;
+    const int t = tap[slot];
+    if (t >= 0 && co < CO && ci < CI) v = w[((long long)t * CI + ci) * CO + co] * (scale != nullptr ? scale[co] : 1.f);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// Per output channel co (one warp each):  S = sum_r W[r,co] * G[grow(r),co]
+//   dgamma = rstd * (S + (bias - mean) * colsum) ; dbeta = colsum ; dbias = scale * colsum
+// and for all r: dW[r,co] = scale[co] * G[grow(r), co].
+__global__ void __launch_bounds__(256) conv_param_grads_kernel(
+    const float* __restrict__ G, const int* __restrict__ g_row_map, const float* __restrict__ w,
+    const float* __restrict__ colsum, const float* __restrict__ scale, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ bias, float eps,
+    float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta, int R,
+    int CO) {
+  // block = 32 channels (x) x 8 row-lanes (y): coalesced along co
+  __shared__ float red[8][33];
+  const int co = blockIdx.x * 32 + threadIdx.x;
+  const float sc = (co < CO && scale != nullptr) ? scale[co] : 1.f;
+  float s = 0.f;
+  if (co < CO) {
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const int gr = g_row_map != nullptr ? g_row_map[r] : r;
+      const float g = G[(long long)gr * CO + co];
+      s += w[(long long)r * CO + co] * g;
+      dW[(long long)r * CO + co] = sc * g;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && co < CO) {
+    float S = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S += red[j][threadIdx.x];
+    const float cs = colsum != nullptr ? colsum[co] : 0.f;
+    if (dbias != nullptr) dbias[co] = sc * cs;
+    if (gamma != nullptr) {
+      const float rstd = rsqrtf(var[co] + eps);
+      const float b = bias != nullptr ? bias[co] : 0.f;
+      dgamma[co] = rstd * (S + (b - mean[co]) * cs);
+      dbeta[co] = cs;
+    }
+  }
+}
+
+// g <- (trainable ? g * grad_scale + coef * p : 0) ; sumsq += sum g^2.   chunk = 256 elements.
+__global__ void __launch_bounds__(256) add_reg_sumsq_kernel(float* __restrict__ grad, const float* __restrict__ param,
+                                                            const float* __restrict__ chunk_coef,
+                                                            const float* __restrict__ chunk_lr, float grad_scale,
+                                                            float* __restrict__ sumsq, long long n) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  const long long nchunks = (n + 255) / 256;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long i = ch * 256 + threadIdx.x;
+    if (i < n) {
+      float g = 0.f;
+      if (chunk_lr[ch] != 0.f) g = grad[i] * grad_scale + chunk_coef[ch] * param[i];
+      grad[i] = g;
+      acc += g * g;
+    }
+  }
+  acc = warp_sum_p(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = sh[threadIdx.x];
+    t += __shfl_xor_sync(0xffu, t, 4);
+    t += __shfl_xor_sync(0xffu, t, 2);
+    t += __shfl_xor_sync(0xffu, t, 1);
+    if (threadIdx.x == 0) atomicAdd(sumsq, t);
+  }
+}
+
+// hyper: [0]=lr  [1]=momentum|beta1  [2]=beta2  [3]=eps  [4]=clipnorm   (device memory: CUDA-graph replays see updates)
+__device__ __forceinline__ float clip_factor(const float* sumsq, const float* hyper) {
+  const float norm = sqrtf(sumsq[0]);
+  const float c = hyper[4];
+  return (c > 0.f && norm >= c) ? c / norm : 1.f;
+}
+
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ param, float* __restrict__ vel,
+                                                       const float* __restrict__ grad,
+                                                       const float* __restrict__ chunk_lr,
+                                                       const float* __restrict__ sumsq, const float* __restrict__ hyper,
+                                                       long long n) {
+  const float cf = clip_factor(sumsq, hyper);
+  const float lr = hyper[0], mom = hyper[1];
+  const long long nchunks = (n + 255) / 256;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (chunk_lr[ch] == 0.f) continue;
+    const long long i = ch * 256 + threadIdx.x;
+    if (i < n) {
+      const float v = mom * vel[i] - lr * (grad[i] * cf);
+      vel[i] = v;
+      param[i] += v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) amsgrad_step_kernel(float* __restrict__ param, float* __restrict__ m,
+                                                           float* __restrict__ v, float* __restrict__ vhat,
+                                                           const float* __restrict__ grad,
+                                                           const float* __restrict__ chunk_lr,
+                                                           const float* __restrict__ sumsq,
+                                                           const float* __restrict__ hyper, long long n) {
+  const float cf = clip_factor(sumsq, hyper);
+  const float lr_t = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+  const long long nchunks = (n + 255) / 256;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (chunk_lr[ch] == 0.f) continue;
+    const long long i = ch * 256 + threadIdx.x;
+    if (i < n) {
+      const float g = grad[i] * cf;
+      const float mi = b1 * m[i] + (1.f - b1) * g;
+      const float vi = b2 * v[i] + (1.f - b2) * g * g;
+      const float vh = fmaxf(vhat[i], vi);
+      m[i] = mi;
+      v[i] = vi;
+      vhat[i] = vh;
+      param[i] -= lr_t * mi / (sqrtf(vh) + eps);
+    }
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+__global__ void pad_cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows,
+                                     int C, int Cpad) {
+  const long long total = rows * Cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long long r = i / Cpad;
+    dst[i] = __float2bfloat16(c < C ? src[r * C + c] : 0.f);
+  }
+}
+
+// out[c] += sum_rows x[r, c] (bf16 [rows, C]).  Block = 32 channel-pairs x 8 row lanes, grid-strided over row slabs.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                          long long rows, int C, int rows_per_block) {
+  __shared__ float red[8][65];
+  const int c2 = blockIdx.x * 32 + threadIdx.x;  // channel pair index
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f;
+  if (2 * c2 < C) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + r * C + 2 * c2);
+      a0 += __low2float(v);
+      a1 += __high2float(v);
+    }
+  }
+  red[threadIdx.y][2 * threadIdx.x] = a0;
+  red[threadIdx.y][2 * threadIdx.x + 1] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && 2 * c2 < C) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0 += red[j][2 * threadIdx.x];
+      s1 += red[j][2 * threadIdx.x + 1];
+    }
+    atomicAdd(out + 2 * c2, s0);
+    atomicAdd(out + 2 * c2 + 1, s1);
+  }
+}
+
+static inline int grid_for_p(long long n, int block, int max_blocks) {
+  long long g = (n + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace urso
+
+using namespace urso;
+
+extern "C" {
+
+int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
+                 float eps, float* scale, float* shift, int32_t C, void* stream) {
+  URSO_REQUIRE(scale && shift, "null pointer");
+  URSO_REQUIRE(gamma == nullptr || (beta && mean && var), "BN needs gamma, beta, mean and var");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, mean, var, bias, eps,
+                                                                                scale, shift, C);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
+                           int32_t rows_out, void* stream) {
+  URSO_REQUIRE(w && out && idx_dev, "null pointer");
+  stage_weight_rows_kernel<<<grid_for_p((long long)rows_out * K, 256, num_sms() * 8), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(w, scale, static_cast<__nv_bfloat16*>(out), idx_dev,
+                                                                  K, CO, rows_out);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_stage_weight_cols(const float* w, const float* scale, void* out, const int32_t* tap_dev, int32_t n_slots,
+                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, void* stream) {
+  URSO_REQUIRE(w && out && tap_dev, "null pointer");
+  stage_weight_cols_kernel<<<grid_for_p((long long)rows_out * n_slots * COp, 256, num_sms() * 8), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(w, scale, static_cast<__nv_bfloat16*>(out), tap_dev,
+                                                                  n_slots, CI, CO, COp, rows_out);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const float* w, const float* colsum,
+                          const float* scale, const float* gamma, const float* mean, const float* var,
+                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta, int32_t R,
+                          int32_t CO, void* stream) {
+  URSO_REQUIRE(G && w && dW, "null pointer");
+  URSO_REQUIRE(gamma == nullptr || (mean && var && dgamma && dbeta && colsum), "BN gradients need mean/var/colsum");
+  URSO_REQUIRE(dbias == nullptr || colsum != nullptr, "bias gradient needs colsum");
+  dim3 block(32, 8);
+  conv_param_grads_kernel<<<(CO + 31) / 32, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      G, g_row_map_dev, w, colsum, scale, gamma, mean, var, bias, eps, dW, dbias, dgamma, dbeta, R, CO);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef, const float* chunk_lr,
+                       float grad_scale, float* sumsq_out, int64_t n, void* stream) {
+  URSO_REQUIRE(grad && param && chunk_coef && chunk_lr && sumsq_out, "null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  URSO_CUDA_OK(cudaMemsetAsync(sumsq_out, 0, sizeof(float), s));
+  add_reg_sumsq_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, s>>>(grad, param, chunk_coef, chunk_lr,
+                                                                                    grad_scale, sumsq_out, n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_sgd_step(float* param, float* vel, const float* grad, const float* chunk_lr, const float* sumsq,
+                  const float* hyper_dev, int64_t n, void* stream) {
+  URSO_REQUIRE(param && vel && grad && chunk_lr && sumsq && hyper_dev, "null pointer");
+  sgd_step_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, vel, grad, chunk_lr, sumsq, hyper_dev, n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float* grad, const float* chunk_lr,
+                      const float* sumsq, const float* hyper_dev, int64_t n, void* stream) {
+  URSO_REQUIRE(param && m && v && vhat && grad && chunk_lr && sumsq && hyper_dev, "null pointer");
+  amsgrad_step_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, m, v, vhat, grad, chunk_lr, sumsq, hyper_dev, n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  URSO_REQUIRE(x && y, "null pointer");
+  cast_f32_bf16_kernel<<<grid_for_p(n, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+  URSO_REQUIRE(x && y, "null pointer");
+  cast_bf16_f32_kernel<<<grid_for_p(n, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_pad_cast_rows(const float* src, void* dst, int64_t rows, int32_t C, int32_t Cpad, void* stream) {
+  URSO_REQUIRE(src && dst && Cpad >= C, "bad arguments");
+  pad_cast_rows_kernel<<<grid_for_p(rows * Cpad, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), rows, C, Cpad);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, void* stream) {
+  URSO_REQUIRE(x && out && C % 2 == 0, "bad arguments");
+  int slabs = (int)((rows + 511) / 512);
+  int max_slabs = num_sms() * 4;
+  if (max_slabs < 1) max_slabs = 592;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  const int rpb = (int)((rows + slabs - 1) / slabs);
+  dim3 grid((C / 2 + 31) / 32, slabs), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), out,
+                                                                            rows, C, rpb);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

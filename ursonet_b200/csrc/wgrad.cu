@@ -1,0 +1,295 @@
+// Engine W: weight-gradient GEMM on tcgen05 tensor cores.
+//
+//   G[t][p, q] += sum over pixels  P_t[pixel + shift_t, p] * Q[pixel, q]
+//
+// The reduction (MMA K) dimension is the PIXEL axis, so both operands are "MN-major": a TMA box of
+// {64 channels, TW, TH, 1} lands in shared memory as 64 pixel rows of 128 bytes -- exactly the canonical
+// SWIZZLE_128B MN-major UMMA atom (8 pixel rows x 64 channels per 1 KB group, SBO = 1 KB between groups,
+// LBO = distance between 64-channel atoms).  No transposition of activations or gradients is ever materialised.
+//
+// One CTA owns a 128-channel P tile x BLOCK_Q-channel Q tile for up to T filter taps (T*BLOCK_Q <= 512 TMEM columns,
+// all taps reuse the single Q tile per K step) over a contiguous range of pixel blocks (split-K); results are
+// reduced into the fp32 gradient with atomics.
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace urso {
+
+struct WSegDev {
+  int16_t map_id, dh, dw, pad;
+};
+
+struct WgradParams {
+  CUtensorMap p_maps[URSO_MAX_AMAPS];
+  CUtensorMap q_map;
+  WSegDev seg[URSO_MAX_SEGS];
+  int n_seg, taps_per_cta, n_seg_groups;
+  int PC, QC;
+  int p_tiles, q_tiles;
+  int tiles_w, tiles_h, TW, TH;
+  int n_pix_blocks, split_k;
+  int stages, stage_bytes;
+  int tmem_cols;
+  float* g;
+  long long g_seg_stride, g_sp, g_sq;
+};
+
+constexpr int kAtomBytes = 64 * 64 * 2;  // 64 pixels x 64 channels bf16 = 8 KB
+
+template <int BLOCK_Q>
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int QA = BLOCK_Q / 64;  // 64-channel atoms in the Q tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item decode: blockIdx.x -> (split, q_tile, p_tile, seg_group); split fastest so that CTAs that run
+  // concurrently stream different pixels of the same operand columns.
+  int wi = blockIdx.x;
+  const int split = wi % p.split_k;  wi /= p.split_k;
+  const int q_tile = wi % p.q_tiles; wi /= p.q_tiles;
+  const int p_tile = wi % p.p_tiles; wi /= p.p_tiles;
+  const int seg_group = wi;
+  const int seg0 = seg_group * p.taps_per_cta;
+  const int T = min(p.taps_per_cta, p.n_seg - seg0);
+  const int kb_begin = (int)((long long)p.n_pix_blocks * split / p.split_k);
+  const int kb_end = (int)((long long)p.n_pix_blocks * (split + 1) / p.split_k);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.p_maps[i]);
+    tma_prefetch_desc(&p.q_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (QA + 2 * T) * kAtomBytes;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int twi = kb % p.tiles_w;
+        const int rest = kb / p.tiles_w;
+        const int thi = rest % p.tiles_h;
+        const int img = rest / p.tiles_h;
+        const int h0 = thi * p.TH, w0 = twi * p.TW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], bytes);
+        uint8_t* base = smem + stage * p.stage_bytes;
+#pragma unroll 1
+        for (int a = 0; a < QA; ++a)
+          tma_load_4d(base + a * kAtomBytes, &p.q_map, &full_bar[stage], q_tile * BLOCK_Q + a * 64, w0, h0, img);
+        uint8_t* pbase = base + QA * kAtomBytes;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          const WSegDev sg = p.seg[seg0 + t];
+          tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128, w0 + sg.dw,
+                      h0 + sg.dh, img);
+          tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128 + 64,
+                      w0 + sg.dw, h0 + sg.dh, img);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_Q, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t p_addr = q_addr + QA * kAtomBytes;
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x UMMA_K(16) = 4 x two 8-pixel groups (2 KB)
+            uint64_t ad = umma_desc_sw128(p_addr + (2 * t) * kAtomBytes + k * 2048, kAtomBytes, 1024);
+            uint64_t bd = umma_desc_sw128(q_addr + k * 2048, kAtomBytes, 1024);
+            umma_bf16(tmem_base + t * BLOCK_Q, ad, bd, idesc, (kb > kb_begin) || (k > 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int pch = p_tile * 128 + row;
+    if (kb_end > kb_begin) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      for (int t = 0; t < T; ++t) {
+        float* grow = p.g + (long long)(seg0 + t) * p.g_seg_stride + (long long)pch * p.g_sp;
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_Q / 32; ++j) {
+          const int col0 = q_tile * BLOCK_Q + j * 32;
+          if (col0 >= p.QC) break;
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + t * BLOCK_Q + j * 32, acc);
+          tmem_ld_wait();
+          if (pch < p.PC) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i < p.QC) atomicAdd(grow + (long long)(col0 + i) * p.g_sq, __uint_as_float(acc[i]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace urso
+
+struct urso_wgrad {
+  urso::WgradParams params;
+  int block_q, grid, smem_bytes;
+};
+
+template <int BLOCK_Q>
+static int launch_wgrad(const urso_wgrad* h, cudaStream_t stream) {
+  static int attr_smem = 0;
+  if (attr_smem < h->smem_bytes) {
+    URSO_CUDA_OK(cudaFuncSetAttribute(urso::wgrad_kernel<BLOCK_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      220 * 1024));
+    attr_smem = 220 * 1024;
+  }
+  urso::wgrad_kernel<BLOCK_Q><<<h->grid, 256, h->smem_bytes, stream>>>(h->params);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
+  using namespace urso;
+  URSO_REQUIRE(d != nullptr && out != nullptr, "null argument");
+  URSO_REQUIRE(d->n_p >= 1 && d->n_p <= URSO_MAX_AMAPS, "n_p=%d out of range", d->n_p);
+  URSO_REQUIRE(d->n_seg >= 1 && d->n_seg <= URSO_MAX_SEGS, "n_seg=%d out of range", d->n_seg);
+  URSO_REQUIRE(d->TW * d->TH == 64, "TW*TH must be 64 (got %dx%d)", d->TW, d->TH);
+  URSO_REQUIRE(d->g != nullptr, "null gradient output");
+  auto* h = new urso_wgrad();
+  WgradParams& p = h->params;
+  memset(&p, 0, sizeof(p));
+  int bq = d->block_q;
+  if (bq == 0) bq = d->QC >= 256 ? 256 : (d->QC > 64 ? 128 : 64);
+  if (bq != 64 && bq != 128 && bq != 256) {
+    set_error("block_q=%d unsupported", bq);
+    delete h;
+    return 2;
+  }
+  h->block_q = bq;
+  for (int i = 0; i < URSO_MAX_AMAPS; ++i) {
+    if (int rc = make_view_map(&p.p_maps[i], d->p[i < d->n_p ? i : 0], d->TW, d->TH)) {
+      delete h;
+      return rc;
+    }
+  }
+  if (int rc = make_view_map(&p.q_map, d->q, d->TW, d->TH)) {
+    delete h;
+    return rc;
+  }
+  for (int s = 0; s < d->n_seg; ++s) {
+    if (d->seg[s].map_id < 0 || d->seg[s].map_id >= d->n_p) {
+      set_error("segment %d: bad map id %d", s, d->seg[s].map_id);
+      delete h;
+      return 2;
+    }
+    p.seg[s] = WSegDev{(int16_t)d->seg[s].map_id, (int16_t)d->seg[s].dh, (int16_t)d->seg[s].dw, 0};
+  }
+  p.n_seg = d->n_seg;
+  int tmax = 512 / bq;
+  // smem: each stage holds the Q tile + 2 atoms per tap; keep at least 2 stages
+  const int qa = bq / 64;
+  while (tmax > 1 && (qa + 2 * tmax) * kAtomBytes * 2 > 200 * 1024) --tmax;
+  p.taps_per_cta = d->n_seg < tmax ? d->n_seg : tmax;
+  p.n_seg_groups = (d->n_seg + p.taps_per_cta - 1) / p.taps_per_cta;
+  p.PC = d->PC;
+  p.QC = d->QC;
+  p.p_tiles = (d->PC + 127) / 128;
+  p.q_tiles = (d->QC + bq - 1) / bq;
+  p.TW = d->TW;
+  p.TH = d->TH;
+  p.tiles_w = (d->OW + d->TW - 1) / d->TW;
+  p.tiles_h = (d->OH + d->TH - 1) / d->TH;
+  long long nblk = (long long)p.tiles_w * p.tiles_h * d->NB;
+  if (nblk <= 0 || nblk > 0x7fffffffLL) {
+    set_error("bad pixel block count %lld", nblk);
+    delete h;
+    return 2;
+  }
+  p.n_pix_blocks = (int)nblk;
+  p.stage_bytes = (qa + 2 * p.taps_per_cta) * kAtomBytes;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  int cols = p.taps_per_cta * bq;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < cols) p.tmem_cols *= 2;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  int items = p.n_seg_groups * p.p_tiles * p.q_tiles;
+  int split = d->split_k;
+  if (split <= 0) {
+    split = (2 * sms + items - 1) / items;  // aim for ~2 waves
+    int max_split = p.n_pix_blocks / 8;     // at least 8 K-steps per CTA
+    if (max_split < 1) max_split = 1;
+    if (split > max_split) split = max_split;
+  }
+  if (split > p.n_pix_blocks) split = p.n_pix_blocks;
+  if (split < 1) split = 1;
+  p.split_k = split;
+  p.g = d->g;
+  p.g_seg_stride = d->g_seg_stride;
+  p.g_sp = d->g_sp;
+  p.g_sq = d->g_sq;
+  h->grid = items * split;
+  h->smem_bytes = p.stages * p.stage_bytes + 256 + 1024;
+  *out = h;
+  return 0;
+}
+
+extern "C" int urso_wgrad_launch(urso_wgrad_t* h, void* stream) {
+  URSO_REQUIRE(h != nullptr, "null handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (h->block_q) {
+    case 64: return launch_wgrad<64>(h, s);
+    case 128: return launch_wgrad<128>(h, s);
+    case 256: return launch_wgrad<256>(h, s);
+  }
+  urso::set_error("unsupported BLOCK_Q %d", h->block_q);
+  return 2;
+}
+
+extern "C" void urso_wgrad_destroy(urso_wgrad_t* h) { delete h; }

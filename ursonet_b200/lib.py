@@ -1,0 +1,209 @@
+"""ctypes binding of liburso_b200.so (the C-ABI declared in include/urso_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+The library is built in-tree by `make -C ursonet_b200/csrc` (see __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liburso_b200.so")
+
+MAX_AMAPS = 8
+MAX_SEGS = 32
+
+
+class View4(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("N", C.c_int32),
+                ("stride_w", C.c_int64), ("stride_h", C.c_int64), ("stride_n", C.c_int64)]
+
+
+class Seg(C.Structure):
+    _fields_ = [("map_id", C.c_int32), ("dh", C.c_int32), ("dw", C.c_int32), ("c_chunks", C.c_int32)]
+
+
+class Pix(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sn", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64)]
+
+
+class ConvGemmDesc(C.Structure):
+    _fields_ = [("a", View4 * MAX_AMAPS), ("n_a", C.c_int32), ("b", C.c_void_p), ("b_rows", C.c_int32),
+                ("b_k", C.c_int32), ("seg", Seg * MAX_SEGS), ("n_seg", C.c_int32),
+                ("OW", C.c_int32), ("OH", C.c_int32), ("NB", C.c_int32), ("TW", C.c_int32), ("TH", C.c_int32),
+                ("out", Pix), ("out_fp32", C.c_int32), ("shift", C.c_void_p), ("addend", Pix), ("mask", Pix),
+                ("relu", C.c_int32), ("colsum", C.c_void_p), ("block_n", C.c_int32)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("p", View4 * MAX_AMAPS), ("n_p", C.c_int32), ("q", View4), ("seg", Seg * MAX_SEGS),
+                ("n_seg", C.c_int32), ("PC", C.c_int32), ("QC", C.c_int32),
+                ("OW", C.c_int32), ("OH", C.c_int32), ("NB", C.c_int32), ("TW", C.c_int32), ("TH", C.c_int32),
+                ("g", C.c_void_p), ("g_seg_stride", C.c_int64), ("g_sp", C.c_int64), ("g_sq", C.c_int64),
+                ("split_k", C.c_int32), ("block_q", C.c_int32)]
+
+
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+# name -> argtypes (all return int unless listed in _RESTYPES); kept in sync with include/urso_b200.h
+SIGNATURES = {
+    "urso_version": [],
+    "urso_last_error": [],
+    "urso_num_sms": [],
+    "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
+    "urso_convgemm_launch": [_vp, _vp],
+    "urso_convgemm_destroy": [_vp],
+    "urso_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(_vp)],
+    "urso_wgrad_launch": [_vp, _vp],
+    "urso_wgrad_destroy": [_vp],
+    "urso_stem_stage": [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp],
+    "urso_maxpool_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "urso_maxpool_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "urso_dense_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "urso_dense_bias_act": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "urso_dense_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "urso_softmax_xent": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
+    "urso_rel_loss": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
+    "urso_quat_head": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
+    "urso_bn_fold": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
+    "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 4 + [_i32, _i32, _vp],
+    "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
+    "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "urso_amsgrad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "urso_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "urso_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
+    "urso_pad_cast_rows": [_vp, _vp, _i64, _i32, _i32, _vp],
+    "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
+}
+_RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None}
+
+_lib = None
+
+
+class UrsoError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UrsoError(f"{LIB_PATH} not found: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                        "(or __graft_entry__.build()); this package has no CPU / eager fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library diverge
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().urso_last_error()
+        raise UrsoError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on error."""
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def view4(t):
+    """urso_view4 of a bf16 NHWC torch tensor/view [N,H,W,C] (channel stride must be 1)."""
+    import torch
+    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    n, h, w, c = t.shape
+    return View4(t.data_ptr(), c, w, h, n, t.stride(2), t.stride(1), t.stride(0))
+
+
+def pix(t):
+    """urso_pix of an NHWC tensor/view (any dtype)."""
+    if t is None:
+        return Pix(None, 0, 0, 0)
+    assert t.dim() == 4 and t.stride(3) == 1
+    return Pix(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+
+class ConvGemm:
+    """Owning wrapper of a urso_convgemm_t plan (tensor maps are encoded once; launch is graph-capturable)."""
+
+    def __init__(self, a_views, b, segs, out, OW, OH, NB, TW, TH, shift=None, addend=None, mask=None, relu=False,
+                 colsum=None, block_n=0):
+        import torch
+        d = ConvGemmDesc()
+        assert 1 <= len(a_views) <= MAX_AMAPS and 1 <= len(segs) <= MAX_SEGS
+        for i, v in enumerate(a_views):
+            d.a[i] = view4(v)
+        d.n_a = len(a_views)
+        assert b.dtype == torch.bfloat16 and b.dim() == 2 and b.is_contiguous()
+        d.b, d.b_rows, d.b_k = b.data_ptr(), b.shape[0], b.shape[1]
+        for i, (m, dh, dw, ch) in enumerate(segs):
+            d.seg[i] = Seg(m, dh, dw, ch)
+        d.n_seg = len(segs)
+        d.OW, d.OH, d.NB, d.TW, d.TH = OW, OH, NB, TW, TH
+        d.out = pix(out)
+        d.out_fp32 = 1 if out.dtype == torch.float32 else 0
+        d.shift = ptr(shift)
+        d.addend, d.mask = pix(addend), pix(mask)
+        d.relu = int(relu)
+        d.colsum = ptr(colsum)
+        d.block_n = block_n
+        self._keep = (a_views, b, out, shift, addend, mask, colsum)   # keep tensors alive
+        h = _vp()
+        check(load().urso_convgemm_create(C.byref(d), C.byref(h)), "urso_convgemm_create")
+        self._h = h
+
+    def launch(self):
+        check(load().urso_convgemm_launch(self._h, stream_ptr()), "urso_convgemm_launch")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.urso_convgemm_destroy(self._h)
+            self._h = None
+
+
+class Wgrad:
+    """Owning wrapper of a urso_wgrad_t plan."""
+
+    def __init__(self, p_views, q_view, segs, PC, QC, OW, OH, NB, TW, TH, g, g_seg_stride, g_sp, g_sq, split_k=0,
+                 block_q=0):
+        import torch
+        d = WgradDesc()
+        for i, v in enumerate(p_views):
+            d.p[i] = view4(v)
+        d.n_p = len(p_views)
+        d.q = view4(q_view)
+        for i, (m, dh, dw) in enumerate(segs):
+            d.seg[i] = Seg(m, dh, dw, 0)
+        d.n_seg = len(segs)
+        d.PC, d.QC, d.OW, d.OH, d.NB, d.TW, d.TH = PC, QC, OW, OH, NB, TW, TH
+        assert g.dtype == torch.float32
+        d.g, d.g_seg_stride, d.g_sp, d.g_sq = g.data_ptr(), g_seg_stride, g_sp, g_sq
+        d.split_k, d.block_q = split_k, block_q
+        self._keep = (p_views, q_view, g)
+        h = _vp()
+        check(load().urso_wgrad_create(C.byref(d), C.byref(h)), "urso_wgrad_create")
+        self._h = h
+
+    def launch(self):
+        check(load().urso_wgrad_launch(self._h, stream_ptr()), "urso_wgrad_launch")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.urso_wgrad_destroy(self._h)
+            self._h = None
