@@ -23,6 +23,9 @@ extern "C" {
 int urso_version(void);
 const char* urso_last_error(void);
 int urso_num_sms(void);
+/* struct sizes, so that FFI bindings can verify their layout against this header */
+int urso_sizeof_convgemm_desc(void);
+int urso_sizeof_wgrad_desc(void);
 
 /* A 4-D NHWC bf16 view (possibly strided): element (n,h,w,c) at base + n*stride_n + h*stride_h + w*stride_w + c.
  * C must be a multiple of 64 for MMA operands; strides are in ELEMENTS and must be multiples of 8. */
@@ -140,11 +143,12 @@ int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const
  * frozen-BN scale folded in:
  *   rows (fprop):  out[row, k] = w[idx[k], row] * scale[row]                 row < rows_out (zero rows beyond CO)
  *   cols (dgrad):  out[ci, slot*COp + co] = w[tap[slot]*CI + ci, co] * scale[co]
- * idx / tap are device int32 arrays; -1 selects zero padding. */
+ * idx / tap are device int32 arrays; -1 selects zero padding.  ld_out = row pitch of `out` in elements, so that
+ * several convolutions can be staged side by side into one K-concatenated operand (fused fan-in dgrad). */
 int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
-                           int32_t rows_out, void* stream);
+                           int32_t rows_out, int64_t ld_out, void* stream);
 int urso_stage_weight_cols(const float* w, const float* scale, void* out, const int32_t* tap_dev, int32_t n_slots,
-                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, void* stream);
+                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, int64_t ld_out, void* stream);
 /* From the raw wgrad G[R'][CO] (fp32; row r of the HWIO kernel lives at G row g_row_map[r], identity if NULL) and
  * colsum[c] = sum_pixels du: dW = scale*G, dbias = scale*colsum, dbeta = colsum,
  * dgamma = rstd*(sum_r W[r,c]*G[r,c] + (bias-mean)*colsum).  gamma == NULL: no BN; dbias == NULL: no bias. */

@@ -82,4 +82,6 @@ extern "C" {
 int urso_version(void) { return 100; }
 const char* urso_last_error(void) { return urso::g_err.c_str(); }
 int urso_num_sms(void) { return urso::num_sms(); }
+int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
+int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }
 }

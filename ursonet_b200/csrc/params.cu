@@ -32,7 +32,7 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 // Threads run along k (contiguous in out); the strided read of w is served by L2 (weights are small).
 __global__ void stage_weight_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                          __nv_bfloat16* __restrict__ out, const int* __restrict__ idx, int K, int CO,
-                                         int rows_out) {
+                                         int rows_out, long long ld_out) {
   const long long total = (long long)rows_out * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
@@ -40,14 +40,14 @@ __global__ void stage_weight_rows_kernel(const float* __restrict__ w, const floa
     float v = 0.f;
     const int src = idx[k];
     if (src >= 0 && row < CO) v = w[(long long)src * CO + row] * (scale != nullptr ? scale[row] : 1.f);
-    out[i] = __float2bfloat16(v);
+    out[(long long)row * ld_out + k] = __float2bfloat16(v);
   }
 }
 
 // Dgrad operand: out[ci, slot*COp + co] = w[(tap[slot]*CI + ci)*CO + co] * scale[co]   (tap[slot] = -1 => zeros).
 __global__ void stage_weight_cols_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                          __nv_bfloat16* __restrict__ out, const int* __restrict__ tap, int n_slots,
-                                         int CI, int CO, int COp, int rows_out) {
+                                         int CI, int CO, int COp, int rows_out, long long ld_out) {
   const int K = n_slots * COp;
   const long long total = (long long)rows_out * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -57,7 +57,7 @@ __global__ void stage_weight_cols_kernel(const float* __restrict__ w, const floa
     float v = 0.f;
     const int t = tap[slot];
     if (t >= 0 && co < CO && ci < CI) v = w[((long long)t * CI + ci) * CO + co] * (scale != nullptr ? scale[co] : 1.f);
-    out[i] = __float2bfloat16(v);
+    out[(long long)ci * ld_out + k] = __float2bfloat16(v);
   }
 }
 
@@ -252,21 +252,23 @@ int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const
 }
 
 int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
-                           int32_t rows_out, void* stream) {
+                           int32_t rows_out, int64_t ld_out, void* stream) {
   URSO_REQUIRE(w && out && idx_dev, "null pointer");
+  URSO_REQUIRE(ld_out >= K, "ld_out < K");
   stage_weight_rows_kernel<<<grid_for_p((long long)rows_out * K, 256, num_sms() * 8), 256, 0,
                              static_cast<cudaStream_t>(stream)>>>(w, scale, static_cast<__nv_bfloat16*>(out), idx_dev,
-                                                                  K, CO, rows_out);
+                                                                  K, CO, rows_out, ld_out);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int urso_stage_weight_cols(const float* w, const float* scale, void* out, const int32_t* tap_dev, int32_t n_slots,
-                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, void* stream) {
+                           int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, int64_t ld_out, void* stream) {
   URSO_REQUIRE(w && out && tap_dev, "null pointer");
+  URSO_REQUIRE(ld_out >= (int64_t)n_slots * COp, "ld_out < K");
   stage_weight_cols_kernel<<<grid_for_p((long long)rows_out * n_slots * COp, 256, num_sms() * 8), 256, 0,
                              static_cast<cudaStream_t>(stream)>>>(w, scale, static_cast<__nv_bfloat16*>(out), tap_dev,
-                                                                  n_slots, CI, CO, COp, rows_out);
+                                                                  n_slots, CI, CO, COp, rows_out, ld_out);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -49,6 +49,8 @@ SIGNATURES = {
     "urso_version": [],
     "urso_last_error": [],
     "urso_num_sms": [],
+    "urso_sizeof_convgemm_desc": [],
+    "urso_sizeof_wgrad_desc": [],
     "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
     "urso_convgemm_launch": [_vp, _vp],
     "urso_convgemm_destroy": [_vp],
@@ -65,8 +67,8 @@ SIGNATURES = {
     "urso_rel_loss": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
     "urso_quat_head": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
     "urso_bn_fold": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
-    "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
-    "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp],
+    "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
     "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 4 + [_i32, _i32, _vp],
     "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
@@ -98,6 +100,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the header and the library diverge
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.urso_sizeof_convgemm_desc() != C.sizeof(ConvGemmDesc) or lib.urso_sizeof_wgrad_desc() != C.sizeof(WgradDesc):
+        raise UrsoError("ctypes struct layout does not match include/urso_b200.h (rebuild the library)")
     _lib = lib
     return lib
 
