@@ -171,8 +171,10 @@ int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float
 /* ---- small elementwise helpers */
 int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
-/* dst[b, 0:Cpad] (bf16) = src[b, 0:C] (fp32), zero padded: stages head gradients as an Engine-F operand. */
-int urso_pad_cast_rows(const float* src, void* dst, int64_t rows, int32_t C, int32_t Cpad, void* stream);
+/* dst[r, 0:Cpad] (bf16) = src[r, 0:C] + src2[r, 0:C] (fp32; src2 may be NULL), zero padded to Cpad channels: sums the
+ * two heads' input gradients and stages them as an Engine-F / Engine-W operand. */
+int urso_pad_cast_rows(const float* src, const float* src2, void* dst, int64_t rows, int32_t C, int32_t Cpad,
+                       void* stream);
 int urso_colsum_bf16(const void* x, float* out, int64_t rows, int32_t C, void* stream);
 
 #ifdef __cplusplus

@@ -240,5 +240,8 @@ def test_small_helpers():
     assert torch.allclose(cs, xb.float().sum(0), rtol=1e-4, atol=1e-3)
     src = torch.randn(50, 32, device=DEV)
     dst = torch.empty(50, 64, dtype=torch.bfloat16, device=DEV)
-    lib.call("urso_pad_cast_rows", src.data_ptr(), dst.data_ptr(), 50, 32, 64, s)
+    lib.call("urso_pad_cast_rows", src.data_ptr(), None, dst.data_ptr(), 50, 32, 64, s)
     assert torch.equal(dst[:, :32], src.to(torch.bfloat16)) and (dst[:, 32:] == 0).all()
+    src2 = torch.randn(50, 32, device=DEV)
+    lib.call("urso_pad_cast_rows", src.data_ptr(), src2.data_ptr(), dst.data_ptr(), 50, 32, 64, s)
+    assert torch.equal(dst[:, :32], (src + src2).to(torch.bfloat16)) and (dst[:, 32:] == 0).all()

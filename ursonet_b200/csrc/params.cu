@@ -188,13 +188,15 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
 }
-__global__ void pad_cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows,
-                                     int C, int Cpad) {
+__global__ void pad_cast_rows_kernel(const float* __restrict__ src, const float* __restrict__ src2,
+                                     __nv_bfloat16* __restrict__ dst, long long rows, int C, int Cpad) {
   const long long total = rows * Cpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cpad);
     const long long r = i / Cpad;
-    dst[i] = __float2bfloat16(c < C ? src[r * C + c] : 0.f);
+    float v = 0.f;
+    if (c < C) v = src[r * C + c] + (src2 != nullptr ? src2[r * C + c] : 0.f);
+    dst[i] = __float2bfloat16(v);
   }
 }
 
@@ -332,10 +334,11 @@ int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
   return 0;
 }
 
-int urso_pad_cast_rows(const float* src, void* dst, int64_t rows, int32_t C, int32_t Cpad, void* stream) {
+int urso_pad_cast_rows(const float* src, const float* src2, void* dst, int64_t rows, int32_t C, int32_t Cpad,
+                       void* stream) {
   URSO_REQUIRE(src && dst && Cpad >= C, "bad arguments");
   pad_cast_rows_kernel<<<grid_for_p(rows * Cpad, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), rows, C, Cpad);
+      src, src2, static_cast<__nv_bfloat16*>(dst), rows, C, Cpad);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,619 @@
+"""Execution engine: static plan of C-ABI launches for the UrsoNet forward / backward / update on one B200.
+
+Replaces the reference's L1/L0 (Keras `fit_generator`/`predict` -> TF Session.run, net.py:1152,1241-1251): the graph
+(`graph.build_graph`) is lowered ONCE into flat launch lists over pre-allocated device buffers; every launch goes
+through liburso_b200.so (no autograd graph, no torch ops on the data path except memset).  The lists are then
+captured into CUDA graphs, so a train step is two graph replays around one NCCL all-reduce of the flat gradient arena.
+
+Memory layout (HBM):
+  params / grads / optimizer state : flat fp32 arenas, every tensor 256-element aligned, Keras layouts (HWIO, [in,out])
+  activations                      : bf16 NHWC, one buffer per conv output (kept for backward), fp32 for the heads
+  gradients of activations (du)    : bf16 NHWC, masked by the consumer's ReLU at production time
+  staged GEMM operands             : bf16 K-major weight matrices with the frozen-BN scale folded in (rebuilt per step)
+"""
+import math
+import re
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import convplan as P
+from . import lib
+from .graph import ConvSpec, Graph, build_graph, weight_entries
+
+BN_EPS = 1e-3      # keras BatchNormalization default (net.py:60)
+ALIGN = 256        # arena alignment in elements (== optimizer chunk)
+
+
+def _align(n):
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+class ParamStore:
+    """Flat fp32 arenas for trainable weights (+ grads) and BN moving statistics, addressed by Keras weight names."""
+
+    def __init__(self, graph: Graph, device, weight_decay: float):
+        self.entries = weight_entries(graph)
+        self.device = device
+        off_t = off_s = 0
+        self.index: Dict[str, tuple] = {}
+        for name, shape, trainable, reg in self.entries:
+            n = int(np.prod(shape))
+            if trainable:
+                self.index[name] = ("t", off_t, shape, reg)
+                off_t += _align(n)
+            else:
+                self.index[name] = ("s", off_s, shape, False)
+                off_s += _align(n)
+        self.n_train, self.n_stats = off_t, max(off_s, ALIGN)
+        self.flat = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+        self.stats = torch.zeros(self.n_stats, dtype=torch.float32, device=device)
+        nchunks = self.n_train // ALIGN
+        coef = torch.zeros(nchunks, dtype=torch.float32)
+        self.chunk_layer: List[str] = [""] * nchunks
+        for name, (kind, off, shape, reg) in self.index.items():
+            if kind != "t":
+                continue
+            n = int(np.prod(shape))
+            c0, c1 = off // ALIGN, (off + _align(n)) // ALIGN
+            if reg:   # d/dw [wd * sum(w^2) / size(w)] = 2 wd w / size(w)   (net.py:1008-1012)
+                coef[c0:c1] = 2.0 * weight_decay / n
+            layer = name.split("/")[0]
+            for c in range(c0, c1):
+                self.chunk_layer[c] = layer
+        self.chunk_coef = coef.to(device)
+        self.chunk_lr = torch.ones(nchunks, dtype=torch.float32, device=device)
+
+    def view(self, name, arena=None):
+        kind, off, shape, _ = self.index[name]
+        base = arena if arena is not None else (self.flat if kind == "t" else self.stats)
+        return base[off:off + int(np.prod(shape))].view(*shape)
+
+    def has(self, name):
+        return name in self.index
+
+    def names(self):
+        return [e[0] for e in self.entries]
+
+    def init_keras_defaults(self, seed=0, pretrained_like=False):
+        """Glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1 (what `--weights none` gives)."""
+        g = torch.Generator().manual_seed(seed)
+        for name, shape, _t, _r in self.entries:
+            if name.endswith("/kernel"):
+                if len(shape) == 4:
+                    fan_in, fan_out = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
+                else:
+                    fan_in, fan_out = shape
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                w = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * lim
+            elif name.endswith("/gamma") or name.endswith("/moving_variance"):
+                w = torch.ones(shape, dtype=torch.float64)
+                if pretrained_like:
+                    w = 0.5 + torch.rand(shape, generator=g, dtype=torch.float64)
+            else:
+                w = torch.zeros(shape, dtype=torch.float64)
+                if pretrained_like:
+                    w = 0.1 * torch.randn(shape, generator=g, dtype=torch.float64)
+            self.view(name).copy_(w.to(torch.float32))
+
+    def state_dict(self):
+        return {name: self.view(name).detach().cpu().numpy().copy() for name in self.names()}
+
+    def load_state_dict(self, sd, by_name=True, exclude=None):
+        """By-name load with an exclude list of LAYER names, like net.py:816-852. Returns the names loaded."""
+        loaded = []
+        for name in self.names():
+            layer = name.split("/")[0]
+            if exclude and layer in exclude:
+                continue
+            if name in sd:
+                w = torch.as_tensor(np.asarray(sd[name]), dtype=torch.float32)
+                if tuple(w.shape) != tuple(self.index[name][2]):
+                    raise ValueError(f"shape mismatch for {name}: {tuple(w.shape)} vs {self.index[name][2]}")
+                self.view(name).copy_(w)
+                loaded.append(name)
+        return loaded
+
+    def set_trainable(self, layer_regex: str):
+        """chunk_lr[c] = 1 where the owning layer's name fully matches the regex (net.py:1030-1066)."""
+        mask = torch.tensor([1.0 if (l and re.fullmatch(layer_regex, l)) else 0.0 for l in self.chunk_layer])
+        self.chunk_lr.copy_(mask)
+        return int(mask.sum().item())
+
+
+class Engine:
+    """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
+
+    def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0):
+        lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
+        if not torch.cuda.is_available():
+            raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
+        self.cfg, self.B, self.training, self.device, self.world = cfg, int(batch_size), training, device, world_size
+        self.graph: Graph = build_graph(cfg)
+        self.H, self.W = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
+        self.params = ParamStore(self.graph, device, cfg.WEIGHT_DECAY)
+        self.params.init_keras_defaults(seed)
+        self.n_launches = {"stage": 0, "fwd": 0, "bwd": 0, "update": 0}
+        self._keep = []          # plan objects / index tensors kept alive
+        self._zero_specs = []    # (name, numel) carved from the zero arena
+        self._alloc()
+        self._build_forward()
+        if training:
+            self._build_backward()
+            self._build_update()
+        self._finalise_zero_arena()
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _new(self, shape, dtype=torch.bfloat16):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def _alloc(self):
+        g, B = self.graph, self.B
+        self.img_u8 = self._new((B, self.H, self.W, 3), torch.uint8)
+        self.img_f32 = None      # allocated on demand (reference-style molded fp32 input)
+        self.mean3 = torch.tensor(np.asarray(self.cfg.MEAN_PIXEL), dtype=torch.float32, device=self.device)
+        self.E = self._new((B, self.H // 2 + 3, self.W // 2, 64))
+        self.act: Dict[str, torch.Tensor] = {}
+        for name, (h, w, c) in g.shapes.items():
+            self.act[name] = self._new((B, h, w, c), torch.float32 if name == "bottleneck_layer" else torch.bfloat16)
+        self.head: Dict[str, torch.Tensor] = {}
+        for d in g.dense:
+            self.head[d.name] = None   # carved from the zero arena (split-K atomics accumulate into them)
+            self._zero_specs.append(("head:" + d.name, B * d.cout))
+        self.ori_q = self._new((B, 4), torch.float32) if g.ori_mode == "quaternion" else None
+        n_ori = g.dense[-1].cout
+        self.gt_loc = self._new((B, 3 if g.loc_mode == "regression" else self.cfg.LOC_BINS_PER_DIM ** 3), torch.float32)
+        self.gt_ori = self._new((B, 4 if g.ori_mode == "quaternion" else n_ori), torch.float32)
+        self.losses = self._new((2,), torch.float32)        # [loc_loss * w, ori_loss * w]
+        self.scale: Dict[str, torch.Tensor] = {}
+        self.shift: Dict[str, torch.Tensor] = {}
+        for c in g.convs:
+            self.scale[c.name] = self._new((c.cout,), torch.float32)
+            self.shift[c.name] = self._new((c.cout,), torch.float32)
+        if self.training:
+            self.grads = torch.zeros_like(self.params.flat)
+            self.dact: Dict[str, torch.Tensor] = {}
+            self.dhead: Dict[str, torch.Tensor] = {}
+            self.hyper = self._new((8,), torch.float32)
+            self.sumsq = self._new((1,), torch.float32)
+            self.opt_state = [torch.zeros_like(self.params.flat) for _ in range(1 if self.cfg.OPTIMIZER == "SGD" else 3)]
+            self.opt_t = 0
+
+    def _zero_view(self, key):
+        off, n = self._zero_index[key]
+        return self.zero_arena[off:off + n]
+
+    def _finalise_zero_arena(self):
+        """All buffers that must be zero at the start of a step (atomic accumulators) live in ONE arena -> one memset."""
+        off = 0
+        self._zero_index = {}
+        for key, n in self._zero_specs:
+            self._zero_index[key] = (off, n)
+            off += _align(n)
+        self.zero_arena = torch.zeros(max(off, ALIGN), dtype=torch.float32, device=self.device)
+        for fn in self._late_binds:
+            fn()
+
+    # ------------------------------------------------------------------ plan helpers
+    def _idx(self, values):
+        t = torch.tensor(list(values), dtype=torch.int32, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _conv_weight_ptrs(self, c: ConvSpec):
+        p = self.params
+        w = p.view(c.name + "/kernel")
+        bias = p.view(c.name + "/bias") if c.bias else None
+        if c.bn:
+            bn = [p.view(f"{c.bn}/{k}") for k in ("gamma", "beta", "moving_mean", "moving_variance")]
+        else:
+            bn = [None] * 4
+        return w, bias, bn
+
+    def _build_forward(self):
+        g, B = self.graph, self.B
+        S = lib.stream_ptr
+        self.ops_stage, self.ops_fwd, self.ops_loss = [], [], []
+        self._late_binds = []
+        self.Bf: Dict[str, torch.Tensor] = {}
+        for c in g.convs:
+            w, bias, bn = self._conv_weight_ptrs(c)
+            sc, sh = self.scale[c.name], self.shift[c.name]
+            self.ops_stage.append(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
+                "urso_bn_fold", lib.ptr(bn[0]), lib.ptr(bn[1]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
+                sc.data_ptr(), sh.data_ptr(), c.cout, S()))
+            if c.stem:
+                segs, idx = P.stem_segments(), P.stem_weight_index(3)
+                geom = None
+            else:
+                h, w_, _ = g.shapes[c.src]
+                geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w_)
+                segs, idx = P.fwd_segments(geom)
+            K = len(idx)
+            bmat = self._new((c.cout, K))
+            self.Bf[c.name] = bmat
+            idx_d = self._idx(idx)
+            self.ops_stage.append(lambda w=w, sc=sc, bmat=bmat, idx_d=idx_d, K=K, c=c: lib.call(
+                "urso_stage_weight_rows", w.data_ptr(), sc.data_ptr(), bmat.data_ptr(), idx_d.data_ptr(), K, c.cout,
+                c.cout, K, S()))
+            out = self.act[c.dst]
+            addend = self.act[c.addend] if c.addend else None
+            oh, ow = g.shapes[c.dst][0], g.shapes[c.dst][1]
+            if c.stem:
+                tw, th = P.pick_patch(oh, ow, 128)
+                plan = lib.ConvGemm([self.E], bmat, segs, out, ow, oh, B, tw, th, shift=sh, relu=c.relu)
+            elif c.k == 1 and c.stride == 1:
+                M = B * oh * ow
+                x = self.act[c.src].view(1, 1, M, c.cin)
+                plan = lib.ConvGemm([x], bmat, segs, out.view(1, 1, M, c.cout), M, 1, 1, 128, 1, shift=sh,
+                                    addend=addend.view(1, 1, M, c.cout) if addend is not None else None, relu=c.relu)
+            else:
+                tw, th = P.pick_patch(oh, ow, 128)
+                plan = lib.ConvGemm(P.input_views(self.act[c.src], c.stride), bmat, segs, out, ow, oh, B, tw, th,
+                                    shift=sh, addend=addend, relu=c.relu)
+            self._keep.append(plan)
+            self.ops_fwd.append(plan.launch)
+            if c.stem:
+                ph, pw, _ = g.shapes[c.dst]
+                self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
+                src, dst = self.act[c.dst], self.act["pool1"]
+                self.ops_fwd.append(lambda src=src, dst=dst, ph=ph, pw=pw: lib.call(
+                    "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(self.argmax), B, ph, pw, 64, S()))
+        # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332)
+        for d in g.dense:
+            w, b = self.params.view(d.name + "/kernel"), self.params.view(d.name + "/bias")
+
+            def bind(d=d):
+                self.head[d.name] = self._zero_view("head:" + d.name).view(self.B, d.cout)
+            self._late_binds.append(bind)
+
+            def run(d=d, w=w, b=b):
+                x = self.act["bottleneck_layer"] if d.src == "bottleneck_layer" else self.head[d.src]
+                y = self.head[d.name]
+                lib.call("urso_dense_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), self.B, d.cin, d.cout, S())
+                lib.call("urso_dense_bias_act", y.data_ptr(), b.data_ptr(), self.B, d.cout, d.act, S())
+            self.ops_fwd.append(run)
+        if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
+            self.ops_fwd.append(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
+                                                 self.ori_q.data_ptr(), None, None, self.B, 1.0, S()))
+
+    # ------------------------------------------------------------------ backward plan
+    def _build_backward(self):
+        g, B, cfg = self.graph, self.B, self.cfg
+        S = lib.stream_ptr
+        self.ops_bwd = []
+        wl = float(cfg.LOSS_WEIGHTS.get("loc_loss", 1.0))
+        wo = float(cfg.LOSS_WEIGHTS.get("ori_loss", 1.0))
+        for d in g.dense:
+            self.dhead[d.name] = self._new((B, d.cout), torch.float32)
+        self.dfeat = [self._new((B, g.nr_features), torch.float32) for _ in range(2)]
+        loc_l, ori_l = self.losses[0:1], self.losses[1:2]
+
+        # ---- losses (net.py:656-669, 705-762) -> gradients w.r.t. the head outputs
+        def loss_ops():
+            loc, dloc = self.head["loc_final"], self.dhead["loc_final"]
+            if g.loc_mode == "regression":
+                lib.call("urso_rel_loss", loc.data_ptr(), self.gt_loc.data_ptr(), dloc.data_ptr(), loc_l.data_ptr(), B, 3,
+                         wl, S())
+            else:
+                lib.call("urso_softmax_xent", loc.data_ptr(), self.gt_loc.data_ptr(), dloc.data_ptr(), loc_l.data_ptr(),
+                         B, loc.shape[1], wl, S())
+            if g.ori_mode == "quaternion":
+                lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), self.gt_ori.data_ptr(), self.ori_q.data_ptr(),
+                         self.dhead["ori_q"].data_ptr(), ori_l.data_ptr(), B, wo, S())
+            else:
+                z = self.head["ori_final"]
+                lib.call("urso_softmax_xent", z.data_ptr(), self.gt_ori.data_ptr(), self.dhead["ori_final"].data_ptr(),
+                         ori_l.data_ptr(), B, z.shape[1], wo, S())
+        self.ops_loss.append(loss_ops)
+
+        # ---- heads backward (reverse order); dx of the first layer of each branch goes to dfeat[branch]
+        for d in reversed(g.dense):
+            branch = 0 if d.name.startswith("loc") else 1
+            gw = self.params.view(d.name + "/kernel", self.grads)
+            gb = self.params.view(d.name + "/bias", self.grads)
+            w = self.params.view(d.name + "/kernel")
+
+            def run(d=d, w=w, gw=gw, gb=gb, branch=branch):
+                x = self.act["bottleneck_layer"] if d.src == "bottleneck_layer" else self.head[d.src]
+                dx = self.dfeat[branch] if d.src == "bottleneck_layer" else self.dhead[d.src]
+                lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), self.head[d.name].data_ptr(),
+                         self.dhead[d.name].data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, d.cin, d.cout,
+                         d.act, S())
+            self.ops_bwd.append(run)
+        if cfg.NR_DENSE_LAYERS == 0:
+            raise NotImplementedError("NR_DENSE_LAYERS=0 backward")   # CLI fixes it to 1 (pose_estimator.py:820)
+
+        # ---- gradient buffers of activations
+        bw = g.shapes["bottleneck_layer"][2]
+        h6, w6 = g.shapes["bottleneck_layer"][:2]
+        self.dact["bottleneck_layer"] = self._new((B, h6, w6, P.ceil64(bw)))   # zero padded bf16 operand
+        self.ops_bwd.append(lambda: lib.call(
+            "urso_pad_cast_rows", self.dfeat[0].data_ptr(), self.dfeat[1].data_ptr(),
+            self.dact["bottleneck_layer"].data_ptr(), B * h6 * w6, bw, P.ceil64(bw), S()))
+        producers = {c.dst: c for c in g.convs}
+        cons_conv: Dict[str, List[ConvSpec]] = {}
+        cons_add: Dict[str, List[ConvSpec]] = {}
+        for c in g.convs:
+            cons_conv.setdefault(c.src, []).append(c)
+            if c.addend:
+                cons_add.setdefault(c.addend, []).append(c)
+        self.colsum: Dict[str, Optional[torch.Tensor]] = {}
+
+        def colsum_for(buf):
+            key = "colsum:" + buf
+            if key not in [k for k, _ in self._zero_specs]:
+                self._zero_specs.append((key, g.shapes[buf][2] if buf != "bottleneck_layer" else P.ceil64(bw)))
+            return key
+
+        # process buffers in reverse production order
+        order = [c.dst for c in g.convs]
+        order.insert(1, "pool1")
+        self.Bd = {}
+        for X in reversed(order):
+            if X == "bottleneck_layer":
+                key = colsum_for(X)
+                self.ops_bwd.append(lambda key=key: lib.call(
+                    "urso_colsum_bf16", self.dact["bottleneck_layer"].data_ptr(), self._zero_view(key).data_ptr(),
+                    B * h6 * w6, P.ceil64(bw), S()))
+                self.colsum[X] = key
+            elif X == g.pool_src:     # stem output: gradient arrives through the max-pool
+                h, w, c = g.shapes[X]
+                self.dact[X] = self._new((B, h, w, c))
+                key = colsum_for(X)
+                self.ops_bwd.append(lambda X=X, h=h, w=w, c=c, key=key: (
+                    lib.call("urso_maxpool_bwd", self.act[X].data_ptr(), self.argmax.data_ptr(),
+                             self.dact["pool1"].data_ptr(), self.dact[X].data_ptr(), B, h, w, c, S()),
+                    lib.call("urso_colsum_bf16", self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B * h * w, c,
+                             S())))
+                self.colsum[X] = key
+            else:
+                convs = cons_conv.get(X, [])
+                adds = cons_add.get(X, [])
+                if not convs and len(adds) == 1 and X not in g.relu_buffers:
+                    # linear shortcut branch: d(out)/d(sc) = 1 -> alias the consumer's gradient
+                    self.dact[X] = self.dact[adds[0].dst]
+                    self.colsum[X] = self.colsum[adds[0].dst]
+                else:
+                    prod = producers.get(X)
+                    need_cs = prod is not None and bool(prod.bias or prod.bn or prod.addend in
+                                                        [c.dst for c in g.convs if not c.relu and (c.bias or c.bn)])
+                    self._build_dgrad_group(X, convs, adds, colsum_for, need_cs)
+            if X in producers:
+                self._build_wgrad(producers[X])
+
+    def _build_dgrad_group(self, X, convs, adds, colsum_for, need_cs):
+        """du_X = mask_X( sum_convs dgrad(du_conv.dst, W_conv) + sum_adds du_add.dst ), one Engine-F launch per
+        output phase with the convolutions' K ranges concatenated (fused gradient fan-in)."""
+        g, B = self.graph, self.B
+        S = lib.stream_ptr
+        h, w, cin = g.shapes[X]
+        assert len(adds) <= 1 and convs, (X, len(adds), len(convs))
+        stride = convs[0].stride
+        assert all(c.stride == stride for c in convs)
+        assert not (adds and stride != 1)
+        self.dact[X] = self._new((B, h, w, cin))
+        key = colsum_for(X) if need_cs else None
+        self.colsum[X] = key
+        mask = self.act[X] if X in g.relu_buffers else None
+        addend = self.dact[adds[0].dst] if adds else None
+        geoms = [P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w) for c in convs]
+        phases = [P.dgrad_phases(gm) for gm in geoms]
+        need_zero = False
+        flat_ok = stride == 1 and all(c.k == 1 for c in convs)
+        launches = []
+        for pi in range(stride * stride):
+            oph, opw = phases[0][pi][0], phases[0][pi][1]
+            segs, parts, ktot = [], [], 0
+            for ci, c in enumerate(convs):
+                _, _, sg, tap_map = phases[ci][pi]
+                if not sg:
+                    continue
+                cop = P.ceil64(c.cout)
+                segs += [(ci, dh, dw, ch) for (_m, dh, dw, ch) in sg]
+                parts.append((c, tap_map, ktot, cop))
+                ktot += len(tap_map) * cop
+            if not segs:
+                need_zero = True
+                continue
+            bmat = self._new((cin, ktot))
+            self.Bd[(X, pi)] = bmat
+            for c, tap_map, koff, cop in parts:
+                wk = self.params.view(c.name + "/kernel")
+                sc = self.scale[c.name]
+                tap_d = self._idx(tap_map)
+                dst = bmat[:, koff:]
+                self.ops_stage.append(lambda wk=wk, sc=sc, dst=dst, tap_d=tap_d, n=len(tap_map), c=c, cop=cop, ktot=ktot:
+                                      lib.call("urso_stage_weight_cols", wk.data_ptr(), sc.data_ptr(), dst.data_ptr(),
+                                               tap_d.data_ptr(), n, c.cin, c.cout, cop, c.cin, ktot, S()))
+            a_views = [self.dact[c.dst] for c in convs]
+            tgt = self.dact[X][:, oph::stride, opw::stride, :]
+            m_v = mask[:, oph::stride, opw::stride, :] if mask is not None else None
+            cs_key = key
+            if flat_ok:
+                M = B * h * w
+                a_views = [v.view(1, 1, M, v.shape[3]) for v in a_views]
+                launches.append(dict(a=a_views, b=bmat, segs=segs, out=self.dact[X].view(1, 1, M, cin), OW=M, OH=1, NB=1,
+                                     TW=128, TH=1, addend=addend.view(1, 1, M, cin) if addend is not None else None,
+                                     mask=mask.view(1, 1, M, cin) if mask is not None else None, cs=cs_key))
+            else:
+                th_, tw_ = tgt.shape[1], tgt.shape[2]
+                tw, th = P.pick_patch(th_, tw_, 128)
+                launches.append(dict(a=a_views, b=bmat, segs=segs, out=tgt, OW=tw_, OH=th_, NB=B, TW=tw, TH=th,
+                                     addend=addend, mask=m_v, cs=cs_key))
+        if need_zero:
+            buf = self.dact[X]
+            self.ops_bwd.append(lambda buf=buf: buf.zero_())
+        for L in launches:
+            def make(L=L):
+                plan_box = {}
+
+                def bind():
+                    cs = self._zero_view(L["cs"]) if L["cs"] else None
+                    plan_box["p"] = lib.ConvGemm(L["a"], L["b"], L["segs"], L["out"], L["OW"], L["OH"], L["NB"], L["TW"],
+                                                 L["TH"], addend=L["addend"], mask=L["mask"], colsum=cs)
+                self._late_binds.append(bind)
+                return lambda: plan_box["p"].launch()
+            self.ops_bwd.append(make())
+
+    def _build_wgrad(self, c: ConvSpec):
+        g, B = self.graph, self.B
+        S = lib.stream_ptr
+        du = self.dact[c.dst]
+        qc = c.cout
+        if c.stem:
+            segs = [(m, dh, dw) for (m, dh, dw, _ch) in P.stem_segments()]
+            p_views, pc = [self.E], 64
+            oh, ow = g.shapes[c.dst][:2]
+            n_rows = 4 * 64
+            row_map = self._idx(P.stem_grad_row_map(3))
+        else:
+            h, w, _ = g.shapes[c.src]
+            geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
+            segs = P.wgrad_segments(geom)
+            p_views, pc = P.input_views(self.act[c.src], c.stride), c.cin
+            oh, ow = geom.oh, geom.ow
+            n_rows = c.k * c.k * c.cin
+            row_map = None
+        gkey = "G:" + c.name
+        self._zero_specs.append((gkey, n_rows * c.cout))
+        swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout
+        flat = (not c.stem) and c.k == 1 and c.stride == 1
+        box = {}
+
+        def bind():
+            G = self._zero_view(gkey)
+            if flat:
+                M = B * oh * ow
+                xv, dv = self.act[c.src].view(1, 1, M, c.cin), du.view(1, 1, M, du.shape[3])
+                if swap:   # wide side on the 128-row MMA M dimension; transposed accumulation into HWIO
+                    box["p"] = lib.Wgrad([dv], xv, [(0, 0, 0)], qc, c.cin, M, 1, 1, 64, 1, G, c.cin * c.cout, 1, c.cout)
+                else:
+                    box["p"] = lib.Wgrad([xv], dv, [(0, 0, 0)], c.cin, qc, M, 1, 1, 64, 1, G, c.cin * c.cout, c.cout, 1)
+            else:
+                tw, th = P.pick_patch(oh, ow, 64)
+                box["p"] = lib.Wgrad(p_views, du, segs, pc, qc, ow, oh, B, tw, th, G, pc * c.cout, c.cout, 1)
+        self._late_binds.append(bind)
+        self.ops_bwd.append(lambda: box["p"].launch())
+        # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form)
+        w, bias, bn = self._conv_weight_ptrs(c)
+        pv = self.params.view
+        dW = pv(c.name + "/kernel", self.grads)
+        dbias = pv(c.name + "/bias", self.grads) if c.bias else None
+        dgamma = pv(c.bn + "/gamma", self.grads) if c.bn else None
+        dbeta = pv(c.bn + "/beta", self.grads) if c.bn else None
+        cs_key = self.colsum.get(c.dst) if (c.bias or c.bn) else None
+        sc = self.scale[c.name]
+        R = c.k * c.k * c.cin
+
+        def run():
+            cs = self._zero_view(cs_key) if cs_key else None
+            lib.call("urso_conv_param_grads", self._zero_view(gkey).data_ptr(), lib.ptr(row_map), w.data_ptr(),
+                     lib.ptr(cs), sc.data_ptr(), lib.ptr(bn[0]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
+                     dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta), R, c.cout, S())
+        self.ops_bwd.append(run)
+
+    def _build_update(self):
+        S = lib.stream_ptr
+        p = self.params
+        n = p.n_train
+        self.ops_update = []
+        self.ops_update.append(lambda: lib.call(
+            "urso_add_reg_sumsq", self.grads.data_ptr(), p.flat.data_ptr(), p.chunk_coef.data_ptr(),
+            p.chunk_lr.data_ptr(), 1.0 / self.world, self.sumsq.data_ptr(), n, S()))
+        if self.cfg.OPTIMIZER == "SGD":
+            self.ops_update.append(lambda: lib.call(
+                "urso_sgd_step", p.flat.data_ptr(), self.opt_state[0].data_ptr(), self.grads.data_ptr(),
+                p.chunk_lr.data_ptr(), self.sumsq.data_ptr(), self.hyper.data_ptr(), n, S()))
+        else:
+            self.ops_update.append(lambda: lib.call(
+                "urso_amsgrad_step", p.flat.data_ptr(), self.opt_state[0].data_ptr(), self.opt_state[1].data_ptr(),
+                self.opt_state[2].data_ptr(), self.grads.data_ptr(), p.chunk_lr.data_ptr(), self.sumsq.data_ptr(),
+                self.hyper.data_ptr(), n, S()))
+
+    # ------------------------------------------------------------------ running
+    def _run(self, ops):
+        for op in ops:
+            op()
+
+    def _stage_input(self):
+        S = lib.stream_ptr
+        if self._input_kind == "u8":
+            lib.call("urso_stem_stage", self.img_u8.data_ptr(), 1, 1, self.mean3.data_ptr(), self.E.data_ptr(), self.B,
+                     self.H, self.W, S())
+        else:
+            lib.call("urso_stem_stage", self.img_f32.data_ptr(), 0, 0, None, self.E.data_ptr(), self.B, self.H, self.W, S())
+
+    _input_kind = "u8"
+
+    def set_input_kind(self, kind):
+        """'u8': raw uint8 RGB, mean subtracted on device.  'molded': fp32 already mean-subtracted (net.py:1337-1348)."""
+        assert kind in ("u8", "molded")
+        if kind == "molded" and self.img_f32 is None:
+            self.img_f32 = self._new((self.B, self.H, self.W, 3), torch.float32)
+        if kind != self._input_kind:
+            self._graphs = {}
+        self._input_kind = kind
+
+    def _phase_fwd(self):
+        self.zero_arena.zero_()
+        self._run(self.ops_stage)
+        self._stage_input()
+        self._run(self.ops_fwd)
+
+    def _phase_train(self):
+        self._phase_fwd()
+        self._run(self.ops_loss)
+        self._run(self.ops_bwd)
+
+    def _replay(self, key, fn, use_graph=True):
+        if not use_graph:
+            fn()
+            return
+        gr = self._graphs.get(key)
+        if gr is None:
+            fn()                                   # eager warm-up (sets function attributes, loads modules)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            self._graphs[key] = gr
+        gr.replay()
+
+    def forward(self, use_graph=True):
+        """Runs the forward plan on the current input buffers; returns (loc [B,3|bins], ori [B,n|4]) device tensors."""
+        self._replay("fwd", self._phase_fwd, use_graph)
+        ori = self.ori_q if self.graph.ori_mode == "quaternion" else self.head[self.graph.ori_out]
+        return self.head["loc_final"], ori
+
+    def set_hyper(self, lr, momentum=None, clipnorm=None):
+        cfg = self.cfg
+        momentum = cfg.LEARNING_MOMENTUM if momentum is None else momentum
+        clipnorm = cfg.GRADIENT_CLIP_NORM if clipnorm is None else clipnorm
+        if cfg.OPTIMIZER == "SGD":
+            h = [lr, momentum, 0, 0, clipnorm, 0, 0, 0]
+        else:   # Keras Adam(amsgrad): lr_t = lr * sqrt(1-b2^t) / (1-b1^t), t counted from 1
+            t = self.opt_t + 1
+            eps = 1e-4 if getattr(cfg, "F16", False) else 1e-7
+            h = [lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t), 0.9, 0.999, eps, clipnorm, 0, 0, 0]
+        self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+
+    def train_step(self, lr, allreduce=None, use_graph=True):
+        """One optimisation step on the current input/label buffers: fwd + loss + bwd (graph A), optional
+        all-reduce of the flat gradient arena, regulariser + clip + update (graph B)."""
+        assert self.training
+        self.set_hyper(lr)
+        self._replay("train", self._phase_train, use_graph)
+        if allreduce is not None:
+            allreduce(self.grads)
+        self._replay("update", lambda: self._run(self.ops_update), use_graph)
+        self.opt_t += 1
+
+    def count_launches(self):
+        """Number of kernels of this library launched per train step / forward (for bench.py's gpu_launches)."""
+        n_fwd = len(self.ops_stage) + 1 + len(self.ops_fwd) + len(self.graph.dense)   # dense op = 2 kernels
+        if not self.training:
+            return n_fwd
+        return n_fwd + 2 + len(self.ops_bwd) + 3 * len(self.graph.dense) + len(self.ops_update)

@@ -75,7 +75,7 @@ SIGNATURES = {
     "urso_amsgrad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "urso_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "urso_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
-    "urso_pad_cast_rows": [_vp, _vp, _i64, _i32, _i32, _vp],
+    "urso_pad_cast_rows": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None}
