@@ -197,45 +197,93 @@ def batchnorm_frozen(x, p, name, eps=BN_EPS):
 # --------------------------------------------------------------------------------------
 # the graph (net.py:161-199, 242-282, 288-352, 639-643)
 # --------------------------------------------------------------------------------------
-def backbone_forward(p, x, cfg, taps=None):
-    def C(name, x, stride=1, padding="valid"):
-        return conv2d(x, p[name + "/kernel"], p.get(name + "/bias"), stride, padding)
+class _GradRound(torch.autograd.Function):
+    """identity forward; backward rounds the gradient to bf16 (models the engine's bf16 gradient buffers)."""
 
+    @staticmethod
+    def forward(ctx, x):
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _q(x):
+    """round to bf16 with a straight-through gradient (models bf16 storage of activations / staged weights)."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def conv_bn(x, p, conv, bn, stride, padding, quant):
+    """Conv2D(+bias) -> frozen BatchNorm.  quant=True evaluates the algebraically identical folded form the engine
+    uses: conv(x, bf16(W * scale)) + shift with scale = gamma/sqrt(var+eps), shift = (bias-mean)*scale+beta."""
+    w, b = p[conv + "/kernel"], p.get(conv + "/bias")
+    if not quant:
+        y = conv2d(x, w, b, stride, padding)
+        return batchnorm_frozen(y, p, bn) if bn else y
+    if bn:
+        scale = p[bn + "/gamma"] / torch.sqrt(p[bn + "/moving_variance"] + BN_EPS)
+        shift = ((b if b is not None else 0.0) - p[bn + "/moving_mean"]) * scale + p[bn + "/beta"]
+    else:
+        scale, shift = 1.0, (b if b is not None else 0.0)
+    return conv2d(x, _q(w * scale), None, stride, padding) + shift
+
+
+def backbone_forward(p, x, cfg, taps=None, quant=False):
+    """quant=True inserts the engine's bf16 rounding points (activations after each fused epilogue, staged weights,
+    gradient buffers after each ReLU mask) so that parity can be checked at the kernel's own precision."""
     def tap(name, v):
         if taps is not None:
             taps[name] = v
         return v
 
+    def act(u, relu=True):
+        if quant:
+            u = _GradRound.apply(u)
+        y = F.relu(u) if relu else u
+        return _q(y) if quant else y
+
+    if quant:
+        x = _q(x)
     if cfg.BACKBONE in ("resnet50", "resnet101"):
-        x = C("conv1", x, 2, 3)                                         # ZeroPadding2D(3) + 7x7/s2 valid
-        x = tap("conv1_relu", F.relu(batchnorm_frozen(x, p, "bn_conv1")))
+        x = conv_bn(x, p, "conv1", "bn_conv1", 2, 3, quant)             # ZeroPadding2D(3) + 7x7/s2 valid
+        x = tap("conv1_relu", act(x))
         x = tap("pool1", maxpool3x3s2_same(x))
+        if quant:
+            x = _GradRound.apply(x)
         for stage, blk, has_sc, stride, _f in deep_blocks(cfg.BACKBONE):
             cb, bb = f"res{stage}{blk}_branch", f"bn{stage}{blk}_branch"
-            y = F.relu(batchnorm_frozen(C(cb + "2a", x, stride), p, bb + "2a"))   # stride on FIRST 1x1
-            y = F.relu(batchnorm_frozen(C(cb + "2b", y, 1, "same"), p, bb + "2b"))
-            y = batchnorm_frozen(C(cb + "2c", y), p, bb + "2c")
-            sc = batchnorm_frozen(C(cb + "1", x, stride), p, bb + "1") if has_sc else x
-            x = tap(f"res{stage}{blk}_out", F.relu(y + sc))
+            y = act(conv_bn(x, p, cb + "2a", bb + "2a", stride, "valid", quant))      # stride on FIRST 1x1
+            y = act(conv_bn(y, p, cb + "2b", bb + "2b", 1, "same", quant))
+            y = conv_bn(y, p, cb + "2c", bb + "2c", 1, "valid", quant)
+            sc = conv_bn(x, p, cb + "1", bb + "1", stride, "valid", quant) if has_sc else x
+            if quant and has_sc:
+                sc = _q(sc)                                                            # shortcut branch stored in bf16
+            x = tap(f"res{stage}{blk}_out", act(y + sc))
     else:
-        x = C("conv0", x, 2, 3)
-        x = tap("conv0_relu", F.relu(batchnorm_frozen(x, p, "bn_conv0")))
+        x = conv_bn(x, p, "conv0", "bn_conv0", 2, 3, quant)
+        x = tap("conv0_relu", act(x))
         x = tap("pool1", maxpool3x3s2_same(x))
+        if quant:
+            x = _GradRound.apply(x)
         for stage, block, _filt, stride, cut in shallow_blocks(cfg.BACKBONE):
             base = f"stage{stage + 1}_unit{block + 1}_"
-            sc = C(base + "sc", x, stride) if cut == "post" else x      # raw block input, no BN
-            y = C(base + "conv1", x, stride, 1)                         # ZeroPadding2D(1) + valid
-            y = F.relu(batchnorm_frozen(y, p, base + "bn2"))
-            y = C(base + "conv2", y, 1, 1)
-            x = tap(base + "relu2", F.relu(y + sc))
+            sc = conv_bn(x, p, base + "sc", None, stride, "valid", quant) if cut == "post" else x   # raw input, no BN
+            if quant and cut == "post":
+                sc = _q(sc)
+            y = act(conv_bn(x, p, base + "conv1", base + "bn2", stride, 1, quant))    # ZeroPadding2D(1) + valid
+            y = conv_bn(y, p, base + "conv2", None, 1, 1, quant)
+            x = tap(base + "relu2", act(y + sc))
     return x
 
 
-def forward(p, images, cfg, taps=None):
+def forward(p, images, cfg, taps=None, quant=False):
     """images: [B,H,W,3] mean-subtracted ('molded', net.py:1337-1348). Returns (loc, ori).
     Training and inference graphs give the same (loc, ori) (frozen BN), net.py:680/691."""
-    c5 = backbone_forward(p, images, cfg, taps)
-    c6 = conv2d(c5, p["bottleneck_layer/kernel"], p["bottleneck_layer/bias"], 2, "same")
+    c5 = backbone_forward(p, images, cfg, taps, quant)
+    c6 = conv_bn(c5, p, "bottleneck_layer", None, 2, "same", quant)
+    if quant:
+        c6 = _GradRound.apply(c6)
     if taps is not None:
         taps["bottleneck_layer"] = c6
     feat = c6.reshape(c6.shape[0], -1)                                  # NHWC flatten (net.py:298,332)
@@ -292,9 +340,9 @@ def reg_loss(p, cfg, trainable=None):
     return tot
 
 
-def total_loss(p, batch, cfg, trainable=None):
+def total_loss(p, batch, cfg, trainable=None, quant=False):
     images, gt_loc, gt_ori = batch
-    loc, ori = forward(p, images, cfg)
+    loc, ori = forward(p, images, cfg, quant=quant)
     loc_loss, ori_loss = head_losses(loc, ori, gt_loc, gt_ori, cfg)
     wl = cfg.LOSS_WEIGHTS.get("loc_loss", 1.0)
     wo = cfg.LOSS_WEIGHTS.get("ori_loss", 1.0)
@@ -302,12 +350,12 @@ def total_loss(p, batch, cfg, trainable=None):
     return tot, (loc, ori, wl * loc_loss, wo * ori_loss)
 
 
-def gradients(p, batch, cfg, trainable=None):
+def gradients(p, batch, cfg, trainable=None, quant=False):
     """d total_loss / d trainable weights by autograd on the restated forward (what TF autodiff computes)."""
     names = [n for n in p if is_trainable(n) and (trainable is None or n in trainable)]
     leaves = {n: p[n].detach().clone().requires_grad_(True) for n in names}
     q = dict(p); q.update(leaves)
-    tot, aux = total_loss(q, batch, cfg, trainable)
+    tot, aux = total_loss(q, batch, cfg, trainable, quant)
     grads = torch.autograd.grad(tot, [leaves[n] for n in names])
     return dict(zip(names, grads)), tot.detach(), tuple(a.detach() for a in aux)
 
@@ -347,10 +395,10 @@ def amsgrad_step(p, state, grads, lr, clipnorm, beta1=0.9, beta2=0.999, eps=1e-7
     return newp, norm
 
 
-def train_step(p, state, batch, cfg, lr=None, trainable=None):
+def train_step(p, state, batch, cfg, lr=None, trainable=None, quant=False):
     """One Keras train_on_batch: grads of (weighted head losses + L2 reg) -> clip -> update."""
     lr = cfg.LEARNING_RATE if lr is None else lr
-    grads, tot, aux = gradients(p, batch, cfg, trainable)
+    grads, tot, aux = gradients(p, batch, cfg, trainable, quant)
     if cfg.OPTIMIZER == "SGD":
         newp, norm = sgd_step(p, state, grads, lr, cfg.LEARNING_MOMENTUM, cfg.GRADIENT_CLIP_NORM)
     else:

@@ -1,11 +1,16 @@
 """End-to-end GPU parity of the engine (all launches through the C-ABI) against the fp64 oracle on the same seeded
 weights / inputs: forward outputs, losses, every parameter gradient, and the weights after one optimizer step.
 
-Tolerances (bf16 activations + bf16 staged weights, fp32 accumulation; oracle in fp64):
-  forward loc / ori logits : max |diff| <= 3e-2 * max |ref|     (bf16 eps = 3.9e-3 accumulated over <= 53 layers)
-  per-tensor gradients     : ||g - g_ref|| / ||g_ref|| <= 8e-2 for tensors whose norm is above noise
-  updated weights          : max |w - w_ref| <= 1e-3 * lr-scaled update size + fp32 eps
-The split-bf16 parity mode (1e-3 gate of BASELINE.json) is covered in test_gpu_parity_mode.py.
+Two oracles are used (both fp64 arithmetic):
+  * quant=True  -- the restatement with the engine's bf16 ROUNDING POINTS inserted (activations after each fused
+    epilogue, BN-folded staged weights, gradient buffers after each ReLU mask).  Remaining differences are fp32
+    accumulation order and the occasional 1-ulp rounding flip it causes, so the gates are tight:
+      stem/pool exact to 2e-3; end-to-end outputs 3e-2; gradient direction cos >= 0.95 (a random, un-normalised deep
+      net amplifies 1-ulp rounding flips chaotically).  The BUG-CATCHING comparison is layer-local: each layer's
+      output / gradients recomputed in fp64 from the engine's own stored tensors must agree to 4e-3.
+  * quant=False -- the plain fp64 graph.  It measures what bf16 storage costs on a randomly initialised (chaotic,
+    un-normalised-input) network: forward <= 3e-2, gradient direction cos >= 0.93.  The 1e-3 forward gate of
+    BASELINE.json is met by the split-bf16 parity mode (test_gpu_parity_mode.py), not by bf16 storage.
 """
 import numpy as np
 import pytest
@@ -70,6 +75,26 @@ def test_forward_matches_oracle(backbone, classify):
     eng.img_u8.copy_(img)
     loc, ori = eng.forward(use_graph=False)
     torch.cuda.synchronize()
+    # layer-local exactness: every conv output recomputed in fp64 from the engine's OWN bf16 input must agree to
+    # bf16 output rounding (rms 2^-9, max 2^-8 + fp32 accumulation noise)
+    P64 = {k: v.double() for k, v in p64.items()}
+    mean = torch.tensor(O.MEAN_PIXEL, dtype=torch.float64)
+    with torch.no_grad():
+        for c in eng.graph.convs:
+            x = (img.double() - mean).to(torch.bfloat16).double() if c.stem else eng.act[c.src].double().cpu()
+            y = O.conv_bn(x, P64, c.name, c.bn, c.stride, c.padding, quant=True)
+            if c.addend:
+                y = y + eng.act[c.addend].double().cpu()
+            if c.relu:
+                y = torch.relu(y)
+            got = eng.act[c.dst].double().cpu()
+            rms = (got - y).norm().item() / max(y.norm().item(), 1e-30)
+            assert rms <= 3e-3 and rel(got, y) <= 1e-2, (c.name, rms, rel(got, y))
+    qt = {}
+    qloc, qori = O.forward(p64, O.mold_image(img), cfg, qt, quant=True)
+    assert rel(eng.act["pool1"].double().cpu(), qt["pool1"].detach()) <= 2e-3
+    assert rel(loc.double().cpu(), qloc.detach()) <= 3e-2
+    assert rel(ori.double().cpu(), qori.detach()) <= 3e-2
     taps = {}
     rloc, rori = O.forward(p64, O.mold_image(img), cfg, taps)
     # intermediate activations first: localises a failure to a layer
@@ -86,6 +111,58 @@ def test_forward_matches_oracle(backbone, classify):
     assert rel(loc2.double().cpu(), rloc) <= 3e-2
 
 
+def local_backward_check(eng, p64, cfg):
+    """Layer-local exactness of the backward plan.  A randomly initialised deep net amplifies 1-ulp bf16 rounding
+    flips chaotically, so END-TO-END gradients can only be compared loosely; instead every layer's gradients are
+    recomputed in fp64 FROM THE ENGINE'S OWN stored tensors (its bf16 input activation and its bf16 output gradient)
+    and must match tightly.  This pins the wiring: which buffer feeds which launch, masks, fan-in, strides, phases."""
+    from ursonet_b200.graph import build_graph
+    g = eng.graph
+    P64 = {k: v.double() for k, v in p64.items()}
+    cons = {}
+    for c in g.convs:
+        cons.setdefault(c.src, []).append(c)
+    adds = {}
+    for c in g.convs:
+        if c.addend:
+            adds.setdefault(c.addend, []).append(c)
+    mean = torch.tensor(O.MEAN_PIXEL, dtype=torch.float64)
+    report = []
+    for c in g.convs:
+        du = eng.dact[c.dst].double().cpu()[..., :c.cout]
+        if c.stem:
+            x = (eng.img_u8.double().cpu() - mean).to(torch.bfloat16).double()
+        else:
+            x = eng.act[c.src].double().cpu()
+        names = [c.name + "/kernel"] + ([c.name + "/bias"] if c.bias else []) + \
+                ([c.bn + "/gamma", c.bn + "/beta"] if c.bn else [])
+        leaves = {n: P64[n].clone().requires_grad_(True) for n in names}
+        q = dict(P64); q.update(leaves)
+        y = O.conv_bn(x, q, c.name, c.bn, c.stride, c.padding, quant=True)
+        grads = torch.autograd.grad(y, [leaves[n] for n in names], du)
+        for n, gref in zip(names, grads):
+            got = eng.params.view(n, eng.grads).double().cpu()
+            e = (got - gref).norm().item() / max(gref.norm().item(), 1e-30)
+            report.append((n, e))
+    for X, convs in cons.items():
+        if X == "image":
+            continue
+        x = eng.act[X].double().cpu().requires_grad_(True)
+        tot = torch.zeros_like(x)
+        for c in convs:
+            du = eng.dact[c.dst].double().cpu()[..., :c.cout]
+            y = O.conv_bn(x, P64, c.name, c.bn, c.stride, c.padding, quant=True)
+            tot = tot + torch.autograd.grad(y, x, du)[0]
+        for c in adds.get(X, []):
+            tot = tot + eng.dact[c.dst].double().cpu()
+        if X in g.relu_buffers:
+            tot = tot * (x.detach() > 0)
+        got = eng.dact[X].double().cpu()
+        e = (got - tot).norm().item() / max(tot.norm().item(), 1e-30)
+        report.append(("d:" + X, e))
+    return report
+
+
 @pytest.mark.parametrize("backbone,classify,optimizer", [("resnet18", True, "SGD"), ("resnet50", True, "SGD"),
                                                          ("resnet50", False, "ADAM")])
 def test_train_step_matches_oracle(backbone, classify, optimizer):
@@ -99,38 +176,57 @@ def test_train_step_matches_oracle(backbone, classify, optimizer):
     eng.img_u8.copy_(img)
     eng.gt_loc.copy_(gt_loc)
     eng.gt_ori.copy_(gt_ori)
+    # ---- 1. forward + backward only (no update): layer-local exactness, tolerance 4e-3 (bf16 rounding of du: 2^-9 rms)
+    eng._phase_train()
+    torch.cuda.synchronize()
+    rep = local_backward_check(eng, p64, cfg)
+    bad = [(n, round(e, 5)) for n, e in rep if e > 4e-3]
+    assert not bad, bad[:12]
+    # ---- 2. the full step against the oracle with the engine's rounding points (quant=True)
     eng.train_step(lr, use_graph=False)
     torch.cuda.synchronize()
-    state = {}
-    newp, info = O.train_step(p64, state, (O.mold_image(img), gt_loc.double(), gt_ori.double()), cfg, lr=lr)
+    batch = (O.mold_image(img), gt_loc.double(), gt_ori.double())
+    newp, info = O.train_step(p64, {}, batch, cfg, lr=lr, quant=True)
     losses = eng.losses.double().cpu()
-    assert abs(losses[0].item() - info["loc_loss"].item()) <= 3e-2 * abs(info["loc_loss"].item()) + 1e-4
-    assert abs(losses[1].item() - info["ori_loss"].item()) <= 3e-2 * abs(info["ori_loss"].item()) + 1e-4
-    # gradients: eng.grads holds d(loss)/dw + regulariser after the update phase (add_reg_sumsq rewrites it in place)
-    bad = []
+    assert abs(losses[0].item() - info["loc_loss"].item()) <= 1e-2 * abs(info["loc_loss"].item()) + 1e-4
+    assert abs(losses[1].item() - info["ori_loss"].item()) <= 1e-2 * abs(info["ori_loss"].item()) + 1e-4
+    # end-to-end gradients (eng.grads now includes the regulariser): chaotic amplification of rounding flips through
+    # the random net (53 layers for RN-50) limits this to direction -- the tight check is the layer-local one above
     gmax = max(g.norm().item() for g in info["grads"].values())
     for name, gref in info["grads"].items():
-        got = eng.params.view(name, eng.grads).double().cpu()
         n = gref.norm().item()
         if n < 1e-3 * gmax:
             continue
-        e = (got - gref).norm().item() / n
-        if e > 8e-2:
-            bad.append((name, e, n))
-    assert not bad, bad[:10]
+        got = eng.params.view(name, eng.grads).double().cpu()
+        cos = (got * gref).sum().item() / (got.norm().item() * n)
+        assert cos >= 0.95 and (got - gref).norm().item() / n <= 0.3, (name, cos)
     norm = float(torch.sqrt(eng.sumsq.double().cpu())[0])
-    assert abs(norm - info["grad_norm"].item()) <= 5e-2 * info["grad_norm"].item()
-    # one optimizer step: compare the update (w_new - w_old), which removes the fp32 representation of w itself
-    worst = 0.0
+    assert abs(norm - info["grad_norm"].item()) <= 3e-2 * info["grad_norm"].item()
+    # the optimizer update itself is exact given the engine's own gradient: recompute it on the host in fp64
+    gflat = eng.grads.double().cpu()
+    gn = float(torch.sqrt((gflat * gflat).sum()))
+    assert abs(gn - norm) <= 1e-4 * gn
+    cf = cfg.GRADIENT_CLIP_NORM / gn if gn >= cfg.GRADIENT_CLIP_NORM else 1.0
     for name in info["grads"]:
-        upd = eng.params.view(name).double().cpu() - p64[name].float().double()
-        ref = newp[name] - p64[name]
-        scale = ref.abs().max().item()
-        if scale < 1e-12:
+        w0 = p64[name].float().double()
+        gq = eng.params.view(name, eng.grads).double().cpu() * cf
+        if optimizer == "SGD":
+            ref = w0 - lr * gq                       # first step: v = -lr*g ; p += v
+        else:
+            m, v = 0.1 * gq, 0.001 * gq * gq
+            lr_t = lr * (1 - 0.999) ** 0.5 / (1 - 0.9)
+            ref = w0 - lr_t * m / (torch.sqrt(v) + 1e-7)
+        got = eng.params.view(name).double().cpu()
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6), name
+    # ---- 3. against the un-quantised fp64 graph: direction of every sizeable gradient is preserved
+    _, info64 = O.train_step(p64, {}, batch, cfg, lr=lr)
+    for name, gref in info64["grads"].items():
+        if gref.norm().item() < 1e-3 * gmax:
             continue
-        worst = max(worst, (upd - ref).abs().max().item() / scale)
-    assert worst <= (0.15 if optimizer == "SGD" else 1.5), worst   # AMSGrad normalises: sign-like update, noisier
-    # a second step through CUDA graphs runs and changes the weights
+        got = eng.params.view(name, eng.grads).double().cpu()
+        cos = (got * gref).sum().item() / (got.norm().item() * gref.norm().item())
+        assert cos >= 0.93, (name, cos)
+    # ---- 4. further steps through CUDA graphs run and change the weights
     before = eng.params.flat.clone()
     eng.train_step(lr, use_graph=True)
     eng.train_step(lr, use_graph=True)

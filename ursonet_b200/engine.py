@@ -122,6 +122,17 @@ class ParamStore:
         return int(mask.sum().item())
 
 
+class OpRec:
+    """One entry of a launch list: the callable plus what it is (for profiling / launch accounting)."""
+    __slots__ = ("fn", "kind", "name", "flops", "bytes", "launches")
+
+    def __init__(self, fn, kind, name, flops=0.0, nbytes=0.0, launches=1):
+        self.fn, self.kind, self.name, self.flops, self.bytes, self.launches = fn, kind, name, flops, nbytes, launches
+
+    def __call__(self):
+        self.fn()
+
+
 class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
@@ -254,7 +265,10 @@ class Engine:
                 plan = lib.ConvGemm(P.input_views(self.act[c.src], c.stride), bmat, segs, out, ow, oh, B, tw, th,
                                     shift=sh, addend=addend, relu=c.relu)
             self._keep.append(plan)
-            self.ops_fwd.append(plan.launch)
+            fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
+            nb = 2.0 * B * (g.shapes[c.src][0] * g.shapes[c.src][1] * c.cin if not c.stem else self.E[0].numel()) \
+                + (4.0 if c.out_fp32 else 2.0) * B * oh * ow * c.cout * (2 if c.addend else 1) + 2.0 * bmat.numel()
+            self.ops_fwd.append(OpRec(plan.launch, "conv_fwd", c.name, fl, nb))
             if c.stem:
                 ph, pw, _ = g.shapes[c.dst]
                 self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
@@ -274,7 +288,7 @@ class Engine:
                 y = self.head[d.name]
                 lib.call("urso_dense_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), self.B, d.cin, d.cout, S())
                 lib.call("urso_dense_bias_act", y.data_ptr(), b.data_ptr(), self.B, d.cout, d.act, S())
-            self.ops_fwd.append(run)
+            self.ops_fwd.append(OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
         if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
             self.ops_fwd.append(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
                                                  self.ori_q.data_ptr(), None, None, self.B, 1.0, S()))
@@ -307,7 +321,7 @@ class Engine:
                 z = self.head["ori_final"]
                 lib.call("urso_softmax_xent", z.data_ptr(), self.gt_ori.data_ptr(), self.dhead["ori_final"].data_ptr(),
                          ori_l.data_ptr(), B, z.shape[1], wo, S())
-        self.ops_loss.append(loss_ops)
+        self.ops_loss.append(OpRec(loss_ops, "loss", "losses", launches=2))
 
         # ---- heads backward (reverse order); dx of the first layer of each branch goes to dfeat[branch]
         for d in reversed(g.dense):
@@ -322,7 +336,7 @@ class Engine:
                 lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), self.head[d.name].data_ptr(),
                          self.dhead[d.name].data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, d.cin, d.cout,
                          d.act, S())
-            self.ops_bwd.append(run)
+            self.ops_bwd.append(OpRec(run, "dense_bwd", d.name, 4.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 3))
         if cfg.NR_DENSE_LAYERS == 0:
             raise NotImplementedError("NR_DENSE_LAYERS=0 backward")   # CLI fixes it to 1 (pose_estimator.py:820)
 
@@ -363,11 +377,11 @@ class Engine:
                 h, w, c = g.shapes[X]
                 self.dact[X] = self._new((B, h, w, c))
                 key = colsum_for(X)
-                self.ops_bwd.append(lambda X=X, h=h, w=w, c=c, key=key: (
+                self.ops_bwd.append(OpRec(lambda X=X, h=h, w=w, c=c, key=key: (
                     lib.call("urso_maxpool_bwd", self.act[X].data_ptr(), self.argmax.data_ptr(),
                              self.dact["pool1"].data_ptr(), self.dact[X].data_ptr(), B, h, w, c, S()),
                     lib.call("urso_colsum_bf16", self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B * h * w, c,
-                             S())))
+                             S())), "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 3.5, 2))
                 self.colsum[X] = key
             else:
                 convs = cons_conv.get(X, [])
@@ -456,7 +470,10 @@ class Engine:
                                                  L["TH"], addend=L["addend"], mask=L["mask"], colsum=cs)
                 self._late_binds.append(bind)
                 return lambda: plan_box["p"].launch()
-            self.ops_bwd.append(make())
+            fl = sum(2.0 * B * gm.oh * gm.ow * cv.cout * cv.k * cv.k * cv.cin for gm, cv in zip(geoms, convs)) / len(launches)
+            nb = 2.0 * (sum(v.numel() for v in L["a"]) + L["out"].numel() * (2 + (1 if L["addend"] is not None else 0))
+                        + L["b"].numel())
+            self.ops_bwd.append(OpRec(make(), "conv_dgrad", X, fl, nb))
 
     def _build_wgrad(self, c: ConvSpec):
         g, B = self.graph, self.B
@@ -496,7 +513,9 @@ class Engine:
                 tw, th = P.pick_patch(oh, ow, 64)
                 box["p"] = lib.Wgrad(p_views, du, segs, pc, qc, ow, oh, B, tw, th, G, pc * c.cout, c.cout, 1)
         self._late_binds.append(bind)
-        self.ops_bwd.append(lambda: box["p"].launch())
+        fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
+        nb = 2.0 * (sum(v.numel() for v in p_views) + du.numel()) + 4.0 * n_rows * c.cout
+        self.ops_bwd.append(OpRec(lambda: box["p"].launch(), "conv_wgrad", c.name, fl, nb))
         # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form)
         w, bias, bn = self._conv_weight_ptrs(c)
         pv = self.params.view
@@ -611,9 +630,39 @@ class Engine:
         self._replay("update", lambda: self._run(self.ops_update), use_graph)
         self.opt_t += 1
 
-    def count_launches(self):
-        """Number of kernels of this library launched per train step / forward (for bench.py's gpu_launches)."""
-        n_fwd = len(self.ops_stage) + 1 + len(self.ops_fwd) + len(self.graph.dense)   # dense op = 2 kernels
-        if not self.training:
-            return n_fwd
-        return n_fwd + 2 + len(self.ops_bwd) + 3 * len(self.graph.dense) + len(self.ops_update)
+    def count_launches(self, train=True):
+        """Kernels of liburso_b200.so launched per train step (or per forward): bench.py's gpu_launches."""
+        def n(ops):
+            return sum(getattr(o, "launches", 1) for o in ops)
+        total = n(self.ops_stage) + 1 + n(self.ops_fwd)
+        if train and self.training:
+            total += n(self.ops_loss) + n(self.ops_bwd) + n(self.ops_update)
+        return total
+
+    def profile_ops(self, train=True, reps=3):
+        """Eager per-launch timing with CUDA events on the launching stream (cold-ish caches between different ops,
+        which is what a real step sees).  Returns [dict(kind, name, ms, flops, bytes)] for OpRec-tagged launches."""
+        ops = list(self.ops_fwd)
+        if train and self.training:
+            ops += list(self.ops_loss) + list(self.ops_bwd)
+        self._phase_train() if (train and self.training) else self._phase_fwd()    # valid buffers everywhere
+        torch.cuda.synchronize()
+        recs = {}
+        for _ in range(reps):
+            self.zero_arena.zero_()
+            self._run(self.ops_stage)
+            self._stage_input()
+            for i, op in enumerate(ops):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                op()
+                e1.record()
+                recs.setdefault(i, []).append((e0, e1))
+        torch.cuda.synchronize()
+        out = []
+        for i, op in enumerate(ops):
+            if not isinstance(op, OpRec):
+                continue
+            ms = min(a.elapsed_time(b) for a, b in recs[i])
+            out.append(dict(kind=op.kind, name=op.name, ms=ms, flops=op.flops, bytes=op.bytes))
+        return out
