@@ -45,13 +45,19 @@ struct ConvGemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kTrStride = 36;                       // floats; 144-byte rows: conflict-free STS.128 + column LDS
+constexpr int kColsumScratchBytes = 4 * 32 * kTrStride * 4;
+constexpr int kMaxColsumCols = 2048;
+constexpr int kColsumAccBytes = kMaxColsumCols * 4;
 
 template <int BLOCK_N>
 struct ConvGemmCfg {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + 256 /*barriers*/ + 1024 /*align slack*/;
+  // + per-warp 32x36 fp32 transpose scratch and a per-CTA channel accumulator for the fused d(beta) column sums
+  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + 256 /*barriers*/ + 1024 /*align slack*/ +
+                                    kColsumScratchBytes + kColsumAccBytes;
 };
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
@@ -86,6 +92,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  float* s_colacc = s_tr + 4 * 32 * kTrStride;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,6 +114,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (p.colsum != nullptr) {
+    for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -261,22 +272,31 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         if (p.colsum != nullptr) {
-          // per-channel sum over the 32 rows of this warp (butterfly), one atomic per channel per warp
+          // per-channel sums: transpose the warp's 32x32 block through shared memory, each lane sums one column,
+          // accumulate per CTA in shared memory (flushed to HBM once per CTA at the end: no hot global atomics)
+          float* tr = s_tr + q * 32 * kTrStride;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float s = valid ? v[i] : 0.0f;
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (lane == i) atomicAdd(p.colsum + col0 + i, s);
-          }
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(tr + lane * kTrStride + 4 * i) =
+                valid ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+          float s = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) s += tr[r * kTrStride + lane];
+          atomicAdd(&s_colacc[col0 + lane], s);
+          __syncwarp();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if (p.colsum != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      for (int c = threadIdx.x - 128; c < p.ncols; c += 128) {
+        const float s = s_colacc[c];
+        if (s != 0.0f) atomicAdd(p.colsum + c, s);
+      }
     }
   }
 
@@ -320,6 +340,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
                d->TW, d->TH);
   URSO_REQUIRE(d->b_rows % 32 == 0, "b_rows=%d must be a multiple of 32", d->b_rows);
   URSO_REQUIRE(d->out.ptr != nullptr, "null output");
+  URSO_REQUIRE(d->colsum == nullptr || d->b_rows <= urso::kMaxColsumCols, "colsum supports at most %d channels",
+               urso::kMaxColsumCols);
   auto* h = new urso_convgemm();
   ConvGemmParams& p = h->params;
   memset(&p, 0, sizeof(p));
