@@ -1,0 +1,266 @@
+"""Host-side data path feeding the engine: image formatting, dataset readers and the batch generator.
+
+Mirrors the parts of the reference that sit either side of the hot path:
+  utils.resize_image (utils.py:398-511), net.mold_image / compose_image_meta (net.py:1314-1355),
+  dataset.Dataset (dataset.py), urso.Urso (urso.py:27-153), speed.Speed (speed.py), net.load_image_gt /
+  data_generator (net.py:358-559).
+Differences, all deliberate and documented in INTEGRATION.md:
+  * skimage is not available: images are read with cv2 and resized with cv2.INTER_LINEAR (the reference uses
+    skimage.transform.resize(order=1), whose anti-aliasing default is version dependent);
+  * the generator can yield RAW uint8 frames (`raw_uint8=True`): mean subtraction then happens on the GPU inside the
+    stem staging kernel, which cuts the per-step host->device copy 4x (59 MB instead of 236 MB at 640x960x32);
+  * pd.read_csv(header=-1) (urso.py:42) is invalid on pandas >= 1.0: header=None is used;
+  * sim2real / camera-rotation augmentation (net.py:390-438) are not built yet and raise if requested.
+"""
+import json
+import logging
+import os
+
+import cv2
+import numpy as np
+
+from . import labels
+
+
+# ------------------------------------------------------------------------------------------------ image formatting
+def resize_image(image, min_dim=None, max_dim=None, min_scale=None, mode="square"):
+    """Same contract as utils.resize_image: returns (image, window, scale, padding, crop)."""
+    image_dtype = image.dtype
+    h, w = image.shape[:2]
+    window, scale, padding, crop = (0, 0, h, w), 1, [(0, 0), (0, 0), (0, 0)], None
+    if mode == "none":
+        return image, window, scale, padding, crop
+    if min_dim:
+        scale = min_dim / min(h, w)
+    if min_scale and scale < min_scale:
+        scale = min_scale
+    if max_dim and mode != "crop":
+        if round(max(h, w) * scale) > max_dim:
+            scale = max_dim / max(h, w)
+    if scale != 1:
+        image = cv2.resize(image, (round(w * scale), round(h * scale)), interpolation=cv2.INTER_LINEAR)
+    h, w = image.shape[:2]
+    if mode == "square":
+        top, left = (max_dim - h) // 2, (max_dim - w) // 2
+        pads = [(top, max_dim - h - top), (left, max_dim - w - left)]
+    elif mode == "pad64":
+        assert min_dim % 64 == 0, "Minimum dimension must be a multiple of 64"
+        pads = []
+        for n in (h, w):
+            if n % 64 > 0:
+                tot = n - (n % 64) + 64 - n
+                pads.append((tot // 2, tot - tot // 2))
+            else:
+                pads.append((0, 0))
+    elif mode == "crop":
+        y = np.random.randint(0, h - min_dim + 1)
+        x = np.random.randint(0, w - min_dim + 1)
+        return image[y:y + min_dim, x:x + min_dim].astype(image_dtype), (0, 0, min_dim, min_dim), scale, padding, \
+            (y, x, min_dim, min_dim)
+    else:
+        raise Exception("Mode {} not supported".format(mode))
+    padding = pads + [(0, 0)] if image.ndim > 2 else pads
+    image = np.pad(image, padding, mode="constant", constant_values=0)
+    window = (pads[0][0], pads[1][0], h + pads[0][0], w + pads[1][0])
+    return image.astype(image_dtype), window, scale, padding, crop
+
+
+def mold_image(images, config):
+    """RGB float image minus MEAN_PIXEL (net.py:1337-1346)."""
+    return images.astype(np.float32) - config.MEAN_PIXEL
+
+
+def unmold_image(normalized_images, config):
+    return (normalized_images + config.MEAN_PIXEL).astype(np.uint8)
+
+
+def compose_image_meta(image_id, original_image_shape, image_shape, window, scale):
+    """12 floats: id, original shape (3), molded shape (3), window (4), scale (net.py:1314-1334)."""
+    return np.array([image_id] + list(original_image_shape) + list(image_shape) + list(window) + [scale])
+
+
+# ------------------------------------------------------------------------------------------------ datasets
+class Dataset(object):
+    """dataset.Dataset: list of per-image info dicts with accessor methods."""
+
+    def __init__(self):
+        self._image_ids = []
+        self.image_info = []
+
+    def add_image(self, source, image_id, path, **kwargs):
+        info = {"id": image_id, "source": source, "path": path}
+        info.update(kwargs)
+        self.image_info.append(info)
+
+    @property
+    def image_ids(self):
+        return self._image_ids
+
+    def source_image_link(self, image_id):
+        return self.image_info[image_id]["path"]
+
+    def load_location(self, image_id):
+        return self.image_info[image_id]["location"]
+
+    def load_quaternion(self, image_id):
+        return self.image_info[image_id]["quaternion"]
+
+    def load_orientation_encoded(self, image_id):
+        return self.image_info[image_id]["ori_map"]
+
+    def load_image(self, image_id):
+        """[H,W,3] uint8 RGB; grayscale replicated, alpha dropped (urso.py:138-153)."""
+        img = cv2.imread(self.image_info[image_id]["path"], cv2.IMREAD_UNCHANGED)
+        if img is None:
+            raise IOError("cannot read " + self.image_info[image_id]["path"])
+        if img.ndim == 2:
+            img = np.stack([img] * 3, -1)
+        elif img.shape[-1] == 4:
+            img = img[..., [2, 1, 0]]
+        else:
+            img = img[..., ::-1]
+        return np.ascontiguousarray(img)
+
+
+class UrsoCamera:
+    fov_x, fov_y = 90.0 * np.pi / 180, 73.7 * np.pi / 180
+    width, height = 1280, 960
+    fx = width / (2 * np.tan(fov_x / 2))
+    fy = -height / (2 * np.tan(fov_y / 2))
+    K = np.array([[fx, 0, width / 2], [0, fy, height / 2], [0, 0, 1]])
+
+
+class SpeedCamera:
+    fx, fy = 0.0176 / 5.86e-6, 0.0176 / 5.86e-6      # speed.py:15-25: f = 17.6 mm, 5.86 um pixels
+    width, height = 1920, 1200
+    K = np.array([[fx, 0, width / 2], [0, fy, height / 2], [0, 0, 1]])
+
+
+def _hemisphere(q):
+    q = np.asarray(q, dtype=np.float32)
+    return -q if q[3] < 0 else q          # injectivity: keep q4 >= 0 (urso.py:57-61)
+
+
+class Urso(Dataset):
+    """URSO layout: <dir>/<subset>_images.csv (one file name per line) + <subset>_poses_gt.csv (x,y,z,q1..q4)."""
+    camera = UrsoCamera()
+
+    def load_dataset(self, dataset_dir, config, subset):
+        import pandas as pd
+        self.name = "Urso"
+        if not os.path.exists(dataset_dir):
+            print("Image directory '" + dataset_dir + "' not found.")
+            return None
+        files = list(pd.read_csv(os.path.join(dataset_dir, subset + "_images.csv"), names=["filename"], header=None)["filename"])
+        poses = pd.read_csv(os.path.join(dataset_dir, subset + "_poses_gt.csv"))
+        q = np.stack([_hemisphere([poses[k][i] for k in ("q1", "q2", "q3", "q4")]) for i in range(len(files))])
+        self._finish(dataset_dir, files, q, np.stack([poses["x"], poses["y"], poses["z"]], 1)[:len(files)], config, "URSO")
+
+    def _finish(self, dataset_dir, files, q, t, config, source):
+        if not config.REGRESS_LOC:
+            raise NotImplementedError("location classification (--classify_loc, experimental) is not built")
+        if not config.REGRESS_ORI:
+            self.encoder = labels.OrientationEncoder(config.ORI_BINS_PER_DIM, config.BETA)
+            enc = self.encoder.encode(q)
+            self.ori_histogram_map, self.ori_output_mask = self.encoder.H_quat, self.encoder.redundant
+        for i, f in enumerate(files):
+            self.add_image(source, image_id=i, path=os.path.join(dataset_dir, f), location=[float(v) for v in t[i]],
+                           quaternion=q[i], ori_map=enc[i] if not config.REGRESS_ORI else [])
+        self.num_images = len(self.image_info)
+        self._image_ids = np.arange(self.num_images)
+
+
+class Speed(Urso):
+    """SPEED layout (speed.py:29-110): <dir>/<subset>.json = [{filename, q_vbs2tango [w,x,y,z], r_Vo2To_vbs_true}],
+    images under <dir>/images/<subset>/."""
+    camera = SpeedCamera()
+
+    def load_dataset(self, dataset_dir, config, subset):
+        self.name = "Speed"
+        with open(os.path.join(dataset_dir, subset + ".json")) as f:
+            items = json.load(f)
+        folder = "real_test" if subset == "real_test" else ("test" if subset == "test" else "train")
+        files = [os.path.join("images", folder, it["filename"]) for it in items]
+        if items and "q_vbs2tango" in items[0]:
+            q = np.stack([_hemisphere([it["q_vbs2tango"][1], it["q_vbs2tango"][2], it["q_vbs2tango"][3],
+                                       it["q_vbs2tango"][0]]) for it in items])
+            t = np.asarray([it["r_Vo2To_vbs_true"] for it in items], dtype=np.float32)
+        else:
+            q = np.tile(np.array([0, 0, 0, 1], np.float32), (len(items), 1))
+            t = np.zeros((len(items), 3), np.float32)
+        self._finish(dataset_dir, files, q, t, config, "SPEED")
+
+
+def write_synthetic_urso(dataset_dir, n_train=4, n_val=2, n_test=2, width=1280, height=960, seed=0):
+    """A tiny URSO-format dataset of random frames (tests / BASELINE config 1: no real data is reachable here)."""
+    rng = np.random.RandomState(seed)
+    os.makedirs(dataset_dir, exist_ok=True)
+    for subset, n in (("train", n_train), ("val", n_val), ("test", n_test)):
+        names, rows = [], []
+        for i in range(n):
+            name = f"{subset}_{i}_rgb.png"
+            img = rng.randint(0, 256, (height // 8, width // 8, 3), dtype=np.uint8)
+            cv2.imwrite(os.path.join(dataset_dir, name), cv2.resize(img, (width, height), interpolation=cv2.INTER_NEAREST))
+            q = rng.randn(4)
+            q /= np.linalg.norm(q)
+            rows.append([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(5, 40)] + list(q))
+            names.append(name)
+        with open(os.path.join(dataset_dir, subset + "_images.csv"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        with open(os.path.join(dataset_dir, subset + "_poses_gt.csv"), "w") as f:
+            f.write("x,y,z,q1,q2,q3,q4\n" + "\n".join(",".join(repr(float(v)) for v in r) for r in rows) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------ batch generator
+def load_image_gt(dataset, config, image_id):
+    """(image uint8 [H,W,3] resized+padded, image_meta, loc, ori) -- net.py:358-456 without the augmentations."""
+    if getattr(config, "ROT_AUG", False) or getattr(config, "ROT_IMAGE_AUG", False):
+        raise NotImplementedError("camera / in-plane rotation augmentation (net.py:409-438) is not built yet")
+    image = dataset.load_image(image_id)
+    loc = dataset.load_location(image_id)
+    ori = dataset.load_quaternion(image_id) if config.REGRESS_ORI else dataset.load_orientation_encoded(image_id)
+    if getattr(config, "SIM2REAL_AUG", False):
+        # luma written back into the uint8 image (net.py:391-394); the stochastic imgaug pipeline is a 'next' row
+        gray = (0.2126 * image[:, :, 0] + 0.7152 * image[:, :, 1] + 0.0722 * image[:, :, 2]).astype(np.uint8)
+        image = np.stack([gray] * 3, -1)
+    original_shape = image.shape
+    image, window, scale, _padding, _crop = resize_image(image, min_dim=config.IMAGE_MIN_DIM, min_scale=config.IMAGE_MIN_SCALE,
+                                                         max_dim=config.IMAGE_MAX_DIM, mode=config.IMAGE_RESIZE_MODE)
+    meta = compose_image_meta(image_id, original_shape, image.shape, window, scale)
+    return image, meta, loc, ori
+
+
+def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False):
+    """Infinite generator of ([images, image_meta, gt_locs, gt_oris], []) like net.data_generator (net.py:458-559).
+    raw_uint8=True yields un-molded uint8 images (the engine subtracts MEAN_PIXEL on the GPU)."""
+    b, image_index, error_count = 0, -1, 0
+    image_ids = np.copy(dataset.image_ids)
+    n_ori = 4 if config.REGRESS_ORI else config.ORI_BINS_PER_DIM ** 3
+    while True:
+        try:
+            image_index = (image_index + 1) % len(image_ids)
+            if shuffle and image_index == 0:
+                np.random.shuffle(image_ids)
+            image_id = image_ids[image_index]
+            image, meta, loc, ori = load_image_gt(dataset, config, image_id)
+            if b == 0:
+                metas = np.zeros((batch_size,) + meta.shape, dtype=meta.dtype)
+                images = np.zeros((batch_size,) + image.shape, dtype=np.uint8 if raw_uint8 else np.float32)
+                locs = np.zeros((batch_size, 3), dtype=np.float32)
+                oris = np.zeros((batch_size, n_ori), dtype=np.float32)
+            metas[b] = meta
+            images[b] = image if raw_uint8 else mold_image(image, config)
+            locs[b], oris[b] = loc, ori
+            b += 1
+            if b >= batch_size:
+                yield [images, metas, locs, oris], []
+                b = 0
+        except (GeneratorExit, KeyboardInterrupt):
+            raise
+        except NotImplementedError:
+            raise
+        except Exception:
+            logging.exception("Error processing image {}".format(dataset.image_info[image_id]))
+            error_count += 1
+            if error_count > 5:
+                raise

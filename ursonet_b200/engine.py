@@ -607,6 +607,28 @@ class Engine:
         ori = self.ori_q if self.graph.ori_mode == "quaternion" else self.head[self.graph.ori_out]
         return self.head["loc_final"], ori
 
+    def eval_losses(self):
+        """Forward + the two weighted head losses on the current input/label buffers, no backward (the validation
+        steps of fit_generator, net.py:1158-1159).  Returns [loc_loss, ori_loss] as Python floats."""
+        g, B, S = self.graph, self.B, lib.stream_ptr
+        wl = float(self.cfg.LOSS_WEIGHTS.get("loc_loss", 1.0))
+        wo = float(self.cfg.LOSS_WEIGHTS.get("ori_loss", 1.0))
+        self._replay("fwd", self._phase_fwd, True)
+        loc = self.head["loc_final"]
+        if g.loc_mode == "regression":
+            lib.call("urso_rel_loss", loc.data_ptr(), self.gt_loc.data_ptr(), None, self.losses[0:1].data_ptr(), B, 3, wl, S())
+        else:
+            lib.call("urso_softmax_xent", loc.data_ptr(), self.gt_loc.data_ptr(), None, self.losses[0:1].data_ptr(), B,
+                     loc.shape[1], wl, S())
+        if g.ori_mode == "quaternion":
+            lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), self.gt_ori.data_ptr(), self.ori_q.data_ptr(), None,
+                     self.losses[1:2].data_ptr(), B, wo, S())
+        else:
+            z = self.head["ori_final"]
+            lib.call("urso_softmax_xent", z.data_ptr(), self.gt_ori.data_ptr(), None, self.losses[1:2].data_ptr(), B,
+                     z.shape[1], wo, S())
+        return self.losses.tolist()
+
     def set_hyper(self, lr, momentum=None, clipnorm=None):
         cfg = self.cfg
         momentum = cfg.LEARNING_MOMENTUM if momentum is None else momentum
