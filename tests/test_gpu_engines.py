@@ -83,18 +83,39 @@ FWD_CASES = [  # kh, stride, padding, cin, cout, h, w, flatten, block_n
 ]
 
 
+@pytest.mark.parametrize("out_fp32", [True, False], ids=["fp32out_regs", "bf16out_tma"])
 @pytest.mark.parametrize("kh,stride,padding,cin,cout,h,w,flatten,block_n", FWD_CASES)
-def test_engine_f_forward(kh, stride, padding, cin, cout, h, w, flatten, block_n):
+def test_engine_f_forward(kh, stride, padding, cin, cout, h, w, flatten, block_n, out_fp32):
+    """fp32 output exercises the register epilogue, bf16 output the TMA-store epilogue (cout >= 64)."""
     nb = 3 if h <= 20 else 8
     x = bf16_exact(nb, h, w, cin, seed=1)
     wk = bf16_exact(kh, kh, cin, cout, scale=0.05, seed=2)
     scale = torch.ones(cout, dtype=torch.float64)
-    got, _, _ = run_fwd(x, wk, scale, kh, stride, padding, out_fp32=True, flatten=flatten, block_n=block_n)
+    got, _, _ = run_fwd(x, wk, scale, kh, stride, padding, out_fp32=out_fp32, flatten=flatten, block_n=block_n)
     ref = ref_fwd(x, staged_kernel(wk, scale), kh, stride, padding)
     assert got.shape == ref.shape
     assert torch.isfinite(got).all(), "output has NaN: some tile was never written"
     err = (got - ref).abs().max().item()
-    assert err <= 2e-3 * ref.abs().max().item(), f"max abs err {err} vs scale {ref.abs().max().item()}"
+    tol = 2e-3 if out_fp32 else 2 ** -8 + 2e-3          # bf16 output rounding
+    assert err <= tol * ref.abs().max().item(), f"max abs err {err} vs scale {ref.abs().max().item()}"
+
+
+@pytest.mark.parametrize("which", ["addend", "mask", "both"])
+@pytest.mark.parametrize("flatten", [True, False])
+def test_engine_f_tma_epilogue_inputs_many_tiles(which, flatten):
+    """more tiles than SMs x prefetch depth, N = 256 (4 chunks/tile): exercises the per-warp input ring phases"""
+    N, H, W, CI, CO = 8, 40, 64, 64, 256
+    x = bf16_exact(N, H, W, CI, seed=21)
+    wk = bf16_exact(1, 1, CI, CO, scale=0.05, seed=22)
+    scale = torch.ones(CO, dtype=torch.float64)
+    addend = bf16_exact(N, H, W, CO, seed=23) if which in ("addend", "both") else None
+    mask = bf16_exact(N, H, W, CO, seed=24) if which in ("mask", "both") else None
+    got, cs, _ = run_fwd(x, wk, scale, 1, 1, "valid", addend=addend, mask=mask, relu=(which != "mask"), colsum=True,
+                         flatten=flatten)
+    ref = ref_fwd(x, staged_kernel(wk, scale), 1, 1, "valid", None, addend, mask, which != "mask")
+    assert (got - ref).abs().max().item() <= (2 ** -8 + 2e-3) * ref.abs().max().item()
+    # column sums are taken over the bf16-rounded stored values
+    assert torch.allclose(cs, got.sum((0, 1, 2)), rtol=2e-3, atol=1e-2 * ref.abs().max().item())
 
 
 def test_engine_f_epilogue_all_stages():
@@ -109,15 +130,16 @@ def test_engine_f_epilogue_all_stages():
     ref = ref_fwd(x, staged_kernel(wk, scale), 3, 1, "same", shift, addend, mask, True)
     tol = 2 ** -8 * ref.abs().max().item() + 1e-3       # bf16 output rounding
     assert (got - ref).abs().max().item() <= tol
-    assert torch.allclose(cs, ref.sum((0, 1, 2)), rtol=1e-3, atol=1e-2 * ref.abs().max().item())
+    assert torch.allclose(cs, got.sum((0, 1, 2)), rtol=2e-3, atol=1e-2 * ref.abs().max().item())
 
 
 DGRAD_CASES = [(1, 1, "valid", 64, 128, 16, 24), (3, 1, "same", 64, 64, 16, 24), (1, 2, "valid", 128, 64, 16, 24),
                (3, 2, "same", 128, 32, 20, 30), (3, 2, 1, 64, 128, 16, 24)]
 
 
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["fp32out_regs", "bf16out_tma"])
 @pytest.mark.parametrize("kh,stride,padding,cin,cout,h,w", DGRAD_CASES)
-def test_engine_f_dgrad(kh, stride, padding, cin, cout, h, w):
+def test_engine_f_dgrad(kh, stride, padding, cin, cout, h, w, out_dtype):
     from ursonet_b200 import lib
     N = 2
     wk = bf16_exact(kh, kh, cin, cout, scale=0.05, seed=7)
@@ -128,7 +150,7 @@ def test_engine_f_dgrad(kh, stride, padding, cin, cout, h, w):
     cop = P.ceil64(cout)
     du_d = torch.zeros(N, g.oh, g.ow, cop, dtype=torch.bfloat16, device=DEV)
     du_d[..., :cout] = du.to(torch.bfloat16).to(DEV)
-    dx = torch.zeros(N, h, w, cin, dtype=torch.float32, device=DEV)
+    dx = torch.zeros(N, h, w, cin, dtype=out_dtype, device=DEV)
     for oph, opw, segs, tap_map in P.dgrad_phases(g):
         tgt = dx[:, oph::stride, opw::stride, :]
         if not segs:
@@ -139,7 +161,8 @@ def test_engine_f_dgrad(kh, stride, padding, cin, cout, h, w):
         plan.launch()
     torch.cuda.synchronize()
     got = dx.double().cpu()
-    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    tol = 2e-3 if out_dtype == torch.float32 else 2 ** -8 + 2e-3
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
 
 
 WGRAD_CASES = [  # kh, stride, padding, cin, cout, h, w, swap

@@ -9,8 +9,15 @@
 //  * both land in 128B-swizzled shared memory and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued by
 //    one thread; fp32 accumulators live in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
 //    tile i+1.
-//  * epilogue warps: tcgen05.ld -> (+shift, +addend, ReLU, mask) -> bf16/fp32 vector stores, optional per-channel
-//    sums (d beta) -- the BatchNorm / bias / ReLU / residual of net.py:103-116 never touch HBM on their own.
+//  * epilogue (4 warps, one TMEM lane quadrant = 32 pixel rows each), per 64-channel chunk:
+//      tcgen05.ld -> +shift -> +addend -> ReLU -> mask -> bf16
+//    ALL global traffic of the epilogue is TMA as well: every warp prefetches its own 32-row slab of the addend /
+//    mask tensors chunks ahead into a private smem ring (so HBM latency never sits on the critical path) and writes
+//    its output slab with a TMA store from a double-buffered smem slab (full 128-byte lines, automatic clipping of
+//    partial tiles, strided views for stride-2 dgrad).  No cross-warp synchronisation in the epilogue.
+//    A legacy register epilogue (direct vector stores) remains for fp32 outputs / BLOCK_N = 32 (bottleneck conv).
+//  * optional fused per-channel sums of the stored output (d beta): read back from the bf16 output slab
+//    (conflict free), accumulated per CTA in shared memory, flushed with one atomic per channel per CTA.
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
 #include "common.cuh"
@@ -30,12 +37,18 @@ struct PixDev {
 struct ConvGemmParams {
   CUtensorMap a_maps[URSO_MAX_AMAPS];
   CUtensorMap b_map;
+  CUtensorMap out_map, add_map, mask_map;   // epilogue slabs: box {64, bw, bh, 1}
   SegDev seg[URSO_MAX_SEGS];
   int n_seg;
   int OW, OH, NB;
   int TW, TH, tw_shift;
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int ncols;
+  int stages;        // mainloop ring depth (runtime: depends on how much smem the epilogue needs)
+  int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
+  int has_add, has_mask;
+  int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
+  int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
   PixDev out, addend, mask;
   int out_fp32, relu;
   const float* shift;
@@ -45,20 +58,15 @@ struct ConvGemmParams {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kTrStride = 36;                       // floats; 144-byte rows: conflict-free STS.128 + column LDS
-constexpr int kColsumScratchBytes = 4 * 32 * kTrStride * 4;
+constexpr int kMaxStages = 8;
+constexpr int kCtrlBytes = 1024;                    // barriers + tmem slot
 constexpr int kMaxColsumCols = 2048;
 constexpr int kColsumAccBytes = kMaxColsumCols * 4;
-
-template <int BLOCK_N>
-struct ConvGemmCfg {
-  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator stages
-  // + per-warp 32x36 fp32 transpose scratch and a per-CTA channel accumulator for the fused d(beta) column sums
-  static constexpr int kSmemBytes = kStages * (kATileBytes + kBTileBytes) + 256 /*barriers*/ + 1024 /*align slack*/ +
-                                    kColsumScratchBytes + kColsumAccBytes;
-};
+constexpr int kSlabBytes = 32 * 128;                // 32 pixel rows x 64 bf16 channels
+constexpr int kMaxEiDepth = 3;                      // per-warp prefetch ring depth (chunks ahead), runtime <= this
+constexpr int kTrStride = 36;                       // legacy colsum transpose scratch (floats per row)
+constexpr int kLegacyScratchBytes = 4 * 32 * kTrStride * 4;
+constexpr int kSmemBudget = 227 * 1024 - 1024;      // minus alignment slack
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
@@ -79,21 +87,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
+template <int BLOCK_N>
+struct ChunkIter {
+  int tile, j, nch, n_tile, img, h0, w0;
+  bool valid;
+  __device__ __forceinline__ void load(const ConvGemmParams& p) {
+    valid = tile < p.total_tiles;
+    if (valid) {
+      decode_tile(p, tile, n_tile, img, h0, w0);
+      const int rem = p.ncols - n_tile * BLOCK_N;
+      nch = (rem < BLOCK_N ? rem : BLOCK_N) / 64;
+    }
+  }
+  __device__ __forceinline__ void init(const ConvGemmParams& p) {
+    tile = blockIdx.x;
+    j = 0;
+    load(p);
+  }
+  __device__ __forceinline__ void next(const ConvGemmParams& p) {
+    if (++j >= nch) {
+      j = 0;
+      tile += gridDim.x;
+      load(p);
+    }
+  }
+};
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kTmemCols = 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kStages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kATileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBTileBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint8_t* ctrl = sB + kStages * kBTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
-  float* s_colacc = s_tr + 4 * 32 * kTrStride;
+  uint64_t* ei_bar = tempty_bar + 2;                       // [4 warps][kMaxEiDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 4 * kMaxEiDepth);
+  float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
+  float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + kColsumAccBytes);   // legacy epilogue only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +139,11 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.a_maps[i]);
     tma_prefetch_desc(&p.b_map);
+    if (p.epi_tma) {
+      tma_prefetch_desc(&p.out_map);
+      tma_prefetch_desc(&p.add_map);
+      tma_prefetch_desc(&p.mask_map);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -111,9 +154,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
+    for (int i = 0; i < 4 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   if (p.colsum != nullptr) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
   }
@@ -135,10 +179,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + Cfg::kBTileBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
             tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
                         h0 + sg.dh, img);
-            tma_load_2d(sB + stage * Cfg::kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+            tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
             kcol += kBlockK;
             if (++stage == kStages) {
               stage = 0;
@@ -167,7 +211,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kATileBytes);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBTileBytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBTileBytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // K-major SW128: advancing 16 elements = 32 bytes inside the 128B swizzle row
@@ -188,108 +232,249 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     // ------------------------------------------------------------------ epilogue (128 threads <-> 128 TMEM lanes)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      int n_tile, img, h0, w0;
-      decode_tile(p, tile, n_tile, img, h0, w0);
-      const int h = h0 + (row >> p.tw_shift);
-      const int w = w0 + (row & (p.TW - 1));
-      const bool valid = (h < p.OH) && (w < p.OW);
-      const long long o_off = (long long)img * p.out.sn + (long long)h * p.out.sh + (long long)w * p.out.sw;
-      const long long a_off = (long long)img * p.addend.sn + (long long)h * p.addend.sh + (long long)w * p.addend.sw;
-      const long long m_off = (long long)img * p.mask.sn + (long long)h * p.mask.sh + (long long)w * p.mask.sw;
-
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < BLOCK_N / 32; ++j) {
-        const int col0 = n_tile * BLOCK_N + j * 32;
-        if (col0 >= p.ncols) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 32, acc);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-        if (p.shift != nullptr) {
-          const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 s4 = __ldg(sp + i);
-            v[4 * i + 0] += s4.x;
-            v[4 * i + 1] += s4.y;
-            v[4 * i + 2] += s4.z;
-            v[4 * i + 3] += s4.w;
-          }
-        }
-        if (p.addend.ptr != nullptr && valid) {
-          const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.addend.ptr) + a_off + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u = ap[i];
-            v[8 * i + 0] += bf16_lo(u.x);
-            v[8 * i + 1] += bf16_hi(u.x);
-            v[8 * i + 2] += bf16_lo(u.y);
-            v[8 * i + 3] += bf16_hi(u.y);
-            v[8 * i + 4] += bf16_lo(u.z);
-            v[8 * i + 5] += bf16_hi(u.z);
-            v[8 * i + 6] += bf16_lo(u.w);
-            v[8 * i + 7] += bf16_hi(u.w);
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-        }
-        if (p.mask.ptr != nullptr && valid) {
-          const uint4* mp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask.ptr) + m_off + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u = mp[i];
-            v[8 * i + 0] = bf16_lo(u.x) > 0.0f ? v[8 * i + 0] : 0.0f;
-            v[8 * i + 1] = bf16_hi(u.x) > 0.0f ? v[8 * i + 1] : 0.0f;
-            v[8 * i + 2] = bf16_lo(u.y) > 0.0f ? v[8 * i + 2] : 0.0f;
-            v[8 * i + 3] = bf16_hi(u.y) > 0.0f ? v[8 * i + 3] : 0.0f;
-            v[8 * i + 4] = bf16_lo(u.z) > 0.0f ? v[8 * i + 4] : 0.0f;
-            v[8 * i + 5] = bf16_hi(u.z) > 0.0f ? v[8 * i + 5] : 0.0f;
-            v[8 * i + 6] = bf16_lo(u.w) > 0.0f ? v[8 * i + 6] : 0.0f;
-            v[8 * i + 7] = bf16_hi(u.w) > 0.0f ? v[8 * i + 7] : 0.0f;
-          }
-        }
-        if (valid) {
-          if (p.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out.ptr) + o_off + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out.ptr) + o_off + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              op[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
-          }
-        }
-        if (p.colsum != nullptr) {
-          // per-channel sums: transpose the warp's 32x32 block through shared memory, each lane sums one column,
-          // accumulate per CTA in shared memory (flushed to HBM once per CTA at the end: no hot global atomics)
-          float* tr = s_tr + q * 32 * kTrStride;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(tr + lane * kTrStride + 4 * i) =
-                valid ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          __syncwarp();
-          float s = 0.0f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) s += tr[r * kTrStride + lane];
-          atomicAdd(&s_colacc[col0 + lane], s);
-          __syncwarp();
-        }
+    const int rh = row >> p.tw_shift, rw = row & (p.TW - 1);
+    if (p.epi_tma) {
+      // ---------------- TMA epilogue
+      const int slab_h = (q * 32) >> p.tw_shift, slab_w = (q * 32) & (p.TW - 1);   // slab origin inside the patch
+      const int n_in = p.has_add + p.has_mask;
+      const int slot_bytes = n_in * kSlabBytes;
+      const int kEiDepth = p.ei_depth;
+      uint8_t* ei = smem + p.ei_off + q * kEiDepth * slot_bytes;
+      uint8_t* eo = smem + p.eo_off + q * 2 * kSlabBytes;
+      uint64_t* my_bar = ei_bar + q * kMaxEiDepth;
+      const int swz = lane & 7;
+      ChunkIter<BLOCK_N> cur, pf;
+      cur.init(p);
+      pf = cur;
+      int n_pf = 0;   // chunks prefetched so far
+      auto issue_prefetch = [&]() {   // lane 0 only
+        const int slot = n_pf % kEiDepth;
+        uint8_t* dst = ei + slot * slot_bytes;
+        mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
+        const int c = pf.n_tile * BLOCK_N + pf.j * 64;
+        if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
+        if (p.has_mask)
+          tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
+        ++n_pf;
+        pf.next(p);
+      };
+      if (n_in > 0 && lane == 0) {
+        for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      int n_done = 0;   // chunks consumed so far
+      int it = 0;
+      for (; cur.valid; ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int h = cur.h0 + rh, w = cur.w0 + rw;
+        const bool valid = (h < p.OH) && (w < p.OW);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const int nch = cur.nch;
+        for (int j = 0; j < nch; ++j, ++n_done) {
+          const int col0 = cur.n_tile * BLOCK_N + j * 64;
+          const int slot = n_done % kEiDepth;
+          uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
+          uint8_t* out_slab = eo + (n_done & 1) * kSlabBytes;
+          if (n_in > 0) mbar_wait(&my_bar[slot], (n_done / kEiDepth) & 1);
+          if (n_done >= 2) {   // the TMA store that last read this output slab must have drained it
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 64 + half * 32, acc);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+            if (p.shift != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 s4 = __ldg(sp + i);
+                v[4 * i + 0] += s4.x;
+                v[4 * i + 1] += s4.y;
+                v[4 * i + 2] += s4.z;
+                v[4 * i + 3] += s4.w;
+              }
+            }
+            if (p.has_add) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(in_slab + (((half * 4 + i) ^ swz) << 4));
+                v[8 * i + 0] += bf16_lo(u.x);
+                v[8 * i + 1] += bf16_hi(u.x);
+                v[8 * i + 2] += bf16_lo(u.y);
+                v[8 * i + 3] += bf16_hi(u.y);
+                v[8 * i + 4] += bf16_lo(u.z);
+                v[8 * i + 5] += bf16_hi(u.z);
+                v[8 * i + 6] += bf16_lo(u.w);
+                v[8 * i + 7] += bf16_hi(u.w);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            if (p.has_mask) {
+              const uint8_t* ms = in_slab + p.has_add * kSlabBytes;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(ms + (((half * 4 + i) ^ swz) << 4));
+                v[8 * i + 0] = bf16_lo(u.x) > 0.0f ? v[8 * i + 0] : 0.0f;
+                v[8 * i + 1] = bf16_hi(u.x) > 0.0f ? v[8 * i + 1] : 0.0f;
+                v[8 * i + 2] = bf16_lo(u.y) > 0.0f ? v[8 * i + 2] : 0.0f;
+                v[8 * i + 3] = bf16_hi(u.y) > 0.0f ? v[8 * i + 3] : 0.0f;
+                v[8 * i + 4] = bf16_lo(u.z) > 0.0f ? v[8 * i + 4] : 0.0f;
+                v[8 * i + 5] = bf16_hi(u.z) > 0.0f ? v[8 * i + 5] : 0.0f;
+                v[8 * i + 6] = bf16_lo(u.w) > 0.0f ? v[8 * i + 6] : 0.0f;
+                v[8 * i + 7] = bf16_hi(u.w) > 0.0f ? v[8 * i + 7] : 0.0f;
+              }
+            }
+            // rows outside the image are clipped by the TMA store; zero them so the column sums ignore them
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+              if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(out_slab + lane * 128 + (((half * 4 + i) ^ swz) << 4)) = o;
+            }
+          }
+          if (j == nch - 1) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (p.colsum != nullptr) {
+            // lane l sums channel pair l of this chunk over the 32 rows of the bf16 output slab (conflict free:
+            // at a fixed row the 32 lanes read the 32 distinct words of one 128-byte line)
+            float s0 = 0.f, s1 = 0.f;
+            const int c16 = lane >> 2, wsel = (lane & 3) << 2;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(out_slab + r * 128 + ((c16 ^ (r & 7)) << 4) + wsel);
+              s0 += bf16_lo(u);
+              s1 += bf16_hi(u);
+            }
+            atomicAdd(&s_colacc[col0 + 2 * lane], s0);
+            atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1);
+          }
+          if (lane == 0) {
+            tma_store_4d(&p.out_map, out_slab, col0, cur.w0 + slab_w, cur.h0 + slab_h, cur.img);
+            tma_store_commit();
+            if (n_in > 0 && pf.valid) issue_prefetch();   // refill the input slot just consumed
+          }
+        }
+        // advance to the next tile of this CTA
+        cur.j = cur.nch - 1;
+        cur.next(p);
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
+      // ---------------- legacy register epilogue (fp32 output / BLOCK_N == 32)
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        int n_tile, img, h0, w0;
+        decode_tile(p, tile, n_tile, img, h0, w0);
+        const int h = h0 + rh, w = w0 + rw;
+        const bool valid = (h < p.OH) && (w < p.OW);
+        const long long o_off = (long long)img * p.out.sn + (long long)h * p.out.sh + (long long)w * p.out.sw;
+        const long long a_off = (long long)img * p.addend.sn + (long long)h * p.addend.sh + (long long)w * p.addend.sw;
+        const long long m_off = (long long)img * p.mask.sn + (long long)h * p.mask.sh + (long long)w * p.mask.sw;
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_N / 32; ++j) {
+          const int col0 = n_tile * BLOCK_N + j * 32;
+          if (col0 >= p.ncols) break;  // warp-uniform
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 32, acc);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+          if (p.shift != nullptr) {
+            const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 s4 = __ldg(sp + i);
+              v[4 * i + 0] += s4.x;
+              v[4 * i + 1] += s4.y;
+              v[4 * i + 2] += s4.z;
+              v[4 * i + 3] += s4.w;
+            }
+          }
+          if (p.addend.ptr != nullptr && valid) {
+            const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.addend.ptr) + a_off + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = ap[i];
+              v[8 * i + 0] += bf16_lo(u.x);
+              v[8 * i + 1] += bf16_hi(u.x);
+              v[8 * i + 2] += bf16_lo(u.y);
+              v[8 * i + 3] += bf16_hi(u.y);
+              v[8 * i + 4] += bf16_lo(u.z);
+              v[8 * i + 5] += bf16_hi(u.z);
+              v[8 * i + 6] += bf16_lo(u.w);
+              v[8 * i + 7] += bf16_hi(u.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
+          if (p.mask.ptr != nullptr && valid) {
+            const uint4* mp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask.ptr) + m_off + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = mp[i];
+              v[8 * i + 0] = bf16_lo(u.x) > 0.0f ? v[8 * i + 0] : 0.0f;
+              v[8 * i + 1] = bf16_hi(u.x) > 0.0f ? v[8 * i + 1] : 0.0f;
+              v[8 * i + 2] = bf16_lo(u.y) > 0.0f ? v[8 * i + 2] : 0.0f;
+              v[8 * i + 3] = bf16_hi(u.y) > 0.0f ? v[8 * i + 3] : 0.0f;
+              v[8 * i + 4] = bf16_lo(u.z) > 0.0f ? v[8 * i + 4] : 0.0f;
+              v[8 * i + 5] = bf16_hi(u.z) > 0.0f ? v[8 * i + 5] : 0.0f;
+              v[8 * i + 6] = bf16_lo(u.w) > 0.0f ? v[8 * i + 6] : 0.0f;
+              v[8 * i + 7] = bf16_hi(u.w) > 0.0f ? v[8 * i + 7] : 0.0f;
+            }
+          }
+          if (valid) {
+            if (p.out_fp32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out.ptr) + o_off + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out.ptr) + o_off + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                op[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+          if (p.colsum != nullptr) {
+            float* tr = s_tr + q * 32 * kTrStride;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(tr + lane * kTrStride + 4 * i) =
+                  valid ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            float s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) s += tr[r * kTrStride + lane];
+            atomicAdd(&s_colacc[col0 + lane], s);
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
     }
     if (p.colsum != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
@@ -304,7 +489,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -315,20 +500,31 @@ struct urso_convgemm {
   urso::ConvGemmParams params;
   int block_n;
   int grid;
+  int smem_bytes;
 };
 
 template <int BLOCK_N>
 static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
-  using Cfg = urso::ConvGemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
     URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::kSmemBytes));
+                                      227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 256, Cfg::kSmemBytes, stream>>>(h->params);
+  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 256, h->smem_bytes, stream>>>(h->params);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int make_pix_map(CUtensorMap* out, const urso_pix& px, int C, int W, int H, int N, int bw, int bh) {
+  urso_view4 v;
+  v.base = px.ptr;
+  v.C = C; v.W = W; v.H = H; v.N = N;
+  v.stride_w = px.sw; v.stride_h = px.sh; v.stride_n = px.sn;
+  // size-1 dimensions may carry arbitrary strides (torch views): give them a legal multiple of 16 bytes
+  if (H == 1) v.stride_h = (int64_t)W * px.sw;
+  if (N == 1) v.stride_n = (int64_t)(H == 1 ? 1 : H) * v.stride_h;
+  return urso::make_view_map(out, v, bw, bh);
 }
 
 extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t** out) {
@@ -375,10 +571,55 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     delete h;
     return 2;
   }
+  // epilogue flavour and shared-memory plan
+  p.has_add = d->addend.ptr != nullptr;
+  p.has_mask = d->mask.ptr != nullptr;
+  p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
+  int epi_bytes;
+  if (p.epi_tma) {
+    p.ei_depth = (p.has_add + p.has_mask) == 2 ? 2 : kMaxEiDepth;
+    const int ei_bytes = 4 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
+    epi_bytes = ei_bytes + 4 * 2 * kSlabBytes;
+    if (bn == 256 && kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes < 3 * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
+  } else {
+    epi_bytes = kLegacyScratchBytes;
+  }
   h->block_n = bn;
+  const int stage_bytes = kATileBytes + bn * kBlockK * 2;
+  int stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) {
+    set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
+    delete h;
+    return 2;
+  }
+  p.stages = stages;
+  const int fixed = stages * stage_bytes + kCtrlBytes + kColsumAccBytes;
+  if (p.epi_tma) {
+    p.ei_off = (fixed + 1023) / 1024 * 1024;
+    p.eo_off = p.ei_off + 4 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
+    h->smem_bytes = p.eo_off + 4 * 2 * kSlabBytes + 1024;
+  } else {
+    h->smem_bytes = fixed + kLegacyScratchBytes + 1024;
+  }
+  if (h->smem_bytes > 227 * 1024) {
+    set_error("internal: shared memory plan %d bytes exceeds 227 KB", h->smem_bytes);
+    delete h;
+    return 2;
+  }
   if (int rc = make_mat_map(&p.b_map, d->b, d->b_rows, d->b_k, bn)) {
     delete h;
     return rc;
+  }
+  if (p.epi_tma) {
+    const int bw = d->TW < 32 ? d->TW : 32, bh = 32 / bw;
+    int rc = make_pix_map(&p.out_map, d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
+    if (!rc) rc = make_pix_map(&p.add_map, p.has_add ? d->addend : d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
+    if (!rc) rc = make_pix_map(&p.mask_map, p.has_mask ? d->mask : d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
+    if (rc) {
+      delete h;
+      return rc;
+    }
   }
   p.n_seg = d->n_seg;
   p.OW = d->OW; p.OH = d->OH; p.NB = d->NB;
