@@ -19,6 +19,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 
 TRAIN_GFLOP_PER_IMG = 281.02      # BASELINE.md section 2 (cfg2/cfg5): fwd + dgrad + wgrad, 2 FLOP/MAC
 

@@ -110,7 +110,9 @@ int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, c
 /* ---- MaxPooling2D 3x3/s2 'same' on even maps (net.py:176,258): TF pads bottom/right only. bf16 NHWC.
  * argmax (uint8 [B,H/2,W/2,C], may be NULL for inference) records the FIRST maximum of each window (dr*3+ds). */
 int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
-/* dx = (x>0) * scatter(dy to the recorded argmax): TF MaxPoolGrad fused with the stem's ReLU mask. */
+/* dx = scatter(dy to the recorded argmax) (TF MaxPoolGrad).  x (the pooled tensor's input) may be NULL when dy is
+ * already masked by (pooled > 0) -- equivalent to the stem's ReLU mask, since a window's max is 0 only if all its
+ * (post-ReLU) inputs are 0; otherwise dx is additionally masked by x > 0. */
 int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
                      int32_t C, void* stream);
 
@@ -151,11 +153,12 @@ int urso_stage_weight_cols(const float* w, const float* scale, void* out, const 
                            int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, int64_t ld_out, void* stream);
 /* From the raw wgrad G[R'][CO] (fp32; row r of the HWIO kernel lives at G row g_row_map[r], identity if NULL) and
  * colsum[c] = sum_pixels du: dW = scale*G, dbias = scale*colsum, dbeta = colsum,
- * dgamma = rstd*(sum_r W[r,c]*G[r,c] + (bias-mean)*colsum).  gamma == NULL: no BN; dbias == NULL: no bias. */
+ * dgamma = rstd*(sum_r W[r,c]*G[r,c] + (bias-mean)*colsum).  gamma == NULL: no BN; dbias == NULL: no bias.
+ * s_scratch: zeroed fp32 [CO] accumulator for sum_r W*G (needed when gamma != NULL). */
 int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const float* w, const float* colsum,
                           const float* scale, const float* gamma, const float* mean, const float* var,
-                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta, int32_t R,
-                          int32_t CO, void* stream);
+                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta,
+                          float* s_scratch, int32_t R, int32_t CO, void* stream);
 
 /* ---- Optimizer (net.py:979-983,1008-1012; Keras-2 SGD / Adam(amsgrad) with global-norm clipnorm) over flat arenas.
  * chunk_coef[i] applies to elements [256 i, 256 i + 256): reg gradient 2*wd/size(w) (0 for gamma/beta);

@@ -46,6 +46,12 @@ def test_maxpool_fwd_bwd():
     frac_bad = (diff > 1e-2).double().mean().item()
     assert frac_bad < 0.02, frac_bad
     assert abs(got.sum().item() - gref.sum().item()) <= 1e-2 * gref.abs().sum().item()
+    # x == NULL with dy pre-masked by (pooled > 0) gives the same result (how the engine calls it)
+    dym = torch.where(y > 0, dyd, torch.zeros_like(dyd))
+    dx2 = torch.empty_like(xd)
+    lib.call("urso_maxpool_bwd", None, am.data_ptr(), dym.data_ptr(), dx2.data_ptr(), B, H, W, C, lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx)
 
 
 @pytest.mark.parametrize("B,K,N,act", [(4, 640, 1024, 1), (32, 4800, 1024, 1), (32, 1024, 3, 0), (5, 1024, 4096, 1),
@@ -167,9 +173,10 @@ def test_bn_fold_stage_and_param_grads():
     colsum = du.sum((0, 1, 2))
     dW, dbias, dgamma, dbeta = (torch.empty(n, device=DEV) for n in (kh * kh * CI * CO, CO, CO, CO))
     Gd, cd = d(G.float()), d(colsum.float())
+    scratch = torch.zeros(CO, device=DEV)
     lib.call("urso_conv_param_grads", Gd.data_ptr(), None, wd.data_ptr(), cd.data_ptr(), scale.data_ptr(), gd.data_ptr(),
              md.data_ptr(), vd.data_ptr(), biasd.data_ptr(), 1e-3, dW.data_ptr(), dbias.data_ptr(), dgamma.data_ptr(),
-             dbeta.data_ptr(), kh * kh * CI, CO, s)
+             dbeta.data_ptr(), scratch.data_ptr(), kh * kh * CI, CO, s)
     torch.cuda.synchronize()
     assert torch.allclose(dW.double().cpu().reshape(gw.shape), gw, rtol=1e-4, atol=1e-4)
     assert torch.allclose(dbias.double().cpu(), gbias, rtol=1e-4, atol=1e-4)

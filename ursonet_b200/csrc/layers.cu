@@ -161,11 +161,16 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const ui
           if (ai[j] == code) acc[j] += __bfloat162float(g[j]);
       }
     }
-    const uint4 xv = *reinterpret_cast<const uint4*>(x + i * 8);
-    const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
     __nv_bfloat16 o8[8];
+    if (x != nullptr) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(x + i * 8);
+      const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(__bfloat162float(xe[j]) > 0.f ? acc[j] : 0.f);
+      for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(__bfloat162float(xe[j]) > 0.f ? acc[j] : 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(acc[j]);
+    }
     *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<uint4*>(o8);
   }
 }
@@ -267,28 +272,41 @@ __global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restric
   }
 }
 
-// dx[b, k] = sum_n dy[b,n] w[k,n].  One warp per k row, 32 batch rows at a time.
+// dx[b, k] = sum_n dy[b,n] w[k,n].  Block = 8 warps = 8 k rows; dy is staged through shared memory in [32 b][128 n]
+// tiles shared by the 8 warps (8x fewer L2 reads than one warp per row reading dy on its own).
 __global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, int B, int K, int N) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= K) return;
-  const float* wr = w + (long long)warp * N;
+  __shared__ float dys[32][128 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  const float* wr = w + (long long)(k < K ? k : 0) * N;
   for (int b0 = 0; b0 < B; b0 += 32) {
     float acc[32];
 #pragma unroll
     for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-    const int bend = min(32, B - b0);
-    for (int n = lane; n < N; n += 32) {
-      const float wv = __ldg(wr + n);
+    for (int n0 = 0; n0 < N; n0 += 128) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+        const int bb = i >> 7, nn = i & 127;
+        dys[bb][nn] = (b0 + bb < B && n0 + nn < N) ? dy[(long long)(b0 + bb) * N + n0 + nn] : 0.f;
+      }
+      __syncthreads();
+      if (k < K) {
 #pragma unroll
-      for (int b = 0; b < 32; ++b)
-        if (b < bend) acc[b] += wv * __ldg(dy + (long long)(b0 + b) * N + n);
+        for (int t = 0; t < 4; ++t) {
+          const int nn = t * 32 + lane;
+          const float wv = (n0 + nn < N) ? __ldg(wr + n0 + nn) : 0.f;
+#pragma unroll
+          for (int b = 0; b < 32; ++b) acc[b] += wv * dys[b][nn];
+        }
+      }
     }
+    if (k < K) {
 #pragma unroll
-    for (int b = 0; b < 32; ++b) {
-      const float s = warp_sum(acc[b]);
-      if (lane == 0 && b < bend) dx[(long long)(b0 + b) * K + warp] = s;
+      for (int b = 0; b < 32; ++b) {
+        const float sres = warp_sum(acc[b]);
+        if (lane == 0 && b0 + b < B) dx[(long long)(b0 + b) * K + k] = sres;
+      }
     }
   }
 }
@@ -422,7 +440,7 @@ int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H,
 
 int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
                      int32_t C, void* stream) {
-  URSO_REQUIRE(x && argmax && dy && dx, "null pointer");
+  URSO_REQUIRE(argmax && dy && dx, "null pointer");
   const long long total = (long long)B * H * W * (C / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(argmax), static_cast<const __nv_bfloat16*>(dy),

@@ -61,42 +61,53 @@ __global__ void stage_weight_cols_kernel(const float* __restrict__ w, const floa
   }
 }
 
-// Per output channel co (one warp each):  S = sum_r W[r,co] * G[grow(r),co]
-//   dgamma = rstd * (S + (bias - mean) * colsum) ; dbeta = colsum ; dbias = scale * colsum
-// and for all r: dW[r,co] = scale[co] * G[grow(r), co].
+// dW[r,co] = scale[co] * G[grow(r),co] for a slab of rows, and S[co] += sum_{r in slab} W[r,co] * G[grow(r),co]
+// (block = 32 channels x 8 row lanes, grid = channel blocks x row slabs: enough CTAs to fill the chip even for CO = 64).
 __global__ void __launch_bounds__(256) conv_param_grads_kernel(
     const float* __restrict__ G, const int* __restrict__ g_row_map, const float* __restrict__ w,
-    const float* __restrict__ colsum, const float* __restrict__ scale, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ bias, float eps,
-    float* __restrict__ dW, float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta, int R,
-    int CO) {
-  // block = 32 channels (x) x 8 row-lanes (y): coalesced along co
+    const float* __restrict__ scale, float* __restrict__ dW, float* __restrict__ S, int R, int CO, int rows_per_slab,
+    int need_s) {
   __shared__ float red[8][33];
   const int co = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(R, r0 + rows_per_slab);
   const float sc = (co < CO && scale != nullptr) ? scale[co] : 1.f;
   float s = 0.f;
   if (co < CO) {
-    for (int r = threadIdx.y; r < R; r += 8) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
       const int gr = g_row_map != nullptr ? g_row_map[r] : r;
       const float g = G[(long long)gr * CO + co];
       s += w[(long long)r * CO + co] * g;
       dW[(long long)r * CO + co] = sc * g;
     }
   }
+  if (!need_s) return;
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && co < CO) {
-    float S = 0.f;
+    float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) S += red[j][threadIdx.x];
-    const float cs = colsum != nullptr ? colsum[co] : 0.f;
-    if (dbias != nullptr) dbias[co] = sc * cs;
-    if (gamma != nullptr) {
-      const float rstd = rsqrtf(var[co] + eps);
-      const float b = bias != nullptr ? bias[co] : 0.f;
-      dgamma[co] = rstd * (S + (b - mean[co]) * cs);
-      dbeta[co] = cs;
-    }
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    atomicAdd(S + co, t);
+  }
+}
+
+// dgamma = rstd * (S + (bias - mean) * colsum) ; dbeta = colsum ; dbias = scale * colsum
+__global__ void bn_param_finalize_kernel(const float* __restrict__ S, const float* __restrict__ colsum,
+                                         const float* __restrict__ scale, const float* __restrict__ gamma,
+                                         const float* __restrict__ mean, const float* __restrict__ var,
+                                         const float* __restrict__ bias, float eps, float* __restrict__ dbias,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int CO) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= CO) return;
+  const float cs = colsum != nullptr ? colsum[co] : 0.f;
+  const float sc = scale != nullptr ? scale[co] : 1.f;
+  if (dbias != nullptr) dbias[co] = sc * cs;
+  if (gamma != nullptr) {
+    const float rstd = rsqrtf(var[co] + eps);
+    const float b = bias != nullptr ? bias[co] : 0.f;
+    dgamma[co] = rstd * (S[co] + (b - mean[co]) * cs);
+    dbeta[co] = cs;
   }
 }
 
@@ -277,14 +288,26 @@ int urso_stage_weight_cols(const float* w, const float* scale, void* out, const 
 
 int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const float* w, const float* colsum,
                           const float* scale, const float* gamma, const float* mean, const float* var,
-                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta, int32_t R,
-                          int32_t CO, void* stream) {
+                          const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta,
+                          float* s_scratch, int32_t R, int32_t CO, void* stream) {
   URSO_REQUIRE(G && w && dW, "null pointer");
-  URSO_REQUIRE(gamma == nullptr || (mean && var && dgamma && dbeta && colsum), "BN gradients need mean/var/colsum");
+  URSO_REQUIRE(gamma == nullptr || (mean && var && dgamma && dbeta && colsum && s_scratch),
+               "BN gradients need mean/var/colsum and a zeroed [CO] scratch");
   URSO_REQUIRE(dbias == nullptr || colsum != nullptr, "bias gradient needs colsum");
-  dim3 block(32, 8);
-  conv_param_grads_kernel<<<(CO + 31) / 32, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      G, g_row_map_dev, w, colsum, scale, gamma, mean, var, bias, eps, dW, dbias, dgamma, dbeta, R, CO);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cblocks = (CO + 31) / 32;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  int slabs = (2 * sms + cblocks - 1) / cblocks;
+  if (slabs > (R + 7) / 8) slabs = (R + 7) / 8;
+  if (slabs < 1) slabs = 1;
+  const int rps = (R + slabs - 1) / slabs;
+  dim3 block(32, 8), grid(cblocks, (R + rps - 1) / rps);
+  conv_param_grads_kernel<<<grid, block, 0, st>>>(G, g_row_map_dev, w, scale, dW, s_scratch, R, CO, rps,
+                                                  gamma != nullptr ? 1 : 0);
+  if (gamma != nullptr || dbias != nullptr)
+    bn_param_finalize_kernel<<<(CO + 127) / 128, 128, 0, st>>>(s_scratch, colsum, scale, gamma, mean, var, bias, eps,
+                                                              dbias, dgamma, dbeta, CO);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -378,7 +378,7 @@ class Engine:
                 self.dact[X] = self._new((B, h, w, c))
                 key = colsum_for(X)
                 self.ops_bwd.append(OpRec(lambda X=X, h=h, w=w, c=c, key=key: (
-                    lib.call("urso_maxpool_bwd", self.act[X].data_ptr(), self.argmax.data_ptr(),
+                    lib.call("urso_maxpool_bwd", None, self.argmax.data_ptr(),
                              self.dact["pool1"].data_ptr(), self.dact[X].data_ptr(), B, h, w, c, S()),
                     lib.call("urso_colsum_bf16", self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B * h * w, c,
                              S())), "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 3.5, 2))
@@ -411,7 +411,9 @@ class Engine:
         self.dact[X] = self._new((B, h, w, cin))
         key = colsum_for(X) if need_cs else None
         self.colsum[X] = key
-        mask = self.act[X] if X in g.relu_buffers else None
+        # pool1 = max of post-ReLU values: masking its gradient by (pool1 > 0) IS the stem's ReLU mask (a window's max
+        # is 0 only when all its inputs are 0), so the max-pool backward does not have to read the stem output
+        mask = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
         addend = self.dact[adds[0].dst] if adds else None
         geoms = [P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w) for c in convs]
         phases = [P.dgrad_phases(gm) for gm in geoms]
@@ -496,6 +498,9 @@ class Engine:
             row_map = None
         gkey = "G:" + c.name
         self._zero_specs.append((gkey, n_rows * c.cout))
+        skey = "S:" + c.name
+        if c.bn:
+            self._zero_specs.append((skey, c.cout))
         swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout
         flat = (not c.stem) and c.k == 1 and c.stride == 1
         box = {}
@@ -531,8 +536,9 @@ class Engine:
             cs = self._zero_view(cs_key) if cs_key else None
             lib.call("urso_conv_param_grads", self._zero_view(gkey).data_ptr(), lib.ptr(row_map), w.data_ptr(),
                      lib.ptr(cs), sc.data_ptr(), lib.ptr(bn[0]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
-                     dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta), R, c.cout, S())
-        self.ops_bwd.append(run)
+                     dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta),
+                     self._zero_view(skey).data_ptr() if c.bn else None, R, c.cout, S())
+        self.ops_bwd.append(OpRec(run, "param_grads", c.name, 0.0, 12.0 * R * c.cout, 2))
 
     def _build_update(self):
         S = lib.stream_ptr

@@ -69,7 +69,7 @@ SIGNATURES = {
     "urso_bn_fold": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
     "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp],
     "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
-    "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 4 + [_i32, _i32, _vp],
+    "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 5 + [_i32, _i32, _vp],
     "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "urso_amsgrad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
