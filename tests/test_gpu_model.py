@@ -155,7 +155,9 @@ def local_backward_check(eng, p64, cfg):
             tot = tot + torch.autograd.grad(y, x, du)[0]
         for c in adds.get(X, []):
             tot = tot + eng.dact[c.dst].double().cpu()
-        if X in g.relu_buffers:
+        # pool1 is masked too: (pool1 > 0) is exactly the stem's ReLU mask seen through the max (engine.py), which lets
+        # the pool backward skip re-reading the stem output
+        if X in g.relu_buffers or X == "pool1":
             tot = tot * (x.detach() > 0)
         got = eng.dact[X].double().cpu()
         e = (got - tot).norm().item() / max(tot.norm().item(), 1e-30)

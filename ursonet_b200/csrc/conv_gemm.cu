@@ -19,7 +19,8 @@
 //  * optional fused per-channel sums of the stored output (d beta): read back from the bf16 output slab
 //    (conflict free), accumulated per CTA in shared memory, flushed with one atomic per channel per CTA.
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue
+// (4 TMEM lane quadrants x 2 column halves).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -115,7 +116,7 @@ struct ChunkIter {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   constexpr int kTmemCols = 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
     }
     for (int i = 0; i < 4 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     fence_barrier_init();
@@ -228,9 +229,12 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (128 threads <-> 128 TMEM lanes)
+  } else if (warp >= 4 && (p.epi_tma || warp < 8)) {
+    // ------------------------------------------------------------------ epilogue
+    // TMA flavour: 8 warps = 4 TMEM lane quadrants x 2 column halves (two warps share each 32-row x 64-channel
+    // slab: more warps per scheduler hide the ALU latency of the elementwise work).  Legacy flavour: warps 4-7 only.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int rh = row >> p.tw_shift, rw = row & (p.TW - 1);
     if (p.epi_tma) {
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         ++n_pf;
         pf.next(p);
       };
-      if (n_in > 0 && lane == 0) {
+      if (n_in > 0 && half == 0 && lane == 0) {
         for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
       }
       int n_done = 0;   // chunks consumed so far
@@ -277,12 +281,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
           uint8_t* out_slab = eo + (n_done & 1) * kSlabBytes;
           if (n_in > 0) mbar_wait(&my_bar[slot], (n_done / kEiDepth) & 1);
-          if (n_done >= 2) {   // the TMA store that last read this output slab must have drained it
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          if (n_done >= 2 && half == 0 && lane == 0) tma_store_wait_read<1>();   // this output slab has been drained
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");              // #1 (pair of warps sharing the slab)
+          {
             uint32_t acc[32];
             tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 64 + half * 32, acc);
             tmem_ld_wait();
@@ -314,30 +315,34 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 v[8 * i + 7] += bf16_hi(u.w);
               }
             }
-            if (p.relu) {
+            // pack to bf16 first; ReLU and the ReLU-backward mask are exact on the packed values
+            uint32_t pk[16];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            if (p.relu) {
+              const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __nv_bfloat162 t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[i]), z2);
+                pk[i] = *reinterpret_cast<uint32_t*>(&t);
+              }
             }
             if (p.has_mask) {
               const uint8_t* ms = in_slab + p.has_add * kSlabBytes;
+              const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint4 u = *reinterpret_cast<const uint4*>(ms + (((half * 4 + i) ^ swz) << 4));
-                v[8 * i + 0] = bf16_lo(u.x) > 0.0f ? v[8 * i + 0] : 0.0f;
-                v[8 * i + 1] = bf16_hi(u.x) > 0.0f ? v[8 * i + 1] : 0.0f;
-                v[8 * i + 2] = bf16_lo(u.y) > 0.0f ? v[8 * i + 2] : 0.0f;
-                v[8 * i + 3] = bf16_hi(u.y) > 0.0f ? v[8 * i + 3] : 0.0f;
-                v[8 * i + 4] = bf16_lo(u.z) > 0.0f ? v[8 * i + 4] : 0.0f;
-                v[8 * i + 5] = bf16_hi(u.z) > 0.0f ? v[8 * i + 5] : 0.0f;
-                v[8 * i + 6] = bf16_lo(u.w) > 0.0f ? v[8 * i + 6] : 0.0f;
-                v[8 * i + 7] = bf16_hi(u.w) > 0.0f ? v[8 * i + 7] : 0.0f;
+                pk[4 * i + 0] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.x), z2);
+                pk[4 * i + 1] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.y), z2);
+                pk[4 * i + 2] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.z), z2);
+                pk[4 * i + 3] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.w), z2);
               }
             }
             // rows outside the image are clipped by the TMA store; zero them so the column sums ignore them
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint4 o = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+              uint4 o = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
               if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
               *reinterpret_cast<uint4*>(out_slab + lane * 128 + (((half * 4 + i) ^ swz) << 4)) = o;
             }
@@ -348,22 +353,26 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-          __syncwarp();
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");              // #2: slab complete
           if (p.colsum != nullptr) {
-            // lane l sums channel pair l of this chunk over the 32 rows of the bf16 output slab (conflict free:
-            // at a fixed row the 32 lanes read the 32 distinct words of one 128-byte line)
+            // this warp's 32 channels = 16 bf16 pairs: lane l sums pair (l & 15) over rows (l >> 4) * 16 .. + 16
             float s0 = 0.f, s1 = 0.f;
-            const int c16 = lane >> 2, wsel = (lane & 3) << 2;
+            const int pidx = lane & 15, r0 = (lane >> 4) * 16;
+            const int c16 = half * 4 + (pidx >> 2), wsel = (pidx & 3) << 2;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
+            for (int r = r0; r < r0 + 16; ++r) {
               const uint32_t u = *reinterpret_cast<const uint32_t*>(out_slab + r * 128 + ((c16 ^ (r & 7)) << 4) + wsel);
               s0 += bf16_lo(u);
               s1 += bf16_hi(u);
             }
-            atomicAdd(&s_colacc[col0 + 2 * lane], s0);
-            atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            if (lane < 16) {
+              atomicAdd(&s_colacc[col0 + half * 32 + 2 * pidx], s0);
+              atomicAdd(&s_colacc[col0 + half * 32 + 2 * pidx + 1], s1);
+            }
           }
-          if (lane == 0) {
+          if (half == 0 && lane == 0) {
             tma_store_4d(&p.out_map, out_slab, col0, cur.w0 + slab_w, cur.h0 + slab_h, cur.img);
             tma_store_commit();
             if (n_in > 0 && pf.valid) issue_prefetch();   // refill the input slot just consumed
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         cur.j = cur.nch - 1;
         cur.next(p);
       }
-      if (lane == 0) tma_store_wait_all();
+      if (half == 0 && lane == 0) tma_store_wait_all();
     } else {
       // ---------------- legacy register epilogue (fp32 output / BLOCK_N == 32)
       int it = 0;
@@ -477,8 +486,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       }
     }
     if (p.colsum != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      for (int c = threadIdx.x - 128; c < p.ncols; c += 128) {
+      const int n_epi = p.epi_tma ? 256 : 128;         // the epilogue warps only
+      asm volatile("bar.sync 5, %0;" ::"r"(n_epi) : "memory");
+      for (int c = threadIdx.x - 128; c < p.ncols; c += n_epi) {
         const float s = s_colacc[c];
         if (s != 0.0f) atomicAdd(p.colsum + c, s);
       }
@@ -511,7 +521,7 @@ static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
                                       227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 256, h->smem_bytes, stream>>>(h->params);
+  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
