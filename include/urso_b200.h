@@ -105,7 +105,8 @@ void urso_wgrad_destroy(urso_wgrad_t* h);
  * internally): uint8 or fp32 RGB [B,H,W,3] -> bf16 E[B, H/2+3, W/2, 64], E[b,h2,wo,(s2,ph,pw,c)] =
  * (img[2*h2+ph-3, 2*(wo+s2)+pw-3, c] - mean[c]) or 0 outside the image / for c==3. */
 int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, const float* mean3, void* e_out,
-                    int32_t B, int32_t H, int32_t W, void* stream);
+                    int32_t B, int32_t H, int32_t W, int32_t part, void* stream);
+/* part: 0 = bf16(v) (normal); 1 = bf16(v - bf16(v)), the low half of a split-bf16 pair (parity mode, see below). */
 
 /* ---- MaxPooling2D 3x3/s2 'same' on even maps (net.py:176,258): TF pads bottom/right only. bf16 NHWC.
  * argmax (uint8 [B,H/2,W/2,C], may be NULL for inference) records the FIRST maximum of each window (dr*3+ds). */
@@ -148,7 +149,7 @@ int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const
  * idx / tap are device int32 arrays; -1 selects zero padding.  ld_out = row pitch of `out` in elements, so that
  * several convolutions can be staged side by side into one K-concatenated operand (fused fan-in dgrad). */
 int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
-                           int32_t rows_out, int64_t ld_out, void* stream);
+                           int32_t rows_out, int64_t ld_out, int32_t part, void* stream);
 int urso_stage_weight_cols(const float* w, const float* scale, void* out, const int32_t* tap_dev, int32_t n_slots,
                            int32_t CI, int32_t CO, int32_t COp, int32_t rows_out, int64_t ld_out, void* stream);
 /* From the raw wgrad G[R'][CO] (fp32; row r of the HWIO kernel lives at G row g_row_map[r], identity if NULL) and
@@ -170,6 +171,14 @@ int urso_sgd_step(float* param, float* vel, const float* grad, const float* chun
                   const float* hyper_dev, int64_t n, void* stream);
 int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float* grad, const float* chunk_lr,
                       const float* sumsq, const float* hyper_dev, int64_t n, void* stream);
+
+/* ---- split-bf16 parity mode (forward only): every fp32 value x is carried as hi = bf16(x), lo = bf16(x - hi) and a
+ * convolution is evaluated as A_hi.W_hi + A_hi.W_lo + A_lo.W_hi on the tensor cores (three K-segments of Engine F, fp32
+ * accumulation) -- ~2^-16 relative error per operand instead of 2^-9, which meets the 1e-3 forward-parity gate.
+ * urso_split_f32: v = y (+ addend); optional ReLU; out32 = v (may be NULL); hi/lo = the bf16 pair of v. */
+int urso_split_f32(const float* y, const float* addend, float* out32, void* hi, void* lo, int64_t n, int32_t relu,
+                   void* stream);
+int urso_maxpool_fwd_f32(const float* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ---- small elementwise helpers */
 int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);

@@ -228,13 +228,13 @@ def test_stem_stage_and_conv():
     e_out = torch.empty(B, H // 2 + 3, W // 2, 64, dtype=torch.bfloat16, device=DEV)
     img_d, img_f, mean_d = img.to(DEV), img.float().to(DEV), mean.to(DEV)   # keep device buffers alive across calls
     lib.call("urso_stem_stage", img_d.data_ptr(), 1, 1, mean_d.data_ptr(), e_out.data_ptr(), B, H, W,
-             lib.stream_ptr())
+             0, lib.stream_ptr())
     torch.cuda.synchronize()
     assert (e_out.double().cpu() - e_ref.to(torch.bfloat16).double()).abs().max().item() <= 1.0  # 1 bf16 ulp at 255
     # fp32 image input path gives the same staging
     e2 = torch.empty_like(e_out)
     lib.call("urso_stem_stage", img_f.data_ptr(), 0, 1, mean_d.data_ptr(), e2.data_ptr(), B, H, W,
-             lib.stream_ptr())
+             0, lib.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(e2, e_out)
     # 7x7/s2 conv through Engine F on the staged tensor

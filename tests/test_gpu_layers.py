@@ -152,7 +152,7 @@ def test_bn_fold_stage_and_param_grads():
     out = torch.empty(128, len(idx), dtype=torch.bfloat16, device=DEV)
     idx_d = torch.tensor(idx, dtype=torch.int32, device=DEV)
     lib.call("urso_stage_weight_rows", wd.data_ptr(), scale.data_ptr(), out.data_ptr(), idx_d.data_ptr(), len(idx), CO,
-             128, len(idx), s)
+             128, len(idx), 0, s)
     ref = E.stage_rows(w.double(), sref, idx, rows_out=128)
     assert torch.allclose(out.double().cpu(), ref, rtol=2 ** -7, atol=1e-6)
     (_, _, dsegs, tap_map), = P.dgrad_phases(geom)

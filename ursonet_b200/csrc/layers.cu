@@ -41,7 +41,7 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 // E[b, h2, wo, k]  k = s2*16 + ph*8 + pw*4 + c ; one thread writes one 16-byte group (fixed s2,ph: 8 values).
 template <bool U8>
 __global__ void stem_stage_kernel(const void* __restrict__ img, int subtract_mean, const float* __restrict__ mean3,
-                                  __nv_bfloat16* __restrict__ e, int B, int H, int W) {
+                                  __nv_bfloat16* __restrict__ e, int B, int H, int W, int part) {
   const int H2 = H / 2 + 3, WO = W / 2;
   const long long total = (long long)B * H2 * WO * 8;
   const float m0 = subtract_mean ? mean3[0] : 0.f, m1 = subtract_mean ? mean3[1] : 0.f, m2 = subtract_mean ? mean3[2] : 0.f;
@@ -71,10 +71,39 @@ __global__ void stem_stage_kernel(const void* __restrict__ img, int subtract_mea
       }
       v[pw * 4 + 0] = c0; v[pw * 4 + 1] = c1; v[pw * 4 + 2] = c2; v[pw * 4 + 3] = 0.f;
     }
+    if (part == 1) {   // low half of the split-bf16 pair: v - bf16(v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] -= __bfloat162float(__float2bfloat16(v[j]));
+    }
     __nv_bfloat162 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     *reinterpret_cast<uint4*>(e + i * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// fp32 variant of the forward pool (split-bf16 parity mode), one thread per output element group of 4 channels
+__global__ void maxpool_fwd_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int HO = H / 2, WO = W / 2, C4 = C / 4;
+  const long long total = (long long)B * HO * WO * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long r = i / C4;
+    const int wo = (int)(r % WO); r /= WO;
+    const int ho = (int)(r % HO);
+    const int b = (int)(r / HO);
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dr = 0; dr < 3; ++dr) {
+      const int h = 2 * ho + dr;
+      if (h >= H) continue;
+      for (int ds = 0; ds < 3; ++ds) {
+        const int w = 2 * wo + ds;
+        if (w >= W) continue;
+        const float4 u = *reinterpret_cast<const float4*>(x + (((long long)b * H + h) * W + w) * C + c4 * 4);
+        best.x = fmaxf(best.x, u.x); best.y = fmaxf(best.y, u.y); best.z = fmaxf(best.z, u.z); best.w = fmaxf(best.w, u.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = best;
   }
 }
 
@@ -414,16 +443,16 @@ using namespace urso;
 extern "C" {
 
 int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, const float* mean3, void* e_out,
-                    int32_t B, int32_t H, int32_t W, void* stream) {
+                    int32_t B, int32_t H, int32_t W, int32_t part, void* stream) {
   URSO_REQUIRE(img && e_out && (!subtract_mean || mean3), "null pointer");
   URSO_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem input must have even H, W");
   const long long total = (long long)B * (H / 2 + 3) * (W / 2) * 8;
   const int grid = grid_for(total, 256, num_sms() * 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (img_is_u8)
-    stem_stage_kernel<true><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W);
+    stem_stage_kernel<true><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W, part);
   else
-    stem_stage_kernel<false><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W);
+    stem_stage_kernel<false><<<grid, 256, 0, s>>>(img, subtract_mean, mean3, static_cast<__nv_bfloat16*>(e_out), B, H, W, part);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -434,6 +463,15 @@ int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H,
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   maxpool_fwd_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), static_cast<uint8_t*>(argmax), B, H, W, C);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_maxpool_fwd_f32(const float* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  URSO_REQUIRE(x && y, "null pointer");
+  URSO_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool needs even H, W and C %% 4 == 0");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool_fwd_f32_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, C);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

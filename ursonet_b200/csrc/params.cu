@@ -32,7 +32,7 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 // Threads run along k (contiguous in out); the strided read of w is served by L2 (weights are small).
 __global__ void stage_weight_rows_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                          __nv_bfloat16* __restrict__ out, const int* __restrict__ idx, int K, int CO,
-                                         int rows_out, long long ld_out) {
+                                         int rows_out, long long ld_out, int part) {
   const long long total = (long long)rows_out * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
@@ -40,7 +40,9 @@ __global__ void stage_weight_rows_kernel(const float* __restrict__ w, const floa
     float v = 0.f;
     const int src = idx[k];
     if (src >= 0 && row < CO) v = w[(long long)src * CO + row] * (scale != nullptr ? scale[row] : 1.f);
-    out[(long long)row * ld_out + k] = __float2bfloat16(v);
+    __nv_bfloat16 hi = __float2bfloat16(v);
+    if (part == 1) hi = __float2bfloat16(v - __bfloat162float(hi));   // low half of the split-bf16 pair
+    out[(long long)row * ld_out + k] = hi;
   }
 }
 
@@ -241,6 +243,19 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// v = y (+ addend) ; relu ; out32 = v ; hi = bf16(v) ; lo = bf16(v - hi)      (split-bf16 parity mode)
+__global__ void split_f32_kernel(const float* __restrict__ y, const float* __restrict__ addend, float* __restrict__ out32,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long n, int relu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = y[i] + (addend != nullptr ? addend[i] : 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    if (out32 != nullptr) out32[i] = v;
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+
 static inline int grid_for_p(long long n, int block, int max_blocks) {
   long long g = (n + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -265,12 +280,12 @@ int urso_bn_fold(const float* gamma, const float* beta, const float* mean, const
 }
 
 int urso_stage_weight_rows(const float* w, const float* scale, void* out, const int32_t* idx_dev, int32_t K, int32_t CO,
-                           int32_t rows_out, int64_t ld_out, void* stream) {
+                           int32_t rows_out, int64_t ld_out, int32_t part, void* stream) {
   URSO_REQUIRE(w && out && idx_dev, "null pointer");
   URSO_REQUIRE(ld_out >= K, "ld_out < K");
   stage_weight_rows_kernel<<<grid_for_p((long long)rows_out * K, 256, num_sms() * 8), 256, 0,
                              static_cast<cudaStream_t>(stream)>>>(w, scale, static_cast<__nv_bfloat16*>(out), idx_dev,
-                                                                  K, CO, rows_out, ld_out);
+                                                                  K, CO, rows_out, ld_out, part);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -337,6 +352,15 @@ int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float
   URSO_REQUIRE(param && m && v && vhat && grad && chunk_lr && sumsq && hyper_dev, "null pointer");
   amsgrad_step_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, m, v, vhat, grad, chunk_lr, sumsq, hyper_dev, n);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_split_f32(const float* y, const float* addend, float* out32, void* hi, void* lo, int64_t n, int32_t relu,
+                   void* stream) {
+  URSO_REQUIRE(y && hi && lo, "null pointer");
+  split_f32_kernel<<<grid_for_p(n, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, addend, out32, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n, relu);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -136,11 +136,15 @@ class OpRec:
 class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
-    def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0):
+    def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
+                 parity=None):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
         self.cfg, self.B, self.training, self.device, self.world = cfg, int(batch_size), training, device, world_size
+        self.parity = bool(getattr(cfg, "PARITY_MODE", False)) if parity is None else bool(parity)
+        if self.parity and training:
+            raise NotImplementedError("PARITY_MODE (split-bf16 operands) is forward-only")
         self.graph: Graph = build_graph(cfg)
         self.H, self.W = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
         self.params = ParamStore(self.graph, device, cfg.WEIGHT_DECAY)
@@ -149,7 +153,10 @@ class Engine:
         self._keep = []          # plan objects / index tensors kept alive
         self._zero_specs = []    # (name, numel) carved from the zero arena
         self._alloc()
-        self._build_forward()
+        if self.parity:
+            self._build_forward_parity()
+        else:
+            self._build_forward()
         if training:
             self._build_backward()
             self._build_update()
@@ -168,7 +175,12 @@ class Engine:
         self.E = self._new((B, self.H // 2 + 3, self.W // 2, 64))
         self.act: Dict[str, torch.Tensor] = {}
         for name, (h, w, c) in g.shapes.items():
-            self.act[name] = self._new((B, h, w, c), torch.float32 if name == "bottleneck_layer" else torch.bfloat16)
+            f32 = name == "bottleneck_layer" or self.parity       # parity mode: fp32 master + (hi, lo) bf16 pair
+            self.act[name] = self._new((B, h, w, c), torch.float32 if f32 else torch.bfloat16)
+        if self.parity:
+            self.E_lo = torch.zeros_like(self.E)
+            self.act_hi = {n: self._new((B, h, w, c)) for n, (h, w, c) in g.shapes.items() if n != "bottleneck_layer"}
+            self.act_lo = {n: self._new((B, h, w, c)) for n, (h, w, c) in g.shapes.items() if n != "bottleneck_layer"}
         self.head: Dict[str, torch.Tensor] = {}
         for d in g.dense:
             self.head[d.name] = None   # carved from the zero arena (split-K atomics accumulate into them)
@@ -248,7 +260,7 @@ class Engine:
             idx_d = self._idx(idx)
             self.ops_stage.append(lambda w=w, sc=sc, bmat=bmat, idx_d=idx_d, K=K, c=c: lib.call(
                 "urso_stage_weight_rows", w.data_ptr(), sc.data_ptr(), bmat.data_ptr(), idx_d.data_ptr(), K, c.cout,
-                c.cout, K, S()))
+                c.cout, K, 0, S()))
             out = self.act[c.dst]
             addend = self.act[c.addend] if c.addend else None
             oh, ow = g.shapes[c.dst][0], g.shapes[c.dst][1]
@@ -275,6 +287,11 @@ class Engine:
                 src, dst = self.act[c.dst], self.act["pool1"]
                 self.ops_fwd.append(lambda src=src, dst=dst, ph=ph, pw=pw: lib.call(
                     "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(self.argmax), B, ph, pw, 64, S()))
+        self._build_heads_forward()
+
+    def _build_heads_forward(self):
+        g, B = self.graph, self.B
+        S = lib.stream_ptr
         # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332)
         for d in g.dense:
             w, b = self.params.view(d.name + "/kernel"), self.params.view(d.name + "/bias")
@@ -292,6 +309,63 @@ class Engine:
         if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
             self.ops_fwd.append(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
                                                  self.ori_q.data_ptr(), None, None, self.B, 1.0, S()))
+
+    def _build_forward_parity(self):
+        """Forward plan in split-bf16 precision (cfg.PARITY_MODE): every activation x is carried as fp32 plus the pair
+        hi = bf16(x), lo = bf16(x - hi); a conv is three K-segment groups of Engine F, A_hi.W_hi + A_hi.W_lo + A_lo.W_hi,
+        accumulated in fp32 in TMEM; the epilogue adds the folded BN shift and writes fp32; urso_split_f32 then applies
+        the residual add + ReLU in fp32 and regenerates the (hi, lo) pair.  Same launch machinery, ~3x the MMA work."""
+        g, B = self.graph, self.B
+        S = lib.stream_ptr
+        self.ops_stage, self.ops_fwd, self.ops_loss = [], [], []
+        self._late_binds = []
+        self.Bf = {}
+        for c in g.convs:
+            w, bias, bn = self._conv_weight_ptrs(c)
+            sc, sh = self.scale[c.name], self.shift[c.name]
+            self.ops_stage.append(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
+                "urso_bn_fold", lib.ptr(bn[0]), lib.ptr(bn[1]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
+                sc.data_ptr(), sh.data_ptr(), c.cout, S()))
+            if c.stem:
+                segs, idx = P.stem_segments(), P.stem_weight_index(3)
+                views_hi, views_lo = [self.E], [self.E_lo]
+            else:
+                h, w_, _ = g.shapes[c.src]
+                geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w_)
+                segs, idx = P.fwd_segments(geom)
+                views_hi = P.input_views(self.act_hi[c.src], c.stride)
+                views_lo = P.input_views(self.act_lo[c.src], c.stride)
+            K, nv = len(idx), len(views_hi)
+            bmat = self._new((c.cout, 3 * K))
+            self.Bf[c.name] = bmat
+            idx_d = self._idx(idx)
+            for col, part in ((0, 0), (K, 1), (2 * K, 0)):        # [W_hi | W_lo | W_hi]
+                dst = bmat[:, col:]
+                self.ops_stage.append(lambda w=w, sc=sc, dst=dst, idx_d=idx_d, K=K, c=c, part=part: lib.call(
+                    "urso_stage_weight_rows", w.data_ptr(), sc.data_ptr(), dst.data_ptr(), idx_d.data_ptr(), K, c.cout,
+                    c.cout, 3 * K, part, S()))
+            segs3 = list(segs) + list(segs) + [(m + nv, dh, dw, ch) for (m, dh, dw, ch) in segs]   # A_hi, A_hi, A_lo
+            out32 = self.act[c.dst]
+            oh, ow = g.shapes[c.dst][0], g.shapes[c.dst][1]
+            tw, th = P.pick_patch(oh, ow, 128)
+            plan = lib.ConvGemm(views_hi + views_lo, bmat, segs3, out32, ow, oh, B, tw, th, shift=sh)
+            self._keep.append(plan)
+            self.ops_fwd.append(OpRec(plan.launch, "conv_fwd", c.name, 6.0 * B * oh * ow * c.cout * c.k * c.k * c.cin, 0.0))
+            if c.dst != "bottleneck_layer":
+                addend = self.act[c.addend] if c.addend else None
+                hi, lo = self.act_hi[c.dst], self.act_lo[c.dst]
+                self.ops_fwd.append(lambda out32=out32, addend=addend, hi=hi, lo=lo, c=c: lib.call(
+                    "urso_split_f32", out32.data_ptr(), lib.ptr(addend), out32.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                    out32.numel(), int(c.relu), S()))
+            if c.stem:
+                ph, pw, _ = g.shapes[c.dst]
+                self.argmax = None
+                src, dst = self.act[c.dst], self.act["pool1"]
+                hi, lo = self.act_hi["pool1"], self.act_lo["pool1"]
+                self.ops_fwd.append(lambda src=src, dst=dst, hi=hi, lo=lo, ph=ph, pw=pw: (
+                    lib.call("urso_maxpool_fwd_f32", src.data_ptr(), dst.data_ptr(), B, ph, pw, 64, S()),
+                    lib.call("urso_split_f32", dst.data_ptr(), None, None, hi.data_ptr(), lo.data_ptr(), dst.numel(), 0, S())))
+        self._build_heads_forward()
 
     # ------------------------------------------------------------------ backward plan
     def _build_backward(self):
@@ -566,10 +640,12 @@ class Engine:
     def _stage_input(self):
         S = lib.stream_ptr
         if self._input_kind == "u8":
-            lib.call("urso_stem_stage", self.img_u8.data_ptr(), 1, 1, self.mean3.data_ptr(), self.E.data_ptr(), self.B,
-                     self.H, self.W, S())
+            args = (self.img_u8.data_ptr(), 1, 1, self.mean3.data_ptr())
         else:
-            lib.call("urso_stem_stage", self.img_f32.data_ptr(), 0, 0, None, self.E.data_ptr(), self.B, self.H, self.W, S())
+            args = (self.img_f32.data_ptr(), 0, 0, None)
+        lib.call("urso_stem_stage", *args, self.E.data_ptr(), self.B, self.H, self.W, 0, S())
+        if self.parity:
+            lib.call("urso_stem_stage", *args, self.E_lo.data_ptr(), self.B, self.H, self.W, 1, S())
 
     _input_kind = "u8"
 

@@ -57,7 +57,7 @@ SIGNATURES = {
     "urso_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(_vp)],
     "urso_wgrad_launch": [_vp, _vp],
     "urso_wgrad_destroy": [_vp],
-    "urso_stem_stage": [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp],
+    "urso_stem_stage": [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_maxpool_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_maxpool_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_dense_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
@@ -67,12 +67,14 @@ SIGNATURES = {
     "urso_rel_loss": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
     "urso_quat_head": [_vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
     "urso_bn_fold": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
-    "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp],
+    "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp],
     "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
     "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 5 + [_i32, _i32, _vp],
     "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "urso_amsgrad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "urso_split_f32": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "urso_maxpool_fwd_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "urso_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "urso_pad_cast_rows": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
