@@ -180,6 +180,16 @@ int urso_split_f32(const float* y, const float* addend, float* out32, void* hi, 
                    void* stream);
 int urso_maxpool_fwd_f32(const float* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
+/* ---- orientation soft labels on the device (data format either side of the path).
+ * urso_encode_ori: utils.encode_ori_fast (utils.py:319-346) for a batch: quats [B,4] fp32, hquat [nbins,4] fp32 (the
+ * Euler-grid quaternions, 16-byte aligned), redundant [nbins] uint8 mask, var = (beta/n)^2/12 -> enc [B,nbins] fp32.
+ * urso_decode_ori_moments: stable_softmax of the network's logits (utils.py:26-28) and the 4x4 moment matrix
+ * A_b = sum_k p_k H_k H_k^T of se3lib.quat_weighted_avg (se3lib.py:241-248); the quaternion is the principal
+ * eigenvector of A_b (a 4x4 eigen-solve, left to the host). */
+int urso_encode_ori(const float* quats, const float* hquat, const uint8_t* redundant, float* enc, int32_t B,
+                    int32_t nbins, float var, void* stream);
+int urso_decode_ori_moments(const float* logits, const float* hquat, float* A, int32_t B, int32_t nbins, void* stream);
+
 /* ---- small elementwise helpers */
 int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);

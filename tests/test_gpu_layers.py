@@ -252,3 +252,22 @@ def test_small_helpers():
     src2 = torch.randn(50, 32, device=DEV)
     lib.call("urso_pad_cast_rows", src.data_ptr(), src2.data_ptr(), dst.data_ptr(), 50, 32, 64, s)
     assert torch.equal(dst[:, :32], (src + src2).to(torch.bfloat16)) and (dst[:, 32:] == 0).all()
+
+
+def test_device_label_codec_matches_reference_golden():
+    """urso_encode_ori / urso_decode_ori_moments against the REFERENCE's own outputs (tests/golden/labels_golden.npz)."""
+    import os
+    import numpy as np
+    from ursonet_b200 import labels
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels_golden.npz"))
+    for n, beta in [(8, 6.0), (16, 6.0), (12, 3.0)]:
+        codec = labels.DeviceOrientationCodec(labels.OrientationEncoder(n, beta))
+        q = torch.from_numpy(G["quats"]).float().to(DEV)
+        enc = codec.encode(q).cpu().numpy()
+        ref = G[f"enc_{n}_{beta}"]
+        assert np.allclose(enc, ref, atol=2e-6, rtol=2e-3), np.abs(enc - ref).max()
+        assert np.allclose(enc.sum(1), 1.0, atol=1e-5)
+        z = torch.from_numpy(G[f"logits_{n}_{beta}"]).float().to(DEV)
+        qd = codec.decode(z)
+        for a, b in zip(qd, G[f"qavg_{n}_{beta}"]):
+            assert labels.angular_error_deg(a, b) < 0.05

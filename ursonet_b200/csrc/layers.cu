@@ -545,3 +545,90 @@ int urso_quat_head(const float* raw, const float* gt, float* q_out, float* draw,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ orientation soft labels
+//  device versions of utils.encode_ori_fast (utils.py:319-346) and of the PMF decode of
+// pose_estimator.py:406-409 (stable_softmax + the 4x4 moment matrix of se3lib.quat_weighted_avg).
+namespace urso {
+
+// enc[b, k] = exp(-2 (acos(min(1, |<q_b, H_k>|)) / pi)^2 / var) for non-redundant bins, normalised over k.
+__global__ void __launch_bounds__(256) encode_ori_kernel(const float* __restrict__ quats, const float* __restrict__ hquat,
+                                                         const uint8_t* __restrict__ redundant, float* __restrict__ enc,
+                                                         int nbins, float var) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float q0 = quats[b * 4 + 0], q1 = quats[b * 4 + 1], q2 = quats[b * 4 + 2], q3 = quats[b * 4 + 3];
+  float sum = 0.f;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+    float p = 0.f;
+    if (!redundant[k]) {
+      const float4 h = *reinterpret_cast<const float4*>(hquat + 4 * k);
+      const float d = fminf(1.0f, fabsf(q0 * h.x + q1 * h.y + q2 * h.z + q3 * h.w));
+      const float a = acosf(d) * 0.318309886183790672f;
+      p = expf(-2.0f * a * a / var);
+    }
+    enc[(long long)b * nbins + k] = p;
+    sum += p;
+  }
+  sum = block_sum(sum, sh);
+  const float inv = 1.0f / sum;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) enc[(long long)b * nbins + k] *= inv;
+}
+
+// A_b = sum_k softmax(z_b)_k * H_k H_k^T   (symmetric 4x4, 10 unique entries written as a full 16-float matrix)
+__global__ void __launch_bounds__(256) decode_moments_kernel(const float* __restrict__ logits,
+                                                             const float* __restrict__ hquat, float* __restrict__ A,
+                                                             int nbins) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* z = logits + (long long)b * nbins;
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) m = fmaxf(m, z[k]);
+  m = block_max(m, sh);
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  float se = 0.f;
+  for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+    const float w = expf(z[k] - m);
+    se += w;
+    const float4 h = *reinterpret_cast<const float4*>(hquat + 4 * k);
+    acc[0] += w * h.x * h.x; acc[1] += w * h.x * h.y; acc[2] += w * h.x * h.z; acc[3] += w * h.x * h.w;
+    acc[4] += w * h.y * h.y; acc[5] += w * h.y * h.z; acc[6] += w * h.y * h.w;
+    acc[7] += w * h.z * h.z; acc[8] += w * h.z * h.w; acc[9] += w * h.w * h.w;
+  }
+  se = block_sum(se, sh);
+  const float inv = 1.0f / se;
+  float r[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) r[i] = block_sum(acc[i], sh) * inv;
+  if (threadIdx.x == 0) {
+    float* o = A + b * 16;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+    o[4] = r[1]; o[5] = r[4]; o[6] = r[5]; o[7] = r[6];
+    o[8] = r[2]; o[9] = r[5]; o[10] = r[7]; o[11] = r[8];
+    o[12] = r[3]; o[13] = r[6]; o[14] = r[8]; o[15] = r[9];
+  }
+}
+
+}  // namespace urso
+
+extern "C" {
+
+int urso_encode_ori(const float* quats, const float* hquat, const uint8_t* redundant, float* enc, int32_t B,
+                    int32_t nbins, float var, void* stream) {
+  URSO_REQUIRE(quats && hquat && redundant && enc, "null pointer");
+  URSO_REQUIRE((reinterpret_cast<uintptr_t>(hquat) & 15) == 0, "hquat must be 16-byte aligned");
+  urso::encode_ori_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(quats, hquat, redundant, enc, nbins, var);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_decode_ori_moments(const float* logits, const float* hquat, float* A, int32_t B, int32_t nbins, void* stream) {
+  URSO_REQUIRE(logits && hquat && A, "null pointer");
+  urso::decode_moments_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, hquat, A, nbins);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
