@@ -49,6 +49,7 @@ struct ConvGemmParams {
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
   int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
+  int eo_depth;      // per-warp output slabs (TMA stores in flight)
   int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
   PixDev out, addend, mask;
   int out_fp32, relu;
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* ei_bar = tempty_bar + 2;                       // [4 warps][kMaxEiDepth]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 4 * kMaxEiDepth);
+  uint64_t* ei_bar = tempty_bar + 2;                       // [8 warps][kMaxEiDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 8 * kMaxEiDepth);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
   float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + kColsumAccBytes);   // legacy epilogue only
 
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
     }
-    for (int i = 0; i < 4 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
+    for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -238,20 +239,24 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int row = q * 32 + lane;
     const int rh = row >> p.tw_shift, rw = row & (p.TW - 1);
     if (p.epi_tma) {
-      // ---------------- TMA epilogue
+      // ---------------- TMA epilogue.  8 warps: warp set `half` (0/1) of quadrant q takes every other 64-channel
+      // chunk of the quadrant's 32 pixel rows.  The two warps that share a scheduler (and a TMEM lane quadrant) work
+      // on DIFFERENT chunks, each with private smem rings and its own TMA queue: no cross-warp synchronisation.
       const int slab_h = (q * 32) >> p.tw_shift, slab_w = (q * 32) & (p.TW - 1);   // slab origin inside the patch
       const int n_in = p.has_add + p.has_mask;
       const int slot_bytes = n_in * kSlabBytes;
-      const int kEiDepth = p.ei_depth;
-      uint8_t* ei = smem + p.ei_off + q * kEiDepth * slot_bytes;
-      uint8_t* eo = smem + p.eo_off + q * 2 * kSlabBytes;
-      uint64_t* my_bar = ei_bar + q * kMaxEiDepth;
+      const int kEiDepth = p.ei_depth, kEoDepth = p.eo_depth;
+      const int wslot = half * 4 + q;                                    // this warp's ring index
+      uint8_t* ei = smem + p.ei_off + wslot * kEiDepth * slot_bytes;
+      uint8_t* eo = smem + p.eo_off + wslot * kEoDepth * kSlabBytes;
+      uint64_t* my_bar = ei_bar + wslot * kMaxEiDepth;
       const int swz = lane & 7;
       ChunkIter<BLOCK_N> cur, pf;
       cur.init(p);
+      if (half == 1 && cur.valid) cur.next(p);     // set 1 starts at the second chunk of the stream
       pf = cur;
-      int n_pf = 0;   // chunks prefetched so far
-      auto issue_prefetch = [&]() {   // lane 0 only
+      int n_pf = 0;                                // my chunks prefetched so far
+      auto issue_prefetch = [&]() {                // lane 0 only
         const int slot = n_pf % kEiDepth;
         uint8_t* dst = ei + slot * slot_bytes;
         mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
@@ -261,37 +266,47 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         ++n_pf;
         pf.next(p);
+        if (pf.valid) pf.next(p);                  // my chunks are every other one
       };
-      if (n_in > 0 && half == 0 && lane == 0) {
+      if (n_in > 0 && lane == 0) {
         for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
       }
-      int n_done = 0;   // chunks consumed so far
-      int it = 0;
-      for (; cur.valid; ++it) {
+      int n_done = 0;        // my chunks consumed so far
+      int it = 0;            // tiles of this CTA visited
+      int tile_seen = -1;    // last tile whose accumulator this warp has waited for
+      // every tile of the CTA is visited by BOTH warp sets (each must release the accumulator stage exactly once)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int h = cur.h0 + rh, w = cur.w0 + rw;
-        const bool valid = (h < p.OH) && (w < p.OW);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-        const int nch = cur.nch;
-        for (int j = 0; j < nch; ++j, ++n_done) {
+        while (cur.valid && cur.tile == tile) {
+          const int j = cur.j;
+          const int h = cur.h0 + rh, w = cur.w0 + rw;
+          const bool valid = (h < p.OH) && (w < p.OW);
           const int col0 = cur.n_tile * BLOCK_N + j * 64;
           const int slot = n_done % kEiDepth;
-          uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
-          uint8_t* out_slab = eo + (n_done & 1) * kSlabBytes;
+          const uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
+          uint8_t* out_slab = eo + (n_done % kEoDepth) * kSlabBytes;
+          if (n_done >= kEoDepth) {   // the TMA store that last used this output slab must have drained it
+            if (lane == 0) {
+              if (kEoDepth >= 3) tma_store_wait_read<2>();
+              else if (kEoDepth == 2) tma_store_wait_read<1>();
+              else tma_store_wait_read<0>();
+            }
+            __syncwarp();
+          }
           if (n_in > 0) mbar_wait(&my_bar[slot], (n_done / kEiDepth) & 1);
-          if (n_done >= 2 && half == 0 && lane == 0) tma_store_wait_read<1>();   // this output slab has been drained
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");              // #1 (pair of warps sharing the slab)
-          {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
             uint32_t acc[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 64 + half * 32, acc);
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + j * 64 + hf * 32, acc);
             tmem_ld_wait();
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
             if (p.shift != nullptr) {
-              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0 + hf * 32);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 s4 = __ldg(sp + i);
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             if (p.has_add) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(in_slab + (((half * 4 + i) ^ swz) << 4));
+                const uint4 u = *reinterpret_cast<const uint4*>(in_slab + (((hf * 4 + i) ^ swz) << 4));
                 v[8 * i + 0] += bf16_lo(u.x);
                 v[8 * i + 1] += bf16_hi(u.x);
                 v[8 * i + 2] += bf16_lo(u.y);
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(ms + (((half * 4 + i) ^ swz) << 4));
+                const uint4 u = *reinterpret_cast<const uint4*>(ms + (((hf * 4 + i) ^ swz) << 4));
                 pk[4 * i + 0] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.x), z2);
                 pk[4 * i + 1] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.y), z2);
                 pk[4 * i + 2] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.z), z2);
@@ -344,45 +359,41 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             for (int i = 0; i < 4; ++i) {
               uint4 o = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
               if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(out_slab + lane * 128 + (((half * 4 + i) ^ swz) << 4)) = o;
+              *reinterpret_cast<uint4*>(out_slab + lane * 128 + (((hf * 4 + i) ^ swz) << 4)) = o;
             }
-          }
-          if (j == nch - 1) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");              // #2: slab complete
-          if (p.colsum != nullptr) {
-            // this warp's 32 channels = 16 bf16 pairs: lane l sums pair (l & 15) over rows (l >> 4) * 16 .. + 16
-            float s0 = 0.f, s1 = 0.f;
-            const int pidx = lane & 15, r0 = (lane >> 4) * 16;
-            const int c16 = half * 4 + (pidx >> 2), wsel = (pidx & 3) << 2;
-#pragma unroll 8
-            for (int r = r0; r < r0 + 16; ++r) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(out_slab + r * 128 + ((c16 ^ (r & 7)) << 4) + wsel);
-              s0 += bf16_lo(u);
-              s1 += bf16_hi(u);
-            }
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            if (lane < 16) {
-              atomicAdd(&s_colacc[col0 + half * 32 + 2 * pidx], s0);
-              atomicAdd(&s_colacc[col0 + half * 32 + 2 * pidx + 1], s1);
-            }
-          }
-          if (half == 0 && lane == 0) {
+          __syncwarp();          // all lanes have finished reading the input slot and writing the output slab
+          if (lane == 0) {
             tma_store_4d(&p.out_map, out_slab, col0, cur.w0 + slab_w, cur.h0 + slab_h, cur.img);
             tma_store_commit();
             if (n_in > 0 && pf.valid) issue_prefetch();   // refill the input slot just consumed
           }
+          if (p.colsum != nullptr) {
+            // lane l sums channel pair l of this chunk over the 32 rows of the bf16 output slab (conflict free:
+            // at a fixed row the 32 lanes read the 32 distinct words of one 128-byte line)
+            float s0 = 0.f, s1 = 0.f;
+            const int c16 = lane >> 2, wsel = (lane & 3) << 2;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(out_slab + r * 128 + ((c16 ^ (r & 7)) << 4) + wsel);
+              s0 += bf16_lo(u);
+              s1 += bf16_hi(u);
+            }
+            atomicAdd(&s_colacc[col0 + 2 * lane], s0);
+            atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1);
+          }
+          ++n_done;
+          cur.next(p);
+          if (cur.valid) cur.next(p);   // skip the other warp set's chunk
         }
-        // advance to the next tile of this CTA
-        cur.j = cur.nch - 1;
-        cur.next(p);
+        (void)tile_seen;
+        // all of this warp's TMEM reads of the tile are complete: release the accumulator stage (8 arrivals)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
-      if (half == 0 && lane == 0) tma_store_wait_all();
+      if (lane == 0) tma_store_wait_all();
     } else {
       // ---------------- legacy register epilogue (fp32 output / BLOCK_N == 32)
       int it = 0;
@@ -587,9 +598,17 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
   int epi_bytes;
   if (p.epi_tma) {
-    p.ei_depth = (p.has_add + p.has_mask) == 2 ? 2 : kMaxEiDepth;
-    const int ei_bytes = 4 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
-    epi_bytes = ei_bytes + 4 * 2 * kSlabBytes;
+    // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight)
+    // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to mainloop stages.  Short-K
+    // launches are epilogue / store bound: deeper rings keep more TMA traffic in flight.
+    const int n_in = p.has_add + p.has_mask;
+    int ksteps_total = 0;
+    for (int s2 = 0; s2 < d->n_seg; ++s2) ksteps_total += d->seg[s2].c_chunks;
+    const bool heavy = ksteps_total >= 4;
+    p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
+    p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
+    const int ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
+    epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
     if (bn == 256 && kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes < 3 * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
   } else {
     epi_bytes = kLegacyScratchBytes;
@@ -607,8 +626,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   const int fixed = stages * stage_bytes + kCtrlBytes + kColsumAccBytes;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
-    p.eo_off = p.ei_off + 4 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
-    h->smem_bytes = p.eo_off + 4 * 2 * kSlabBytes + 1024;
+    p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
+    h->smem_bytes = p.eo_off + 8 * p.eo_depth * kSlabBytes + 1024;
   } else {
     h->smem_bytes = fixed + kLegacyScratchBytes + 1024;
   }
