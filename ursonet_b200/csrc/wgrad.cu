@@ -25,6 +25,7 @@ struct WgradParams {
   CUtensorMap q_map;
   WSegDev seg[URSO_MAX_SEGS];
   int n_seg, taps_per_cta, n_seg_groups;
+  int pair_mode;   // PC <= 64: the two 64-row halves of the MMA M dimension carry two different filter taps
   int PC, QC;
   int p_tiles, q_tiles;
   int tiles_w, tiles_h, TW, TH;
@@ -61,8 +62,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   const int q_tile = wi % p.q_tiles; wi /= p.q_tiles;
   const int p_tile = wi % p.p_tiles; wi /= p.p_tiles;
   const int seg_group = wi;
+  // "units" = taps (normal) or tap pairs (pair mode)
+  const int n_units = p.pair_mode ? (p.n_seg + 1) / 2 : p.n_seg;
   const int seg0 = seg_group * p.taps_per_cta;
-  const int T = min(p.taps_per_cta, p.n_seg - seg0);
+  const int T = min(p.taps_per_cta, n_units - seg0);
   const int kb_begin = (int)((long long)p.n_pix_blocks * split / p.split_k);
   const int kb_end = (int)((long long)p.n_pix_blocks * (split + 1) / p.split_k);
 
@@ -104,11 +107,19 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         uint8_t* pbase = base + QA * kAtomBytes;
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-          const WSegDev sg = p.seg[seg0 + t];
-          tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128, w0 + sg.dw,
-                      h0 + sg.dh, img);
-          tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128 + 64,
-                      w0 + sg.dw, h0 + sg.dh, img);
+          if (p.pair_mode) {
+            const int ta = 2 * (seg0 + t), tb = min(ta + 1, p.n_seg - 1);   // odd tap count: the last atom repeats a tap
+            const WSegDev sa = p.seg[ta], sb = p.seg[tb];
+            tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sa.map_id], &full_bar[stage], 0, w0 + sa.dw, h0 + sa.dh, img);
+            tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sb.map_id], &full_bar[stage], 0, w0 + sb.dw, h0 + sb.dh,
+                        img);
+          } else {
+            const WSegDev sg = p.seg[seg0 + t];
+            tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128, w0 + sg.dw,
+                        h0 + sg.dh, img);
+            tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128 + 64,
+                        w0 + sg.dw, h0 + sg.dh, img);
+          }
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -145,12 +156,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int pch = p_tile * 128 + row;
     if (kb_end > kb_begin) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       for (int t = 0; t < T; ++t) {
-        float* grow = p.g + (long long)(seg0 + t) * p.g_seg_stride + (long long)pch * p.g_sp;
+        // accumulator row -> (filter tap, P channel)
+        const int tap = p.pair_mode ? 2 * (seg0 + t) + (row >> 6) : seg0 + t;
+        const int pch = p.pair_mode ? (row & 63) : p_tile * 128 + row;
+        const bool row_ok = pch < p.PC && tap < p.n_seg;
+        float* grow = p.g + (long long)tap * p.g_seg_stride + (long long)pch * p.g_sp;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(grow) & 15) == 0;
 #pragma unroll 1
         for (int j = 0; j < BLOCK_Q / 32; ++j) {
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + t * BLOCK_Q + j * 32, acc);
           tmem_ld_wait();
-          if (pch < p.PC) {
+          if (row_ok) {
             if (p.g_sq == 1 && col0 + 32 <= p.QC && vec_ok) {
               // contiguous along q: 16-byte vector reductions (REDG.E.ADD.F32x4), 4x fewer L2 atomic sectors
 #pragma unroll
@@ -243,12 +257,15 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
     p.seg[s] = WSegDev{(int16_t)d->seg[s].map_id, (int16_t)d->seg[s].dh, (int16_t)d->seg[s].dw, 0};
   }
   p.n_seg = d->n_seg;
+  p.pair_mode = (d->PC <= 64 && d->n_seg >= 2) ? 1 : 0;
+  const int n_units = p.pair_mode ? (d->n_seg + 1) / 2 : d->n_seg;
   int tmax = 512 / bq;
-  // smem: each stage holds the Q tile + 2 atoms per tap; keep at least 2 stages
+  // smem: each stage holds the Q tile + 2 atoms per unit; keep at least 3 stages
   const int qa = bq / 64;
-  while (tmax > 1 && (qa + 2 * tmax) * kAtomBytes * 2 > 200 * 1024) --tmax;
-  p.taps_per_cta = d->n_seg < tmax ? d->n_seg : tmax;
-  p.n_seg_groups = (d->n_seg + p.taps_per_cta - 1) / p.taps_per_cta;
+  while (tmax > 1 && (qa + 2 * tmax) * kAtomBytes * 3 > 200 * 1024) --tmax;
+  // balanced groups: e.g. 9 taps with room for 4 per CTA -> 3 + 3 + 3 instead of 4 + 4 + 1
+  p.n_seg_groups = (n_units + tmax - 1) / tmax;
+  p.taps_per_cta = (n_units + p.n_seg_groups - 1) / p.n_seg_groups;
   p.PC = d->PC;
   p.QC = d->QC;
   p.p_tiles = (d->PC + 127) / 128;
