@@ -114,8 +114,9 @@ int urso_maxpool_fwd(const void* x, void* y, void* argmax, int32_t B, int32_t H,
 /* dx = scatter(dy to the recorded argmax) (TF MaxPoolGrad).  x (the pooled tensor's input) may be NULL when dy is
  * already masked by (pooled > 0) -- equivalent to the stem's ReLU mask, since a window's max is 0 only if all its
  * (post-ReLU) inputs are 0; otherwise dx is additionally masked by x > 0. */
-int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
-                     int32_t C, void* stream);
+int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, float* colsum, int32_t B, int32_t H,
+                     int32_t W, int32_t C, void* stream);
+/* colsum (fp32 [C], may be NULL): atomically accumulates the per-channel sums of dx (d beta of the stem's BatchNorm). */
 
 /* ---- Dense layers of the two heads (net.py:302,316,336,345,350): fp32, small batch, weight-bandwidth bound.
  * y[B,N] = act(x[B,K] @ w[K,N] + bias).  act: 0 linear, 1 relu. y must be zeroed by the caller (split-K atomics);

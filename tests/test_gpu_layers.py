@@ -32,7 +32,8 @@ def test_maxpool_fwd_bwd():
     dy = torch.randn(B, H // 2, W // 2, C, generator=g).to(torch.bfloat16)
     dx = torch.empty_like(xd)
     dyd = dy.to(DEV)
-    lib.call("urso_maxpool_bwd", xd.data_ptr(), am.data_ptr(), dyd.data_ptr(), dx.data_ptr(), B, H, W, C,
+    csum = torch.zeros(C, device=DEV)
+    lib.call("urso_maxpool_bwd", xd.data_ptr(), am.data_ptr(), dyd.data_ptr(), dx.data_ptr(), csum.data_ptr(), B, H, W, C,
              lib.stream_ptr())
     torch.cuda.synchronize()
     # oracle: autograd through relu(pre) -> pool, with pre = x where x>0 (distinct positives => unique argmax)
@@ -49,9 +50,10 @@ def test_maxpool_fwd_bwd():
     # x == NULL with dy pre-masked by (pooled > 0) gives the same result (how the engine calls it)
     dym = torch.where(y > 0, dyd, torch.zeros_like(dyd))
     dx2 = torch.empty_like(xd)
-    lib.call("urso_maxpool_bwd", None, am.data_ptr(), dym.data_ptr(), dx2.data_ptr(), B, H, W, C, lib.stream_ptr())
+    lib.call("urso_maxpool_bwd", None, am.data_ptr(), dym.data_ptr(), dx2.data_ptr(), None, B, H, W, C, lib.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(dx2, dx)
+    assert torch.allclose(csum, dx.float().sum((0, 1, 2)), rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("B,K,N,act", [(4, 640, 1024, 1), (32, 4800, 1024, 1), (32, 1024, 3, 0), (5, 1024, 4096, 1),

@@ -153,54 +153,96 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   }
 }
 
-// dx[h,w,c] = (x>0) * sum over windows whose recorded argmax is (h,w) of dy.  One thread: one pixel x 8 channels.
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ argmax,
-                                   const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int B, int H,
-                                   int W, int C) {
+// dx[h,w,c] = [x>0] * sum over windows whose recorded argmax is (h,w) of dy.
+// One thread: a 2x2 block of input pixels x 8 channels.  The block (2i..2i+1, 2j..2j+1) is touched by exactly the four
+// windows (i-1..i) x (j-1..j), so their argmax / dy vectors are loaded once and routed to the four pixels in registers.
+// Optionally accumulates the per-channel sums of dx (d beta of the stem's BatchNorm): shared-memory atomics per block,
+// one global atomic per channel per block.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          const uint8_t* __restrict__ argmax,
+                                                          const __nv_bfloat16* __restrict__ dy,
+                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ colsum,
+                                                          int B, int H, int W, int C) {
+  __shared__ float cs[512];
   const int HO = H / 2, WO = W / 2, C8 = C / 8;
-  const long long total = (long long)B * H * W * C8;
+  if (colsum != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) cs[c] = 0.f;
+    __syncthreads();
+  }
+  const long long total = (long long)B * HO * WO * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
     long long r = i / C8;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
-    float acc[8];
+    const int j = (int)(r % WO); r /= WO;
+    const int ih = (int)(r % HO);
+    const int b = (int)(r / HO);
+    float acc[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // windows containing row h: ho in {h/2 (dr = h - 2ho in {0,1}), h/2 - 1 (dr = 2, only when h even)}
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int ho = h / 2 - a;
-      const int dr = h - 2 * ho;
-      if (ho < 0 || ho >= HO || dr > 2) continue;
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int wo = w / 2 - c;
-        const int ds = w - 2 * wo;
-        if (wo < 0 || wo >= WO || ds > 2) continue;
+        for (int k = 0; k < 8; ++k) acc[a][c][k] = 0.f;
+#pragma unroll
+    for (int dho = -1; dho <= 0; ++dho) {
+      const int ho = ih + dho;
+      if (ho < 0) continue;
+#pragma unroll
+      for (int dwo = -1; dwo <= 0; ++dwo) {
+        const int wo = j + dwo;
+        if (wo < 0) continue;
         const long long o = ((((long long)b * HO + ho) * WO + wo) * C8 + c8) * 8;
         const uint2 av = *reinterpret_cast<const uint2*>(argmax + o);
         const uint4 gv = *reinterpret_cast<const uint4*>(dy + o);
         const uint8_t* ai = reinterpret_cast<const uint8_t*>(&av);
         const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gv);
-        const int code = dr * 3 + ds;
+        // window (ho,wo) covers rows 2ho..2ho+2: relative to this block's first row 2*ih: dr - 2*(ih-ho) in {0,1}
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (ai[j] == code) acc[j] += __bfloat162float(g[j]);
+        for (int k = 0; k < 8; ++k) {
+          const int code = ai[k];
+          const int pr = code / 3 + 2 * dho, pc = code % 3 + 2 * dwo;   // pixel position inside the 2x2 block
+          if (pr >= 0 && pr < 2 && pc >= 0 && pc < 2) {
+            const float gk = __bfloat162float(g[k]);
+            if (pr == 0 && pc == 0) acc[0][0][k] += gk;
+            else if (pr == 0) acc[0][1][k] += gk;
+            else if (pc == 0) acc[1][0][k] += gk;
+            else acc[1][1][k] += gk;
+          }
+        }
       }
     }
-    __nv_bfloat16 o8[8];
-    if (x != nullptr) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(x + i * 8);
-      const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
+    float lsum[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(__bfloat162float(xe[j]) > 0.f ? acc[j] : 0.f);
-    } else {
+    for (int k = 0; k < 8; ++k) lsum[k] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o8[j] = __float2bfloat16(acc[j]);
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long long off = ((((long long)b * H + 2 * ih + a) * W + 2 * j + c) * C8 + c8) * 8;
+        __nv_bfloat16 o8[8];
+        if (x != nullptr) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(x + off);
+          const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o8[k] = __float2bfloat16(__bfloat162float(xe[k]) > 0.f ? acc[a][c][k] : 0.f);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o8[k] = __float2bfloat16(acc[a][c][k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) lsum[k] += __bfloat162float(o8[k]);
+        *reinterpret_cast<uint4*>(dx + off) = *reinterpret_cast<uint4*>(o8);
+      }
     }
-    *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<uint4*>(o8);
+    if (colsum != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&cs[c8 * 8 + k], lsum[k]);
+    }
+  }
+  if (colsum != nullptr) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      if (cs[c] != 0.f) atomicAdd(colsum + c, cs[c]);
   }
 }
 
@@ -476,13 +518,14 @@ int urso_maxpool_fwd_f32(const float* x, float* y, int32_t B, int32_t H, int32_t
   return 0;
 }
 
-int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, int32_t B, int32_t H, int32_t W,
-                     int32_t C, void* stream) {
+int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx, float* colsum, int32_t B, int32_t H,
+                     int32_t W, int32_t C, void* stream) {
   URSO_REQUIRE(argmax && dy && dx, "null pointer");
-  const long long total = (long long)B * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  URSO_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && C <= 512, "maxpool_bwd needs even H, W and C %% 8 == 0, C <= 512");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(argmax), static_cast<const __nv_bfloat16*>(dy),
-      static_cast<__nv_bfloat16*>(dx), B, H, W, C);
+      static_cast<__nv_bfloat16*>(dx), colsum, B, H, W, C);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -451,11 +451,10 @@ class Engine:
                 h, w, c = g.shapes[X]
                 self.dact[X] = self._new((B, h, w, c))
                 key = colsum_for(X)
-                self.ops_bwd.append(OpRec(lambda X=X, h=h, w=w, c=c, key=key: (
-                    lib.call("urso_maxpool_bwd", None, self.argmax.data_ptr(),
-                             self.dact["pool1"].data_ptr(), self.dact[X].data_ptr(), B, h, w, c, S()),
-                    lib.call("urso_colsum_bf16", self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B * h * w, c,
-                             S())), "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 3.5, 2))
+                self.ops_bwd.append(OpRec(lambda X=X, h=h, w=w, c=c, key=key: lib.call(
+                    "urso_maxpool_bwd", None, self.argmax.data_ptr(), self.dact["pool1"].data_ptr(),
+                    self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B, h, w, c, S()),
+                    "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 1.4, 1))
                 self.colsum[X] = key
             else:
                 convs = cons_conv.get(X, [])

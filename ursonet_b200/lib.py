@@ -59,7 +59,7 @@ SIGNATURES = {
     "urso_wgrad_destroy": [_vp],
     "urso_stem_stage": [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_maxpool_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
-    "urso_maxpool_bwd": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "urso_maxpool_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_dense_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "urso_dense_bias_act": [_vp, _vp, _i32, _i32, _i32, _vp],
     "urso_dense_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
