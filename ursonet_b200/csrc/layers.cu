@@ -109,8 +109,20 @@ __global__ void maxpool_fwd_f32_kernel(const float* __restrict__ x, float* __res
 
 // ------------------------------------------------------------------------------------------ max-pool 3x3 / s2 'same'
 // Even H, W: TF pads only bottom/right, so window (ho,wo) covers rows 2ho..2ho+2, cols 2wo..2wo+2 clipped to the map.
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                   uint8_t* __restrict__ argmax, int B, int H, int W, int C) {
+// One thread = one output pixel x 8 channels, all arithmetic on packed bf16x2 / packed bytes (branch free):
+//   m = (new > best) per half-word, best = max, argmax bytes = select(m, code, arg).
+// Out-of-range taps are clamped to the last row / column: a duplicate of an earlier element never wins a strict '>'.
+__device__ __forceinline__ uint32_t gt_mask2(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ argmax,
+                                                          int B, int H, int W, int C) {
   const int HO = H / 2, WO = W / 2, C8 = C / 8;
   const long long total = (long long)B * HO * WO * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -119,45 +131,51 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     const int wo = (int)(r % WO); r /= WO;
     const int ho = (int)(r % HO);
     const int b = (int)(r / HO);
-    float best[8];
-    int arg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+    uint4 v[9];
 #pragma unroll
     for (int dr = 0; dr < 3; ++dr) {
-      const int h = 2 * ho + dr;
-      if (h >= H) continue;
+      const int h = min(2 * ho + dr, H - 1);
 #pragma unroll
       for (int ds = 0; ds < 3; ++ds) {
-        const int w = 2 * wo + ds;
-        if (w >= W) continue;
-        const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + c8 * 8);
-        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float f = __bfloat162float(e[j]);
-          if (f > best[j]) { best[j] = f; arg[j] = dr * 3 + ds; }   // strict > keeps the FIRST maximum
-        }
+        const int w = min(2 * wo + ds, W - 1);
+        v[dr * 3 + ds] = *reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * C + c8 * 8);
       }
     }
-    __nv_bfloat16 o[8];
+    uint4 best = v[0];
+    uint32_t arg_lo = 0u, arg_hi = 0u;   // packed argmax bytes of elements 0-3 / 4-7
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(best[j]);
-    *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<uint4*>(o);
-    if (argmax != nullptr) {
-      uint8_t a[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = (uint8_t)arg[j];
-      *reinterpret_cast<uint2*>(argmax + i * 8) = *reinterpret_cast<uint2*>(a);
+    for (int t = 1; t < 9; ++t) {
+      const uint32_t code4 = 0x01010101u * t;
+      const uint32_t m0 = gt_mask2(v[t].x, best.x), m1 = gt_mask2(v[t].y, best.y);
+      const uint32_t m2 = gt_mask2(v[t].z, best.z), m3 = gt_mask2(v[t].w, best.w);
+      best.x = max2(v[t].x, best.x); best.y = max2(v[t].y, best.y);
+      best.z = max2(v[t].z, best.z); best.w = max2(v[t].w, best.w);
+      const uint32_t bm_lo = __byte_perm(m0, m1, 0x6420), bm_hi = __byte_perm(m2, m3, 0x6420);   // half-word -> byte masks
+      arg_lo = (arg_lo & ~bm_lo) | (code4 & bm_lo);
+      arg_hi = (arg_hi & ~bm_hi) | (code4 & bm_hi);
     }
+    *reinterpret_cast<uint4*>(y + i * 8) = best;
+    if (argmax != nullptr) *reinterpret_cast<uint2*>(argmax + i * 8) = make_uint2(arg_lo, arg_hi);
   }
 }
 
 // dx[h,w,c] = [x>0] * sum over windows whose recorded argmax is (h,w) of dy.
-// One thread: a 2x2 block of input pixels x 8 channels.  The block (2i..2i+1, 2j..2j+1) is touched by exactly the four
-// windows (i-1..i) x (j-1..j), so their argmax / dy vectors are loaded once and routed to the four pixels in registers.
-// Optionally accumulates the per-channel sums of dx (d beta of the stem's BatchNorm): shared-memory atomics per block,
-// one global atomic per channel per block.
+// One thread = a 2x2 block of input pixels x 8 channels.  The block (2i..2i+1, 2j..2j+1) is touched by exactly the four
+// windows (i-1..i) x (j-1..j) and by 9 (window, pixel) combinations whose argmax code is a compile-time constant, so the
+// routing is a packed byte compare + mask (branch free).  Optionally accumulates the per-channel sums of dx (d beta of
+// the stem's BatchNorm): warp-shuffle pre-reduction, shared-memory accumulation, one global atomic per channel per block.
+__device__ __forceinline__ void route(float (&acc)[8], uint2 codes, uint4 g, uint32_t code) {
+  const uint32_t c4 = 0x01010101u * code;
+  const uint32_t e_lo = __vcmpeq4(codes.x, c4), e_hi = __vcmpeq4(codes.y, c4);          // 0xFF per matching byte
+  const uint32_t m0 = __byte_perm(e_lo, 0, 0x1100), m1 = __byte_perm(e_lo, 0, 0x3322);   // byte -> half-word masks
+  const uint32_t m2 = __byte_perm(e_hi, 0, 0x1100), m3 = __byte_perm(e_hi, 0, 0x3322);
+  const uint32_t g0 = g.x & m0, g1 = g.y & m1, g2 = g.z & m2, g3 = g.w & m3;
+  acc[0] += __uint_as_float(g0 << 16); acc[1] += __uint_as_float(g0 & 0xFFFF0000u);
+  acc[2] += __uint_as_float(g1 << 16); acc[3] += __uint_as_float(g1 & 0xFFFF0000u);
+  acc[4] += __uint_as_float(g2 << 16); acc[5] += __uint_as_float(g2 & 0xFFFF0000u);
+  acc[6] += __uint_as_float(g3 << 16); acc[7] += __uint_as_float(g3 & 0xFFFF0000u);
+}
+
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                           const uint8_t* __restrict__ argmax,
                                                           const __nv_bfloat16* __restrict__ dy,
@@ -169,13 +187,35 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     for (int c = threadIdx.x; c < C; c += blockDim.x) cs[c] = 0.f;
     __syncthreads();
   }
+  float lsum[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) lsum[k] = 0.f;
   const long long total = (long long)B * HO * WO * C8;
+  // grid stride is a multiple of C8 (host guarantees it), so a thread always handles the same 8 channels
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % C8);
     long long r = i / C8;
     const int j = (int)(r % WO); r /= WO;
     const int ih = (int)(r % HO);
     const int b = (int)(r / HO);
+    // the four windows (ih-1..ih) x (j-1..j); out-of-range ones contribute nothing (code 0xFF never matches)
+    uint2 cd[2][2];
+    uint4 g[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ho = ih - 1 + a, wo = j - 1 + c;
+        if (ho >= 0 && wo >= 0) {
+          const long long o = ((((long long)b * HO + ho) * WO + wo) * C8 + c8) * 8;
+          cd[a][c] = *reinterpret_cast<const uint2*>(argmax + o);
+          g[a][c] = *reinterpret_cast<const uint4*>(dy + o);
+        } else {
+          cd[a][c] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+          g[a][c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
     float acc[2][2][8];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -183,63 +223,55 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][c][k] = 0.f;
+    // pixel (pa,pc) of the block is element (dr,ds) = (pa + 2 - 2a, pc + 2 - 2c) of window (a,c) when that is in 0..2
 #pragma unroll
-    for (int dho = -1; dho <= 0; ++dho) {
-      const int ho = ih + dho;
-      if (ho < 0) continue;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int dwo = -1; dwo <= 0; ++dwo) {
-        const int wo = j + dwo;
-        if (wo < 0) continue;
-        const long long o = ((((long long)b * HO + ho) * WO + wo) * C8 + c8) * 8;
-        const uint2 av = *reinterpret_cast<const uint2*>(argmax + o);
-        const uint4 gv = *reinterpret_cast<const uint4*>(dy + o);
-        const uint8_t* ai = reinterpret_cast<const uint8_t*>(&av);
-        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gv);
-        // window (ho,wo) covers rows 2ho..2ho+2: relative to this block's first row 2*ih: dr - 2*(ih-ho) in {0,1}
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int code = ai[k];
-          const int pr = code / 3 + 2 * dho, pc = code % 3 + 2 * dwo;   // pixel position inside the 2x2 block
-          if (pr >= 0 && pr < 2 && pc >= 0 && pc < 2) {
-            const float gk = __bfloat162float(g[k]);
-            if (pr == 0 && pc == 0) acc[0][0][k] += gk;
-            else if (pr == 0) acc[0][1][k] += gk;
-            else if (pc == 0) acc[1][0][k] += gk;
-            else acc[1][1][k] += gk;
+        for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            const int dr = pa + 2 - 2 * a, ds = pc + 2 - 2 * c;
+            if (dr <= 2 && ds <= 2) route(acc[pa][pc], cd[a][c], g[a][c], dr * 3 + ds);
           }
-        }
-      }
-    }
-    float lsum[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) lsum[k] = 0.f;
+    for (int pa = 0; pa < 2; ++pa) {
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const long long off = ((((long long)b * H + 2 * ih + a) * W + 2 * j + c) * C8 + c8) * 8;
-        __nv_bfloat16 o8[8];
+      for (int pc = 0; pc < 2; ++pc) {
+        const long long off = ((((long long)b * H + 2 * ih + pa) * W + 2 * j + pc) * C8 + c8) * 8;
         if (x != nullptr) {
           const uint4 xv = *reinterpret_cast<const uint4*>(x + off);
           const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(&xv);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o8[k] = __float2bfloat16(__bfloat162float(xe[k]) > 0.f ? acc[a][c][k] : 0.f);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o8[k] = __float2bfloat16(acc[a][c][k]);
+          for (int k = 0; k < 8; ++k) acc[pa][pc][k] = __bfloat162float(xe[k]) > 0.f ? acc[pa][pc][k] : 0.f;
         }
+        __nv_bfloat162 o[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) lsum[k] += __bfloat162float(o8[k]);
-        *reinterpret_cast<uint4*>(dx + off) = *reinterpret_cast<uint4*>(o8);
+        for (int k = 0; k < 4; ++k) {
+          o[k] = __floats2bfloat162_rn(acc[pa][pc][2 * k], acc[pa][pc][2 * k + 1]);
+          lsum[2 * k] += __low2float(o[k]);
+          lsum[2 * k + 1] += __high2float(o[k]);
+        }
+        *reinterpret_cast<uint4*>(dx + off) = *reinterpret_cast<uint4*>(o);
       }
-    }
-    if (colsum != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&cs[c8 * 8 + k], lsum[k]);
     }
   }
   if (colsum != nullptr) {
+    // lanes l, l+8, l+16, l+24 of a warp hold the same channel group (C8 == 8) -> shuffle-reduce, then smem atomics
+    const int lane = threadIdx.x & 31;
+    if (C8 == 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        lsum[k] += __shfl_xor_sync(0xffffffffu, lsum[k], 8);
+        lsum[k] += __shfl_xor_sync(0xffffffffu, lsum[k], 16);
+      }
+    }
+    if (C8 != 8 || lane < 8) {
+      const int c8 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % C8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&cs[c8 * 8 + k], lsum[k]);
+    }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x)
       if (cs[c] != 0.f) atomicAdd(colsum + c, cs[c]);
@@ -523,6 +555,7 @@ int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx
   URSO_REQUIRE(argmax && dy && dx, "null pointer");
   URSO_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && C <= 512, "maxpool_bwd needs even H, W and C %% 8 == 0, C <= 512");
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  URSO_REQUIRE(256 % (C / 8) == 0, "C/8 must divide the block size");   // keeps a thread on one channel group
   maxpool_bwd_kernel<<<grid_for(total, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const uint8_t*>(argmax), static_cast<const __nv_bfloat16*>(dy),
       static_cast<__nv_bfloat16*>(dx), colsum, B, H, W, C);
