@@ -292,8 +292,11 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   int items = p.n_seg_groups * p.p_tiles * p.q_tiles;
   int split = d->split_k;
   if (split <= 0) {
-    split = (2 * sms + items - 1) / items;  // aim for ~2 waves
-    int max_split = p.n_pix_blocks / 8;     // at least 8 K-steps per CTA
+    // aim for just under 2 full waves (never a third, mostly empty one); at least 8 K-steps per CTA
+    split = (2 * sms) / items;
+    if (split < 1) split = 1;
+    if (items * split < sms && items * (split + 1) <= 2 * sms) ++split;
+    int max_split = p.n_pix_blocks / 8;
     if (max_split < 1) max_split = 1;
     if (split > max_split) split = max_split;
   }
