@@ -34,7 +34,7 @@ def make_cfg(args):
     cfg.BRANCH_SIZE = 1024               # pose_estimator.py:777
     cfg.NR_DENSE_LAYERS = 1              # pose_estimator.py:820
     cfg.ORI_BINS_PER_DIM = args.ori_resolution
-    cfg.REGRESS_ORI = False              # --classify_ori is the CLI default (pose_estimator.py:786)
+    cfg.REGRESS_ORI = bool(getattr(args, "regress_ori", False))   # --classify_ori is the CLI default (pose_estimator.py:786)
     cfg.REGRESS_LOC = True
     cfg.OPTIMIZER = "SGD"
     cfg.IMAGE_RESIZE_MODE = "pad64"
@@ -57,6 +57,8 @@ def synth_batch(cfg, B, seed):
                        torch.rand(B, generator=g) * 35 + 5], 1)
     q = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1)
     q = q * torch.where(q[:, 3:4] < 0, -1.0, 1.0)
+    if cfg.REGRESS_ORI:
+        return img, loc, q.float()
     enc = labels.OrientationEncoder(cfg.ORI_BINS_PER_DIM, cfg.BETA)
     ori = torch.from_numpy(enc.encode(q.numpy())).float()
     return img, loc, ori
@@ -143,6 +145,7 @@ def main():
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--height", type=int, default=600)
     ap.add_argument("--ori_resolution", type=int, default=16)
+    ap.add_argument("--regress_ori", action="store_true", help="quaternion regression head (BASELINE configs[2])")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
@@ -152,7 +155,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = make_cfg(args)
     workload = (f"{args.backbone} ori_resolution={args.ori_resolution} {int(cfg.IMAGE_SHAPE[0])}x{int(cfg.IMAGE_SHAPE[1])} "
-                f"(from {args.width}x{args.height}) batch {args.batch}/GPU, SGD+clipnorm, classify_ori")
+                f"(from {args.width}x{args.height}) batch {args.batch}/GPU, SGD+clipnorm, "
+                f"{'regress_ori quaternion' if args.regress_ori else 'classify_ori'}")
     metric = "train images/sec ResNet-50 bf16 @960x600"
 
     if args.impl == "reference":
