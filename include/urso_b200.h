@@ -70,6 +70,9 @@ typedef struct {
   int32_t relu;
   float* colsum;      /* [b_rows] fp32 or NULL: atomically accumulates per-channel sums of the stored output */
   int32_t block_n;    /* N tile: 0 = auto, else 32 / 64 / 128 / 256 */
+  int32_t halo;       /* 1: halo reuse -- all segments are taps of ONE stride-1 view (n_a == 1, TW == 8, TH == 16): each
+                         64-channel chunk of the input patch (+ its halo) is fetched once and every tap reads a
+                         row-shifted window of it from shared memory instead of re-fetching it from L2 */
 } urso_convgemm_desc;
 
 typedef struct urso_convgemm urso_convgemm_t;

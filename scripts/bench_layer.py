@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ursonet_b200 import lib, convplan as P
 
-def run(M, K, N, addend=False, mask=False, relu=True, block_n=0, colsum=False, reps=20, nsets=4, conv3=None):
+def run(M, K, N, addend=False, mask=False, relu=True, block_n=0, colsum=False, reps=20, nsets=4, conv3=None, halo=False):
     dev = "cuda"
     plans = []
     for s in range(nsets):
@@ -18,9 +18,10 @@ def run(M, K, N, addend=False, mask=False, relu=True, block_n=0, colsum=False, r
             out = torch.empty(B, h, w, N, dtype=torch.bfloat16, device=dev)
             ad = torch.randn(B, h, w, N, device=dev).to(torch.bfloat16) if addend else None
             mk = torch.randn(B, h, w, N, device=dev).to(torch.bfloat16) if mask else None
-            tw, th = P.pick_patch(h, w, 128)
+            tw, th = (8, 16) if halo else P.pick_patch(h, w, 128)
             cs = torch.zeros(N, device=dev) if colsum else None
-            plans.append(lib.ConvGemm([x], bmat, segs, out, w, h, B, tw, th, addend=ad, mask=mk, relu=relu, colsum=cs, block_n=block_n))
+            plans.append(lib.ConvGemm([x], bmat, segs, out, w, h, B, tw, th, addend=ad, mask=mk, relu=relu, colsum=cs,
+                                      block_n=block_n, halo=halo))
             flops = 2.0 * B * h * w * N * 9 * K
             nbytes = 2.0 * B * h * w * (K + N * (1 + addend + mask))
         else:
@@ -61,7 +62,11 @@ if __name__ == "__main__":
         ("st4 2a K1024 N256 bn128", dict(M=76800, K=1024, N=256, block_n=128)),
         ("st5 2c K512 N2048 +add", dict(M=19200, K=512, N=2048, addend=True)),
         ("st2 3x3 64->64", dict(M=0, K=64, N=64, conv3=(32, 160, 240))),
+        ("st2 3x3 64->64 halo", dict(M=0, K=64, N=64, conv3=(32, 160, 240), halo=True)),
+        ("st2 3x3 64->64 halo mask cs", dict(M=0, K=64, N=64, conv3=(32, 160, 240), halo=True, mask=True, relu=False, colsum=True)),
         ("st3 3x3 128->128", dict(M=0, K=128, N=128, conv3=(32, 80, 120))),
+        ("st3 3x3 128->128 halo", dict(M=0, K=128, N=128, conv3=(32, 80, 120), halo=True)),
+        ("st4 3x3 256->256 halo", dict(M=0, K=256, N=256, conv3=(32, 40, 60), halo=True)),
         ("st4 3x3 256->256", dict(M=0, K=256, N=256, conv3=(32, 40, 60))),
         ("st4 3x3 256->256 bn128", dict(M=0, K=256, N=256, conv3=(32, 40, 60), block_n=128)),
         ("st5 3x3 512->512", dict(M=0, K=512, N=512, conv3=(32, 20, 30))),

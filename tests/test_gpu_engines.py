@@ -18,7 +18,7 @@ def bf16_exact(*shape, scale=1.0, seed=0):
 
 
 def run_fwd(x, wk, scale, kh, stride, padding, shift=None, addend=None, mask=None, relu=False, out_fp32=False,
-            colsum=False, block_n=0, flatten=False):
+            colsum=False, block_n=0, flatten=False, halo=False):
     from ursonet_b200 import lib
     N, H, W, CI = x.shape
     CO = wk.shape[3]
@@ -42,9 +42,9 @@ def run_fwd(x, wk, scale, kh, stride, padding, shift=None, addend=None, mask=Non
         plan = lib.ConvGemm(views, bmat, segs, o, M, 1, 1, 128, 1, shift=sd, addend=a2, mask=m2, relu=relu, colsum=cs,
                             block_n=block_n)
     else:
-        tw, th = P.pick_patch(g.oh, g.ow, 128)
+        tw, th = (8, 16) if halo else P.pick_patch(g.oh, g.ow, 128)
         plan = lib.ConvGemm(views, bmat, segs, out, g.ow, g.oh, N, tw, th, shift=sd, addend=ad, mask=md, relu=relu,
-                            colsum=cs, block_n=block_n)
+                            colsum=cs, block_n=block_n, halo=halo)
     plan.launch()
     torch.cuda.synchronize()
     return out.double().cpu(), (cs.double().cpu() if cs is not None else None), bmat.double().cpu()
@@ -116,6 +116,27 @@ def test_engine_f_tma_epilogue_inputs_many_tiles(which, flatten):
     assert (got - ref).abs().max().item() <= (2 ** -8 + 2e-3) * ref.abs().max().item()
     # column sums are taken over the bf16-rounded stored values
     assert torch.allclose(cs, got.sum((0, 1, 2)), rtol=2e-3, atol=1e-2 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,h,w,out_fp32", [(64, 64, 32, 24, True), (64, 64, 32, 24, False),
+                                                  (128, 128, 20, 30, False), (256, 64, 48, 40, False),
+                                                  (64, 128, 160, 240, False)])
+def test_engine_f_halo_mode(cin, cout, h, w, out_fp32):
+    """3x3 taps served from ONE halo tile per channel chunk (row-shifted UMMA descriptors) == per-tap TMA loads."""
+    nb = 2
+    x = bf16_exact(nb, h, w, cin, seed=31)
+    wk = bf16_exact(3, 3, cin, cout, scale=0.05, seed=32)
+    scale = torch.ones(cout, dtype=torch.float64)
+    mask = bf16_exact(nb, h, w, cout, seed=33) if not out_fp32 else None
+    got, cs, _ = run_fwd(x, wk, scale, 3, 1, "same", mask=mask, out_fp32=out_fp32, colsum=not out_fp32, halo=True)
+    ref = ref_fwd(x, staged_kernel(wk, scale), 3, 1, "same", mask=mask)
+    assert torch.isfinite(got).all()
+    tol = 2e-3 if out_fp32 else 2 ** -8 + 2e-3
+    assert (got - ref).abs().max().item() <= tol * ref.abs().max().item()
+    if cs is not None:
+        assert torch.allclose(cs, got.sum((0, 1, 2)), rtol=2e-3, atol=1e-2 * ref.abs().max().item())
+    base, _, _ = run_fwd(x, wk, scale, 3, 1, "same", mask=mask, out_fp32=out_fp32, halo=False)
+    assert (got - base).abs().max().item() <= 1e-2 * ref.abs().max().item()
 
 
 def test_engine_f_epilogue_all_stages():

@@ -55,6 +55,13 @@ struct ConvGemmParams {
   int out_fp32, relu;
   const float* shift;
   float* colsum;
+  int dbg_row_shift, dbg_base_offset;   // descriptor experiments (scripts/exp_desc_shift.py)
+  // halo mode (3x3-style taps on one stride-1 view, TW == 8): ONE TMA box per channel chunk holds the whole
+  // (TH+dh range) x (TW+dw range) pixel halo; every tap's A operand is a row-shifted window of it (UMMA descriptors
+  // swizzle on absolute smem address bits, so a start shifted by whole 128-byte rows reads what TMA wrote).
+  CUtensorMap a_halo_map;
+  int halo, halo_w, halo_dw_min, halo_dh_min, halo_bytes;
+  int a_stages, a_stage_bytes, a_ring_bytes;
 };
 
 constexpr int kBlockM = 128;
@@ -124,14 +131,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kStages = p.stages;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kATileBytes;
+  uint8_t* sB = smem + p.a_ring_bytes;
   uint8_t* ctrl = sB + kStages * kBTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* ei_bar = tempty_bar + 2;                       // [8 warps][kMaxEiDepth]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 8 * kMaxEiDepth);
+  uint64_t* afull_bar = ei_bar + 8 * kMaxEiDepth;          // halo mode: A ring barriers
+  uint64_t* aempty_bar = afull_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
   float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + kColsumAccBytes);   // legacy epilogue only
 
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.a_maps[i]);
     tma_prefetch_desc(&p.b_map);
+    if (p.halo) tma_prefetch_desc(&p.a_halo_map);
     if (p.epi_tma) {
       tma_prefetch_desc(&p.out_map);
       tma_prefetch_desc(&p.add_map);
@@ -157,6 +167,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
     }
     for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -170,7 +184,35 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      int stage = 0, a_stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      const int c_chunks = p.seg[0].c_chunks;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n_tile, img, h0, w0;
+        decode_tile(p, tile, n_tile, img, h0, w0);
+        for (int c = 0; c < c_chunks; ++c) {
+          mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
+          mbar_arrive_expect_tx(&afull_bar[a_stage], p.halo_bytes);
+          tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afull_bar[a_stage], c * kBlockK,
+                      w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+          if (++a_stage == p.a_stages) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+          for (int s = 0; s < p.n_seg; ++s) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
+            tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
+                        n_tile * BLOCK_N);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -196,7 +238,49 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    if (lane == 0 && p.halo) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0, a_stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      const int c_chunks = p.seg[0].c_chunks;
+      const uint32_t sbo = p.halo_w * 128;   // next 8-pixel group = next patch row = halo_w smem rows further
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int c = 0; c < c_chunks; ++c) {
+          mbar_wait(&afull_bar[a_stage], a_phase);
+          const uint32_t a_base = smem_u32(sA + a_stage * p.a_stage_bytes);
+          for (int s = 0; s < p.n_seg; ++s) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const SegDev sg = p.seg[s];
+            const uint32_t a_addr = a_base + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
+            const uint32_t b_addr = smem_u32(sB + stage * kBTileBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, sbo);
+              uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (c | s | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&aempty_bar[a_stage]);   // the halo tile is free once all its taps' MMAs retire
+          if (++a_stage == p.a_stages) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -217,7 +301,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // K-major SW128: advancing 16 elements = 32 bytes inside the 128B swizzle row
-            uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t ad = umma_desc_sw128(a_addr + k * 32 + p.dbg_row_shift * 128, 16, 1024);
+            if (p.dbg_base_offset) ad |= (uint64_t)(((a_addr + p.dbg_row_shift * 128) >> 7) & 7) << 49;
             uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0);
           }
@@ -614,16 +699,57 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     epi_bytes = kLegacyScratchBytes;
   }
   h->block_n = bn;
-  const int stage_bytes = kATileBytes + bn * kBlockK * 2;
-  int stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes) / stage_bytes;
-  if (stages > 6) stages = 6;
-  if (stages < 2) {
-    set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
-    delete h;
-    return 2;
+  int stages;
+  if (d->halo) {
+    // validate + plan the halo ring: one box per channel chunk, B tiles in their own ring
+    int dw_min = 1 << 20, dw_max = -(1 << 20), dh_min = 1 << 20, dh_max = -(1 << 20);
+    bool ok = d->n_a == 1 && d->TW == 8 && d->TH == 16;
+    for (int s2 = 0; s2 < d->n_seg && ok; ++s2) {
+      ok = d->seg[s2].map_id == 0 && d->seg[s2].c_chunks == d->seg[0].c_chunks;
+      dw_min = d->seg[s2].dw < dw_min ? d->seg[s2].dw : dw_min;
+      dw_max = d->seg[s2].dw > dw_max ? d->seg[s2].dw : dw_max;
+      dh_min = d->seg[s2].dh < dh_min ? d->seg[s2].dh : dh_min;
+      dh_max = d->seg[s2].dh > dh_max ? d->seg[s2].dh : dh_max;
+    }
+    if (!ok || dw_max - dw_min > 8 || dh_max - dh_min > 16) {
+      set_error("halo mode needs one stride-1 view, TW == 8, TH == 16, equal chunk counts and small tap offsets");
+      delete h;
+      return 2;
+    }
+    p.halo = 1;
+    p.halo_w = 8 + dw_max - dw_min;
+    const int halo_h = 16 + dh_max - dh_min;
+    p.halo_dw_min = dw_min;
+    p.halo_dh_min = dh_min;
+    p.halo_bytes = p.halo_w * halo_h * 128;
+    p.a_stage_bytes = (p.halo_bytes + 1023) / 1024 * 1024;
+    p.a_stages = 3;
+    p.a_ring_bytes = p.a_stages * p.a_stage_bytes;
+    if (int rc = make_view_map(&p.a_halo_map, d->a[0], p.halo_w, halo_h)) {
+      delete h;
+      return rc;
+    }
+    const int btile = bn * kBlockK * 2;
+    stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes - p.a_ring_bytes) / btile;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 3) {
+      set_error("halo mode: not enough shared memory for the B ring (BLOCK_N=%d)", bn);
+      delete h;
+      return 2;
+    }
+  } else {
+    const int stage_bytes = kATileBytes + bn * kBlockK * 2;
+    stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) {
+      set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
+      delete h;
+      return 2;
+    }
+    p.a_ring_bytes = stages * kATileBytes;
   }
   p.stages = stages;
-  const int fixed = stages * stage_bytes + kCtrlBytes + kColsumAccBytes;
+  const int fixed = p.a_ring_bytes + stages * bn * kBlockK * 2 + kCtrlBytes + kColsumAccBytes;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
     p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
@@ -673,6 +799,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.relu = d->relu;
   p.shift = d->shift;
   p.colsum = d->colsum;
+  if (const char* e = getenv("URSO_DBG_ROW_SHIFT")) p.dbg_row_shift = atoi(e);
+  if (const char* e = getenv("URSO_DBG_BASE_OFFSET")) p.dbg_base_offset = atoi(e);
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   h->grid = p.total_tiles < sms ? p.total_tiles : sms;

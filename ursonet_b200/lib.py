@@ -31,7 +31,7 @@ class ConvGemmDesc(C.Structure):
                 ("b_k", C.c_int32), ("seg", Seg * MAX_SEGS), ("n_seg", C.c_int32),
                 ("OW", C.c_int32), ("OH", C.c_int32), ("NB", C.c_int32), ("TW", C.c_int32), ("TH", C.c_int32),
                 ("out", Pix), ("out_fp32", C.c_int32), ("shift", C.c_void_p), ("addend", Pix), ("mask", Pix),
-                ("relu", C.c_int32), ("colsum", C.c_void_p), ("block_n", C.c_int32)]
+                ("relu", C.c_int32), ("colsum", C.c_void_p), ("block_n", C.c_int32), ("halo", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -151,7 +151,7 @@ class ConvGemm:
     """Owning wrapper of a urso_convgemm_t plan (tensor maps are encoded once; launch is graph-capturable)."""
 
     def __init__(self, a_views, b, segs, out, OW, OH, NB, TW, TH, shift=None, addend=None, mask=None, relu=False,
-                 colsum=None, block_n=0):
+                 colsum=None, block_n=0, halo=False):
         import torch
         d = ConvGemmDesc()
         assert 1 <= len(a_views) <= MAX_AMAPS and 1 <= len(segs) <= MAX_SEGS
@@ -171,6 +171,7 @@ class ConvGemm:
         d.relu = int(relu)
         d.colsum = ptr(colsum)
         d.block_n = block_n
+        d.halo = int(halo)
         self._keep = (a_views, b, out, shift, addend, mask, colsum)   # keep tensors alive
         h = _vp()
         check(load().urso_convgemm_create(C.byref(d), C.byref(h)), "urso_convgemm_create")
