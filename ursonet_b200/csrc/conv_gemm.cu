@@ -182,9 +182,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA issuer: ALL lanes of the warp run the (warp-uniform) control flow and barrier waits; one elected
+  // lane issues the TMA / tcgen05 instructions.  Keeping the loop state warp-uniform lets the compiler hold it in
+  // uniform registers -- a loop that lives inside `if (lane == 0)` costs ~130 SASS instructions per K step in R2UR /
+  // ELECT shuffling and made the single issuing thread the bottleneck of every small-N tile.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && p.halo) {
+    if (p.halo) {
       int stage = 0, a_stage = 0;
       uint32_t phase = 0, a_phase = 0;
       const int c_chunks = p.seg[0].c_chunks;
@@ -193,18 +197,24 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         decode_tile(p, tile, n_tile, img, h0, w0);
         for (int c = 0; c < c_chunks; ++c) {
           mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
-          mbar_arrive_expect_tx(&afull_bar[a_stage], p.halo_bytes);
-          tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afull_bar[a_stage], c * kBlockK,
-                      w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull_bar[a_stage], p.halo_bytes);
+            tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afull_bar[a_stage], c * kBlockK,
+                        w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+          }
+          __syncwarp();
           if (++a_stage == p.a_stages) {
             a_stage = 0;
             a_phase ^= 1;
           }
           for (int s = 0; s < p.n_seg; ++s) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
-            tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
-                        n_tile * BLOCK_N);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
+              tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
+                          n_tile * BLOCK_N);
+            }
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -223,10 +233,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
-            tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
-                        h0 + sg.dh, img);
-            tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
+              tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
+                          h0 + sg.dh, img);
+              tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+            }
+            __syncwarp();
             kcol += kBlockK;
             if (++stage == kStages) {
               stage = 0;
@@ -237,51 +250,55 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0 && p.halo) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    // descriptor = constant high word | (smem address >> 4); advancing K by 16 elements (32 B) adds 2 to the low word
+    constexpr uint64_t kDescHiB = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    if (p.halo) {
       int stage = 0, a_stage = 0;
       uint32_t phase = 0, a_phase = 0;
       const int c_chunks = p.seg[0].c_chunks;
-      const uint32_t sbo = p.halo_w * 128;   // next 8-pixel group = next patch row = halo_w smem rows further
+      // next 8-pixel group = next patch row = halo_w smem rows further
+      const uint64_t desc_hi_a = (uint64_t((p.halo_w * 128) >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int c = 0; c < c_chunks; ++c) {
           mbar_wait(&afull_bar[a_stage], a_phase);
-          const uint32_t a_base = smem_u32(sA + a_stage * p.a_stage_bytes);
+          const uint32_t a_tile = a_base + a_stage * p.a_stage_bytes;
           for (int s = 0; s < p.n_seg; ++s) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const SegDev sg = p.seg[s];
-            const uint32_t a_addr = a_base + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
-            const uint32_t b_addr = smem_u32(sB + stage * kBTileBytes);
+            if (elect_one()) {
+              const SegDev sg = p.seg[s];
+              const uint32_t a_addr = a_tile + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
+              const uint64_t ad = desc_hi_a | (a_addr >> 4);
+              const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
+              umma_bf16(d_tmem, ad, bd, idesc, (c | s) != 0);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, sbo);
-              uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, ad, bd, idesc, (c | s | k) != 0);
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+              if (s == p.n_seg - 1) umma_commit(&aempty_bar[a_stage]);   // halo tile free once all taps retire
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&aempty_bar[a_stage]);   // the halo tile is free once all its taps' MMAs retire
           if (++a_stage == p.a_stages) {
             a_stage = 0;
             a_phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (elect_one()) umma_commit(&tfull_bar[as]);
+        __syncwarp();
       }
-    } else if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       int ksteps = 0;
@@ -289,30 +306,28 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kATileBytes);
-          const uint32_t b_addr = smem_u32(sB + stage * kBTileBytes);
+          if (elect_one()) {
+            const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
+            const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
+            umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // K-major SW128: advancing 16 elements = 32 bytes inside the 128B swizzle row
-            uint64_t ad = umma_desc_sw128(a_addr + k * 32 + p.dbg_row_shift * 128, 16, 1024);
-            if (p.dbg_base_offset) ad |= (uint64_t)(((a_addr + p.dbg_row_shift * 128) >> 7) & 7) << 49;
-            uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (ks | k) != 0);
+            for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && (p.epi_tma || warp < 8)) {
