@@ -19,7 +19,8 @@
 //  * optional fused per-channel sums of the stored output (d beta): read back from the bf16 output slab
 //    (conflict free), accumulated per CTA in shared memory, flushed with one atomic per channel per CTA.
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue
+// Roles (384 threads): warps 0 and 3 = TMA producers (even / odd K steps), warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-11 = epilogue
 // (4 TMEM lane quadrants x 2 column halves).
 #include "common.cuh"
 #include "ptx.cuh"
@@ -186,8 +187,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   // lane issues the TMA / tcgen05 instructions.  Keeping the loop state warp-uniform lets the compiler hold it in
   // uniform registers -- a loop that lives inside `if (lane == 0)` costs ~130 SASS instructions per K step in R2UR /
   // ELECT shuffling and made the single issuing thread the bottleneck of every small-N tile.
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------------ TMA producers (two warps: even / odd K steps;
+    // a single issuing thread cannot arm a barrier and issue two TMA loads per 128-cycle K step of a small-N tile)
+    const int par = warp == 0 ? 0 : 1;
+    int g = 0;   // global K-step counter of this CTA
     if (p.halo) {
       int stage = 0, a_stage = 0;
       uint32_t phase = 0, a_phase = 0;
@@ -196,8 +200,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         int n_tile, img, h0, w0;
         decode_tile(p, tile, n_tile, img, h0, w0);
         for (int c = 0; c < c_chunks; ++c) {
-          mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
-          if (elect_one()) {
+          if (par == 0) mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
+          if (par == 0 && elect_one()) {
             mbar_arrive_expect_tx(&afull_bar[a_stage], p.halo_bytes);
             tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afull_bar[a_stage], c * kBlockK,
                         w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
@@ -207,14 +211,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             a_stage = 0;
             a_phase ^= 1;
           }
-          for (int s = 0; s < p.n_seg; ++s) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
-              tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
-                          n_tile * BLOCK_N);
+          for (int s = 0; s < p.n_seg; ++s, ++g) {
+            if ((g & 1) == par) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
+                tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
+                            n_tile * BLOCK_N);
+              }
+              __syncwarp();
             }
-            __syncwarp();
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -231,15 +237,17 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         int kcol = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
-          for (int c = 0; c < sg.c_chunks; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
-              tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
-                          h0 + sg.dh, img);
-              tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+          for (int c = 0; c < sg.c_chunks; ++c, ++g) {
+            if ((g & 1) == par) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
+                tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
+                            h0 + sg.dh, img);
+                tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+              }
+              __syncwarp();
             }
-            __syncwarp();
             kcol += kBlockK;
             if (++stage == kStages) {
               stage = 0;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tfull_bar[as], aphase);
+        mbar_wait_relaxed(&tfull_bar[as], aphase);
         tc_fence_after();
         while (cur.valid && cur.tile == tile) {
           const int j = cur.j;

@@ -58,6 +58,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Long waits (an epilogue warp waiting for a whole tile of MMAs): let the hardware suspend the warp (time hint in ns)
+// instead of re-polling, so that it does not compete with the producer / MMA warps for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 // ------------------------------------------------------------------ TMA loads (tile mode)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
