@@ -87,72 +87,88 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t bytes = (QA + 2 * T) * kAtomBytes;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+  // Producer / MMA issuer: warp-uniform control flow in all lanes, one elected lane issues (keeps the loop state in
+  // uniform registers; a loop inside `if (lane == 0)` costs >100 SASS instructions per K step in R2UR shuffling).
+  // Two producer warps (0 and 3) take alternate K steps: each K step is (QA + 2T) separate 8 KB TMA boxes.
+  if (warp == 0 || warp == 3) {
+    const int par = warp == 0 ? 0 : 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t bytes = (QA + 2 * T) * kAtomBytes;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      if (((kb - kb_begin) & 1) == par) {
         const int twi = kb % p.tiles_w;
         const int rest = kb / p.tiles_w;
         const int thi = rest % p.tiles_h;
         const int img = rest / p.tiles_h;
         const int h0 = thi * p.TH, w0 = twi * p.TW;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], bytes);
-        uint8_t* base = smem + stage * p.stage_bytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          uint8_t* base = smem + stage * p.stage_bytes;
 #pragma unroll 1
-        for (int a = 0; a < QA; ++a)
-          tma_load_4d(base + a * kAtomBytes, &p.q_map, &full_bar[stage], q_tile * BLOCK_Q + a * 64, w0, h0, img);
-        uint8_t* pbase = base + QA * kAtomBytes;
+          for (int a = 0; a < QA; ++a)
+            tma_load_4d(base + a * kAtomBytes, &p.q_map, &full_bar[stage], q_tile * BLOCK_Q + a * 64, w0, h0, img);
+          uint8_t* pbase = base + QA * kAtomBytes;
 #pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-          if (p.pair_mode) {
-            const int ta = 2 * (seg0 + t), tb = min(ta + 1, p.n_seg - 1);   // odd tap count: the last atom repeats a tap
-            const WSegDev sa = p.seg[ta], sb = p.seg[tb];
-            tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sa.map_id], &full_bar[stage], 0, w0 + sa.dw, h0 + sa.dh, img);
-            tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sb.map_id], &full_bar[stage], 0, w0 + sb.dw, h0 + sb.dh,
-                        img);
-          } else {
-            const WSegDev sg = p.seg[seg0 + t];
-            tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128, w0 + sg.dw,
-                        h0 + sg.dh, img);
-            tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128 + 64,
-                        w0 + sg.dw, h0 + sg.dh, img);
+          for (int t = 0; t < T; ++t) {
+            if (p.pair_mode) {
+              const int ta = 2 * (seg0 + t), tb = min(ta + 1, p.n_seg - 1);   // odd tap count: the last atom repeats a tap
+              const WSegDev sa = p.seg[ta], sb = p.seg[tb];
+              tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sa.map_id], &full_bar[stage], 0, w0 + sa.dw, h0 + sa.dh,
+                          img);
+              tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sb.map_id], &full_bar[stage], 0, w0 + sb.dw,
+                          h0 + sb.dh, img);
+            } else {
+              const WSegDev sg = p.seg[seg0 + t];
+              tma_load_4d(pbase + (2 * t) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128, w0 + sg.dw,
+                          h0 + sg.dh, img);
+              tma_load_4d(pbase + (2 * t + 1) * kAtomBytes, &p.p_maps[sg.map_id], &full_bar[stage], p_tile * 128 + 64,
+                          w0 + sg.dw, h0 + sg.dh, img);
+            }
           }
         }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        __syncwarp();
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_Q, 1, 1);  // both operands MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(smem + stage * p.stage_bytes);
-        const uint32_t p_addr = q_addr + QA * kAtomBytes;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_Q, 1, 1);  // both operands MN-major
+    // MN-major SW128 descriptor: LBO = distance between 64-channel atoms (8 KB), SBO = 1 KB between 8-pixel groups
+    constexpr uint64_t kDescHi = (uint64_t(1024 >> 4) << 32) | (uint64_t(kAtomBytes >> 4) << 16) | (1ull << 46) | (2ull << 61);
+    const uint32_t s_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t q_addr = s_base + stage * p.stage_bytes;
+        const uint64_t bd = kDescHi | (q_addr >> 4);
+        const uint32_t first = kb > kb_begin;
+#pragma unroll 1
         for (int t = 0; t < T; ++t) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x UMMA_K(16) = 4 x two 8-pixel groups (2 KB)
-            uint64_t ad = umma_desc_sw128(p_addr + (2 * t) * kAtomBytes + k * 2048, kAtomBytes, 1024);
-            uint64_t bd = umma_desc_sw128(q_addr + k * 2048, kAtomBytes, 1024);
-            umma_bf16(tmem_base + t * BLOCK_Q, ad, bd, idesc, (kb > kb_begin) || (k > 0));
-          }
+          const uint64_t ad = kDescHi | ((q_addr + (QA + 2 * t) * kAtomBytes) >> 4);
+          const uint32_t d = tmem_base + t * BLOCK_Q;
+          // 64 pixels = 4 x UMMA_K(16); 16 pixels = two 8-pixel groups = 2 KB -> +128 in descriptor units
+          umma_bf16(d, ad, bd, idesc, first);
+          umma_bf16(d, ad + 128, bd + 128, idesc, 1u);
+          umma_bf16(d, ad + 256, bd + 256, idesc, 1u);
+          umma_bf16(d, ad + 384, bd + 384, idesc, 1u);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
+    if (elect_one()) umma_commit(tfull_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
