@@ -63,6 +63,10 @@ struct ConvGemmParams {
   CUtensorMap a_halo_map;
   int halo, halo_w, halo_dw_min, halo_dh_min, halo_bytes;
   int a_stages, a_stage_bytes, a_ring_bytes;
+  // cluster mode: CTA pairs work on two adjacent M tiles of the same N tile; each CTA fetches HALF of the weight tile
+  // and multicasts it to both (halves the L2 -> SM traffic of B, which bounds the large-N tiles)
+  CUtensorMap b_half_map;
+  int cluster, total_pairs;
 };
 
 constexpr int kBlockM = 128;
@@ -90,6 +94,16 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, i
   w0 = twi * p.TW;
 }
 
+// Work items: tiles (one CTA each) or, in cluster mode, tile PAIRS (m_tile = 2*pair + cluster rank, same n_tile).
+__device__ __forceinline__ int work_first(const ConvGemmParams& p) { return p.cluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+__device__ __forceinline__ int work_step(const ConvGemmParams& p) { return p.cluster ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
+__device__ __forceinline__ int work_end(const ConvGemmParams& p) { return p.cluster ? p.total_pairs : p.total_tiles; }
+__device__ __forceinline__ int work_tile(const ConvGemmParams& p, int wk) {
+  if (!p.cluster) return wk;
+  const int ntn = p.n_tiles_n;
+  return (2 * (wk / ntn) + (int)(blockIdx.x & 1)) * ntn + wk % ntn;   // may lie beyond the last tile: an all-OOB dummy
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -100,25 +114,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
 template <int BLOCK_N>
 struct ChunkIter {
-  int tile, j, nch, n_tile, img, h0, w0;
+  int wk, tile, j, nch, n_tile, img, h0, w0;
   bool valid;
   __device__ __forceinline__ void load(const ConvGemmParams& p) {
-    valid = tile < p.total_tiles;
+    valid = wk < work_end(p);
     if (valid) {
+      tile = work_tile(p, wk);
       decode_tile(p, tile, n_tile, img, h0, w0);
       const int rem = p.ncols - n_tile * BLOCK_N;
       nch = (rem < BLOCK_N ? rem : BLOCK_N) / 64;
     }
   }
   __device__ __forceinline__ void init(const ConvGemmParams& p) {
-    tile = blockIdx.x;
+    wk = work_first(p);
     j = 0;
     load(p);
   }
   __device__ __forceinline__ void next(const ConvGemmParams& p) {
     if (++j >= nch) {
       j = 0;
-      tile += gridDim.x;
+      wk += work_step(p);
       load(p);
     }
   }
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.cluster ? 2 : 1);   // cluster: both CTAs' MMAs must have consumed the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -179,7 +194,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to it
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -196,9 +212,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int stage = 0, a_stage = 0;
       uint32_t phase = 0, a_phase = 0;
       const int c_chunks = p.seg[0].c_chunks;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
         int n_tile, img, h0, w0;
-        decode_tile(p, tile, n_tile, img, h0, w0);
+        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
         for (int c = 0; c < c_chunks; ++c) {
           if (par == 0) mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
           if (par == 0 && elect_one()) {
@@ -231,9 +247,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     } else {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const uint32_t crank = p.cluster ? (blockIdx.x & 1) : 0;
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
         int n_tile, img, h0, w0;
-        decode_tile(p, tile, n_tile, img, h0, w0);
+        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
         int kcol = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
@@ -244,7 +261,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
                 tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
                             h0 + sg.dh, img);
-                tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+                if (p.cluster)   // my half of the weight tile, delivered to both CTAs of the pair
+                  tma_load_2d_mcast(sB + stage * kBTileBytes + crank * (kBTileBytes / 2), &p.b_half_map, &full_bar[stage],
+                                    kcol, n_tile * BLOCK_N + crank * (BLOCK_N / 2), (uint16_t)3);
+                else
+                  tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
               }
               __syncwarp();
             }
@@ -270,7 +291,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       // next 8-pixel group = next patch row = halo_w smem rows further
       const uint64_t desc_hi_a = (uint64_t((p.halo_w * 128) >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int ksteps = 0;
       for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -326,7 +347,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
 #pragma unroll
             for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            // smem slot reusable once these MMAs retire (cluster: tell the peer too -- it multicasts into my stage)
+            if (p.cluster) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
+            else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -383,15 +406,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int it = 0;            // tiles of this CTA visited
       int tile_seen = -1;    // last tile whose accumulator this warp has waited for
       // every tile of the CTA is visited by BOTH warp sets (each must release the accumulator stage exactly once)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait_relaxed(&tfull_bar[as], aphase);
         tc_fence_after();
-        while (cur.valid && cur.tile == tile) {
+        while (cur.valid && cur.wk == wk) {
           const int j = cur.j;
           const int h = cur.h0 + rh, w = cur.w0 + rw;
-          const bool valid = (h < p.OH) && (w < p.OW);
+          const bool valid = (h < p.OH) && (w < p.OW) && (cur.img < p.NB);
           const int col0 = cur.n_tile * BLOCK_N + j * 64;
           const int slot = n_done % kEiDepth;
           const uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
@@ -505,13 +528,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     } else {
       // ---------------- legacy register epilogue (fp32 output / BLOCK_N == 32)
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         int n_tile, img, h0, w0;
-        decode_tile(p, tile, n_tile, img, h0, w0);
+        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
         const int h = h0 + rh, w = w0 + rw;
-        const bool valid = (h < p.OH) && (w < p.OW);
+        const bool valid = (h < p.OH) && (w < p.OW) && (img < p.NB);
         const long long o_off = (long long)img * p.out.sn + (long long)h * p.out.sh + (long long)w * p.out.sw;
         const long long a_off = (long long)img * p.addend.sn + (long long)h * p.addend.sh + (long long)w * p.addend.sw;
         const long long m_off = (long long)img * p.mask.sn + (long long)h * p.mask.sh + (long long)w * p.mask.sw;
@@ -615,7 +638,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -640,7 +664,23 @@ static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
                                       227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
+  if (h->params.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::conv_gemm_kernel<BLOCK_N>, h->params));
+  } else {
+    urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
+  }
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -814,6 +854,20 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     return 2;
   }
   p.total_tiles = (int)total;
+  {
+    // cluster pairs: on by default for non-halo launches with enough tiles; URSO_CLUSTER=0/1 overrides (experiments)
+    int want = (!p.halo && total >= 64) ? 1 : 0;
+    if (const char* e = getenv("URSO_CLUSTER")) want = atoi(e) && !p.halo;
+    if (want) {
+      const long long mt = (long long)p.tiles_w * p.tiles_h * d->NB;
+      p.cluster = 1;
+      p.total_pairs = (int)(((mt + 1) / 2) * p.n_tiles_n);
+      if (int rc = make_mat_map(&p.b_half_map, d->b, d->b_rows, d->b_k, bn / 2)) {
+        delete h;
+        return rc;
+      }
+    }
+  }
   p.ncols = d->b_rows;
   p.out = PixDev{d->out.ptr, d->out.sn, d->out.sh, d->out.sw};
   p.addend = PixDev{d->addend.ptr, d->addend.sn, d->addend.sh, d->addend.sw};
@@ -827,6 +881,10 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   int sms = num_sms();
   if (sms <= 0) sms = 148;
   h->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (p.cluster) {
+    const int nclusters = p.total_pairs < sms / 2 ? p.total_pairs : sms / 2;
+    h->grid = 2 * nclusters;
+  }
   *out = h;
   return 0;
 }
