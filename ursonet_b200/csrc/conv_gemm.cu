@@ -734,6 +734,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     }
   }
   int bn = d->block_n;
+  if (bn == 0 && d->b_rows >= 256) {
+    if (const char* e = getenv("URSO_BN_MAX")) bn = atoi(e);   // experiments: cap the N tile
+  }
   if (bn == 0) bn = d->b_rows >= 256 && d->b_rows % 256 == 0 ? 256 : (d->b_rows >= 128 ? 128 : (d->b_rows >= 64 ? 64 : 32));
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
     set_error("block_n=%d unsupported", bn);
@@ -855,9 +858,10 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   }
   p.total_tiles = (int)total;
   {
-    // cluster pairs: on by default for non-halo launches with enough tiles; URSO_CLUSTER=0/1 overrides (experiments)
-    int want = (!p.halo && total >= 64) ? 1 : 0;
-    if (const char* e = getenv("URSO_CLUSTER")) want = atoi(e) && !p.halo;
+    // cluster pairs (experimental, URSO_CLUSTER=1): measured slower on every layer -- a 2-CTA multicast does not reduce
+    // L2 -> SM traffic (the L2 already de-duplicates near-simultaneous unicast requests), see profiles/r01_progress.md
+    int want = 0;
+    if (const char* e = getenv("URSO_CLUSTER")) want = atoi(e) && !p.halo && total >= 64;
     if (want) {
       const long long mt = (long long)p.tiles_w * p.tiles_h * d->NB;
       p.cluster = 1;

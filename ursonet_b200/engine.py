@@ -12,6 +12,7 @@ Memory layout (HBM):
   staged GEMM operands             : bf16 K-major weight matrices with the frozen-BN scale folded in (rebuilt per step)
 """
 import math
+import os
 import re
 from typing import Dict, List, Optional
 
@@ -123,11 +124,15 @@ class ParamStore:
 
 
 class OpRec:
-    """One entry of a launch list: the callable plus what it is (for profiling / launch accounting)."""
-    __slots__ = ("fn", "kind", "name", "flops", "bytes", "launches")
+    """One entry of a launch list: the callable plus what it is (for profiling / launch accounting), the LANE (CUDA
+    stream) it is issued on and the ops of other lanes it must wait for (-> CUDA events / graph edges)."""
+    __slots__ = ("fn", "kind", "name", "flops", "bytes", "launches", "lane", "after", "event", "signal")
 
-    def __init__(self, fn, kind, name, flops=0.0, nbytes=0.0, launches=1):
+    def __init__(self, fn, kind, name, flops=0.0, nbytes=0.0, launches=1, lane=0, after=()):
         self.fn, self.kind, self.name, self.flops, self.bytes, self.launches = fn, kind, name, flops, nbytes, launches
+        self.lane, self.after, self.event, self.signal = lane, [a for a in after if a is not None], None, False
+        for a in self.after:
+            a.signal = True
 
     def __call__(self):
         self.fn()
@@ -137,7 +142,7 @@ class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
-                 parity=None):
+                 parity=None, n_slices=None):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -146,6 +151,22 @@ class Engine:
         if self.parity and training:
             raise NotImplementedError("PARITY_MODE (split-bf16 operands) is forward-only")
         self.graph: Graph = build_graph(cfg)
+        # Batch slices: the conv stack of every slice is an independent chain of launches issued on its own CUDA stream
+        # (lane), so the tail wave of one persistent kernel overlaps the head of another, and the small per-layer
+        # kernels (weight staging, parameter gradients: the "aux" lane) hide behind the convolutions.
+        # Lanes: 0 .. n_slices-1 = the slices' conv chains; optionally one more lane per slice for its weight-gradient
+        # launches (wgrad of a layer and the dgrad chain below it are independent); the last lane = "aux".
+        # URSO_LANES=0 puts everything on one stream.
+        if n_slices is None:
+            n_slices = int(os.environ.get("URSO_SLICES", "1"))
+        self.n_slices = 1 if self.parity else max(1, min(int(n_slices), self.B))
+        self.slices = [(self.B * i // self.n_slices, self.B * (i + 1) // self.n_slices) for i in range(self.n_slices)]
+        multi = (not self.parity) and int(os.environ.get("URSO_LANES", "1")) != 0
+        self.wgrad_lanes = multi and training and int(os.environ.get("URSO_WLANE", "1")) != 0
+        self.aux_lane = (self.n_slices * (2 if self.wgrad_lanes else 1)) if multi else 0
+        if not multi:
+            self.n_slices, self.slices = 1, [(0, self.B)]
+        self._lane_streams = None
         self.H, self.W = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
         self.params = ParamStore(self.graph, device, cfg.WEIGHT_DECAY)
         self.params.init_keras_defaults(seed)
@@ -220,6 +241,16 @@ class Engine:
             fn()
 
     # ------------------------------------------------------------------ plan helpers
+    @staticmethod
+    def _use_halo(k, stride, oh, ow, kc, n):
+        """Halo mode of Engine F (one TMA box per channel chunk shared by all 3x3 taps): needs an 8 x 16 pixel patch that
+        tiles the map without waste.  kc = reduction channels per tap, n = output channels."""
+        import os
+        mode = int(os.environ.get("URSO_HALO", "0"))
+        if not mode or k != 3 or stride != 1 or oh % 16 or ow % 8 or kc % 64:
+            return False
+        return n <= 64 if mode == 1 else True
+
     def _idx(self, values):
         t = torch.tensor(list(values), dtype=torch.int32, device=self.device)
         self._keep.append(t)
@@ -235,21 +266,28 @@ class Engine:
             bn = [None] * 4
         return w, bias, bn
 
+    def _add(self, lst, op):
+        """Append an op to a launch list, remembering the last op of its lane (join points depend on it)."""
+        lst.append(op)
+        self._last[op.lane] = op
+        return op
+
     def _build_forward(self):
         g, B = self.graph, self.B
         S = lib.stream_ptr
         self.ops_stage, self.ops_fwd, self.ops_loss = [], [], []
         self._late_binds = []
+        self._last = {}
         self.Bf: Dict[str, torch.Tensor] = {}
+        aux = self.aux_lane
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
             sc, sh = self.scale[c.name], self.shift[c.name]
-            self.ops_stage.append(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
+            self._add(self.ops_stage, OpRec(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
                 "urso_bn_fold", lib.ptr(bn[0]), lib.ptr(bn[1]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
-                sc.data_ptr(), sh.data_ptr(), c.cout, S()))
+                sc.data_ptr(), sh.data_ptr(), c.cout, S()), "stage", c.name, lane=aux))
             if c.stem:
                 segs, idx = P.stem_segments(), P.stem_weight_index(3)
-                geom = None
             else:
                 h, w_, _ = g.shapes[c.src]
                 geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w_)
@@ -258,41 +296,54 @@ class Engine:
             bmat = self._new((c.cout, K))
             self.Bf[c.name] = bmat
             idx_d = self._idx(idx)
-            self.ops_stage.append(lambda w=w, sc=sc, bmat=bmat, idx_d=idx_d, K=K, c=c: lib.call(
+            staged = self._add(self.ops_stage, OpRec(lambda w=w, sc=sc, bmat=bmat, idx_d=idx_d, K=K, c=c: lib.call(
                 "urso_stage_weight_rows", w.data_ptr(), sc.data_ptr(), bmat.data_ptr(), idx_d.data_ptr(), K, c.cout,
-                c.cout, K, 0, S()))
-            out = self.act[c.dst]
-            addend = self.act[c.addend] if c.addend else None
+                c.cout, K, 0, S()), "stage", c.name, lane=aux))
             oh, ow = g.shapes[c.dst][0], g.shapes[c.dst][1]
-            if c.stem:
-                tw, th = P.pick_patch(oh, ow, 128)
-                plan = lib.ConvGemm([self.E], bmat, segs, out, ow, oh, B, tw, th, shift=sh, relu=c.relu)
-            elif c.k == 1 and c.stride == 1:
-                M = B * oh * ow
-                x = self.act[c.src].view(1, 1, M, c.cin)
-                plan = lib.ConvGemm([x], bmat, segs, out.view(1, 1, M, c.cout), M, 1, 1, 128, 1, shift=sh,
-                                    addend=addend.view(1, 1, M, c.cout) if addend is not None else None, relu=c.relu)
-            else:
-                tw, th = P.pick_patch(oh, ow, 128)
-                plan = lib.ConvGemm(P.input_views(self.act[c.src], c.stride), bmat, segs, out, ow, oh, B, tw, th,
-                                    shift=sh, addend=addend, relu=c.relu)
-            self._keep.append(plan)
-            fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
-            nb = 2.0 * B * (g.shapes[c.src][0] * g.shapes[c.src][1] * c.cin if not c.stem else self.E[0].numel()) \
-                + (4.0 if c.out_fp32 else 2.0) * B * oh * ow * c.cout * (2 if c.addend else 1) + 2.0 * bmat.numel()
-            self.ops_fwd.append(OpRec(plan.launch, "conv_fwd", c.name, fl, nb))
             if c.stem:
                 ph, pw, _ = g.shapes[c.dst]
                 self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
-                src, dst = self.act[c.dst], self.act["pool1"]
-                self.ops_fwd.append(lambda src=src, dst=dst, ph=ph, pw=pw: lib.call(
-                    "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(self.argmax), B, ph, pw, 64, S()))
+            for si, (b0, b1) in enumerate(self.slices):
+                nb_ = b1 - b0
+                out = self.act[c.dst][b0:b1]
+                addend = self.act[c.addend][b0:b1] if c.addend else None
+                if c.stem:
+                    tw, th = P.pick_patch(oh, ow, 128)
+                    plan = lib.ConvGemm([self.E[b0:b1]], bmat, segs, out, ow, oh, nb_, tw, th, shift=sh, relu=c.relu)
+                elif c.k == 1 and c.stride == 1:
+                    M = nb_ * oh * ow
+                    x = self.act[c.src][b0:b1].view(1, 1, M, c.cin)
+                    plan = lib.ConvGemm([x], bmat, segs, out.view(1, 1, M, c.cout), M, 1, 1, 128, 1, shift=sh,
+                                        addend=addend.view(1, 1, M, c.cout) if addend is not None else None, relu=c.relu)
+                else:
+                    tw, th = P.pick_patch(oh, ow, 128)
+                    halo = self._use_halo(c.k, c.stride, oh, ow, c.cin, c.cout)
+                    if halo:
+                        tw, th = 8, 16
+                    plan = lib.ConvGemm(P.input_views(self.act[c.src][b0:b1], c.stride), bmat, segs, out, ow, oh, nb_, tw,
+                                        th, shift=sh, addend=addend, relu=c.relu, halo=halo)
+                self._keep.append(plan)
+                fl = 2.0 * nb_ * oh * ow * c.cout * c.k * c.k * c.cin
+                nb = 2.0 * nb_ * (g.shapes[c.src][0] * g.shapes[c.src][1] * c.cin if not c.stem else self.E[0].numel()) \
+                    + (4.0 if c.out_fp32 else 2.0) * nb_ * oh * ow * c.cout * (2 if c.addend else 1) + 2.0 * bmat.numel()
+                self._add(self.ops_fwd, OpRec(plan.launch, "conv_fwd", c.name, fl, nb, lane=si, after=[staged]))
+                if c.stem:
+                    src, dst = self.act[c.dst][b0:b1], self.act["pool1"][b0:b1]
+                    amax = self.argmax[b0:b1] if self.argmax is not None else None
+                    self._add(self.ops_fwd, OpRec(lambda src=src, dst=dst, amax=amax, ph=ph, pw=pw, nb_=nb_: lib.call(
+                        "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(amax), nb_, ph, pw, 64, S()),
+                        "pool_fwd", "pool1", 0.0, 2.0 * nb_ * ph * pw * 64 * 1.25, lane=si))
         self._build_heads_forward()
+
+    def _join_deps(self):
+        """Ops a lane-0 op must wait for so that every slice lane has finished what it was given so far."""
+        return [self._last.get(ln) for ln in range(1, self.n_slices)]
 
     def _build_heads_forward(self):
         g, B = self.graph, self.B
         S = lib.stream_ptr
-        # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332)
+        # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332); whole batch, lane 0
+        join = self._join_deps()
         for d in g.dense:
             w, b = self.params.view(d.name + "/kernel"), self.params.view(d.name + "/bias")
 
@@ -305,10 +356,13 @@ class Engine:
                 y = self.head[d.name]
                 lib.call("urso_dense_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), self.B, d.cin, d.cout, S())
                 lib.call("urso_dense_bias_act", y.data_ptr(), b.data_ptr(), self.B, d.cout, d.act, S())
-            self.ops_fwd.append(OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
+            self._add(self.ops_fwd, OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2,
+                                          after=join))
+            join = []
         if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
-            self.ops_fwd.append(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
-                                                 self.ori_q.data_ptr(), None, None, self.B, 1.0, S()))
+            self._add(self.ops_fwd, OpRec(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
+                                                           self.ori_q.data_ptr(), None, None, self.B, 1.0, S()),
+                                          "misc", "quat_head"))
 
     def _build_forward_parity(self):
         """Forward plan in split-bf16 precision (cfg.PARITY_MODE): every activation x is carried as fp32 plus the pair
@@ -319,6 +373,7 @@ class Engine:
         S = lib.stream_ptr
         self.ops_stage, self.ops_fwd, self.ops_loss = [], [], []
         self._late_binds = []
+        self._last = {}
         self.Bf = {}
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
@@ -395,7 +450,7 @@ class Engine:
                 z = self.head["ori_final"]
                 lib.call("urso_softmax_xent", z.data_ptr(), self.gt_ori.data_ptr(), self.dhead["ori_final"].data_ptr(),
                          ori_l.data_ptr(), B, z.shape[1], wo, S())
-        self.ops_loss.append(OpRec(loss_ops, "loss", "losses", launches=2))
+        self._add(self.ops_loss, OpRec(loss_ops, "loss", "losses", launches=2))
 
         # ---- heads backward (reverse order); dx of the first layer of each branch goes to dfeat[branch]
         for d in reversed(g.dense):
@@ -410,7 +465,7 @@ class Engine:
                 lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), self.head[d.name].data_ptr(),
                          self.dhead[d.name].data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, d.cin, d.cout,
                          d.act, S())
-            self.ops_bwd.append(OpRec(run, "dense_bwd", d.name, 4.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 3))
+            self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 4.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 3))
         if cfg.NR_DENSE_LAYERS == 0:
             raise NotImplementedError("NR_DENSE_LAYERS=0 backward")   # CLI fixes it to 1 (pose_estimator.py:820)
 
@@ -418,9 +473,9 @@ class Engine:
         bw = g.shapes["bottleneck_layer"][2]
         h6, w6 = g.shapes["bottleneck_layer"][:2]
         self.dact["bottleneck_layer"] = self._new((B, h6, w6, P.ceil64(bw)))   # zero padded bf16 operand
-        self.ops_bwd.append(lambda: lib.call(
+        self._add(self.ops_bwd, OpRec(lambda: lib.call(
             "urso_pad_cast_rows", self.dfeat[0].data_ptr(), self.dfeat[1].data_ptr(),
-            self.dact["bottleneck_layer"].data_ptr(), B * h6 * w6, bw, P.ceil64(bw), S()))
+            self.dact["bottleneck_layer"].data_ptr(), B * h6 * w6, bw, P.ceil64(bw), S()), "misc", "pad_cast"))
         producers = {c.dst: c for c in g.convs}
         cons_conv: Dict[str, List[ConvSpec]] = {}
         cons_add: Dict[str, List[ConvSpec]] = {}
@@ -440,21 +495,27 @@ class Engine:
         order = [c.dst for c in g.convs]
         order.insert(1, "pool1")
         self.Bd = {}
+        self._bwd_root = None
         for X in reversed(order):
             if X == "bottleneck_layer":
                 key = colsum_for(X)
-                self.ops_bwd.append(lambda key=key: lib.call(
+                # whole batch on lane 0; every slice lane starts its backward chain after this op (and after the
+                # dgrad weight staging of the aux lane)
+                self._bwd_root = self._add(self.ops_bwd, OpRec(lambda key=key: lib.call(
                     "urso_colsum_bf16", self.dact["bottleneck_layer"].data_ptr(), self._zero_view(key).data_ptr(),
-                    B * h6 * w6, P.ceil64(bw), S()))
+                    B * h6 * w6, P.ceil64(bw), S()), "misc", "colsum_bottleneck"))
                 self.colsum[X] = key
+                self._bwd_started = set()
             elif X == g.pool_src:     # stem output: gradient arrives through the max-pool
                 h, w, c = g.shapes[X]
                 self.dact[X] = self._new((B, h, w, c))
                 key = colsum_for(X)
-                self.ops_bwd.append(OpRec(lambda X=X, h=h, w=w, c=c, key=key: lib.call(
-                    "urso_maxpool_bwd", None, self.argmax.data_ptr(), self.dact["pool1"].data_ptr(),
-                    self.dact[X].data_ptr(), self._zero_view(key).data_ptr(), B, h, w, c, S()),
-                    "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 1.4, 1))
+                for si, (b0, b1) in enumerate(self.slices):
+                    am, dp, dx = self.argmax[b0:b1], self.dact["pool1"][b0:b1], self.dact[X][b0:b1]
+                    self._add(self.ops_bwd, OpRec(lambda am=am, dp=dp, dx=dx, h=h, w=w, c=c, key=key, n=b1 - b0: lib.call(
+                        "urso_maxpool_bwd", None, am.data_ptr(), dp.data_ptr(), dx.data_ptr(),
+                        self._zero_view(key).data_ptr(), n, h, w, c, S()),
+                        "pool_bwd", X, 0.0, 2.0 * (b1 - b0) * h * w * c * 1.4, 1, lane=si, after=self._bwd_deps(si)))
                 self.colsum[X] = key
             else:
                 convs = cons_conv.get(X, [])
@@ -471,9 +532,17 @@ class Engine:
             if X in producers:
                 self._build_wgrad(producers[X])
 
+    def _bwd_deps(self, lane):
+        """Cross-lane dependency of the FIRST backward op of a slice lane: the whole-batch head backward (lane 0).
+        Later ops of the lane are ordered behind it by the stream."""
+        if lane in self._bwd_started:
+            return []
+        self._bwd_started.add(lane)
+        return [self._bwd_root]
+
     def _build_dgrad_group(self, X, convs, adds, colsum_for, need_cs):
         """du_X = mask_X( sum_convs dgrad(du_conv.dst, W_conv) + sum_adds du_add.dst ), one Engine-F launch per
-        output phase with the convolutions' K ranges concatenated (fused gradient fan-in)."""
+        output phase (and batch slice) with the convolutions' K ranges concatenated (fused gradient fan-in)."""
         g, B = self.graph, self.B
         S = lib.stream_ptr
         h, w, cin = g.shapes[X]
@@ -486,15 +555,14 @@ class Engine:
         self.colsum[X] = key
         # pool1 = max of post-ReLU values: masking its gradient by (pool1 > 0) IS the stem's ReLU mask (a window's max
         # is 0 only when all its inputs are 0), so the max-pool backward does not have to read the stem output
-        mask = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
-        addend = self.dact[adds[0].dst] if adds else None
+        mask_all = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
         geoms = [P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w) for c in convs]
         phases = [P.dgrad_phases(gm) for gm in geoms]
         need_zero = False
         flat_ok = stride == 1 and all(c.k == 1 for c in convs)
-        launches = []
+        staged = []      # (phase index, segs, bmat)
+        stage_op = None  # last weight-staging op of this group (aux lane, in order: waiting for it covers them all)
         for pi in range(stride * stride):
-            oph, opw = phases[0][pi][0], phases[0][pi][1]
             segs, parts, ktot = [], [], 0
             for ci, c in enumerate(convs):
                 _, _, sg, tap_map = phases[ci][pi]
@@ -514,50 +582,62 @@ class Engine:
                 sc = self.scale[c.name]
                 tap_d = self._idx(tap_map)
                 dst = bmat[:, koff:]
-                self.ops_stage.append(lambda wk=wk, sc=sc, dst=dst, tap_d=tap_d, n=len(tap_map), c=c, cop=cop, ktot=ktot:
-                                      lib.call("urso_stage_weight_cols", wk.data_ptr(), sc.data_ptr(), dst.data_ptr(),
-                                               tap_d.data_ptr(), n, c.cin, c.cout, cop, c.cin, ktot, S()))
-            a_views = [self.dact[c.dst] for c in convs]
-            tgt = self.dact[X][:, oph::stride, opw::stride, :]
-            m_v = mask[:, oph::stride, opw::stride, :] if mask is not None else None
-            cs_key = key
-            if flat_ok:
-                M = B * h * w
-                a_views = [v.view(1, 1, M, v.shape[3]) for v in a_views]
-                launches.append(dict(a=a_views, b=bmat, segs=segs, out=self.dact[X].view(1, 1, M, cin), OW=M, OH=1, NB=1,
-                                     TW=128, TH=1, addend=addend.view(1, 1, M, cin) if addend is not None else None,
-                                     mask=mask.view(1, 1, M, cin) if mask is not None else None, cs=cs_key))
-            else:
-                th_, tw_ = tgt.shape[1], tgt.shape[2]
-                tw, th = P.pick_patch(th_, tw_, 128)
-                launches.append(dict(a=a_views, b=bmat, segs=segs, out=tgt, OW=tw_, OH=th_, NB=B, TW=tw, TH=th,
-                                     addend=addend, mask=m_v, cs=cs_key))
-        if need_zero:
-            buf = self.dact[X]
-            self.ops_bwd.append(lambda buf=buf: buf.zero_())
-        for L in launches:
-            def make(L=L):
-                plan_box = {}
+                stage_op = self._add(self.ops_stage, OpRec(
+                    lambda wk=wk, sc=sc, dst=dst, tap_d=tap_d, n=len(tap_map), c=c, cop=cop, ktot=ktot:
+                    lib.call("urso_stage_weight_cols", wk.data_ptr(), sc.data_ptr(), dst.data_ptr(), tap_d.data_ptr(), n,
+                             c.cin, c.cout, cop, c.cin, ktot, S()), "stage", c.name, lane=self.aux_lane))
+            staged.append((pi, segs, bmat))
+        for si, (b0, b1) in enumerate(self.slices):
+            nb_ = b1 - b0
+            dX = self.dact[X][b0:b1]
+            mask = mask_all[b0:b1] if mask_all is not None else None
+            addend = self.dact[adds[0].dst][b0:b1] if adds else None
+            if need_zero:
+                self._add(self.ops_bwd, OpRec(lambda dX=dX: dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(), lane=si,
+                                              after=self._bwd_deps(si)))
+            for pi, segs, bmat in staged:
+                oph, opw = phases[0][pi][0], phases[0][pi][1]
+                a_views = [self.dact[c.dst][b0:b1] for c in convs]
+                tgt = dX[:, oph::stride, opw::stride, :]
+                m_v = mask[:, oph::stride, opw::stride, :] if mask is not None else None
+                if flat_ok:
+                    M = nb_ * h * w
+                    L = dict(a=[v.view(1, 1, M, v.shape[3]) for v in a_views], b=bmat, segs=segs,
+                             out=dX.view(1, 1, M, cin), OW=M, OH=1, NB=1, TW=128, TH=1,
+                             addend=addend.view(1, 1, M, cin) if addend is not None else None,
+                             mask=mask.view(1, 1, M, cin) if mask is not None else None, cs=key)
+                else:
+                    th_, tw_ = tgt.shape[1], tgt.shape[2]
+                    tw, th = P.pick_patch(th_, tw_, 128)
+                    halo = len(convs) == 1 and self._use_halo(convs[0].k, stride, th_, tw_, convs[0].cout, cin)
+                    if halo:
+                        tw, th = 8, 16
+                    L = dict(a=a_views, b=bmat, segs=segs, out=tgt, OW=tw_, OH=th_, NB=nb_, TW=tw, TH=th,
+                             addend=addend, mask=m_v, cs=key, halo=halo)
 
-                def bind():
-                    cs = self._zero_view(L["cs"]) if L["cs"] else None
-                    plan_box["p"] = lib.ConvGemm(L["a"], L["b"], L["segs"], L["out"], L["OW"], L["OH"], L["NB"], L["TW"],
-                                                 L["TH"], addend=L["addend"], mask=L["mask"], colsum=cs)
-                self._late_binds.append(bind)
-                return lambda: plan_box["p"].launch()
-            fl = sum(2.0 * B * gm.oh * gm.ow * cv.cout * cv.k * cv.k * cv.cin for gm, cv in zip(geoms, convs)) / len(launches)
-            nb = 2.0 * (sum(v.numel() for v in L["a"]) + L["out"].numel() * (2 + (1 if L["addend"] is not None else 0))
-                        + L["b"].numel())
-            self.ops_bwd.append(OpRec(make(), "conv_dgrad", X, fl, nb))
+                def make(L=L):
+                    plan_box = {}
+
+                    def bind():
+                        cs = self._zero_view(L["cs"]) if L["cs"] else None
+                        plan_box["p"] = lib.ConvGemm(L["a"], L["b"], L["segs"], L["out"], L["OW"], L["OH"], L["NB"],
+                                                     L["TW"], L["TH"], addend=L["addend"], mask=L["mask"], colsum=cs,
+                                                     halo=L.get("halo", False))
+                    self._late_binds.append(bind)
+                    return lambda: plan_box["p"].launch()
+                fl = sum(2.0 * nb_ * gm.oh * gm.ow * cv.cout * cv.k * cv.k * cv.cin for gm, cv in zip(geoms, convs)) \
+                    / len(staged)
+                nbytes = 2.0 * (sum(v.numel() for v in L["a"]) + L["out"].numel() * (2 + (1 if addend is not None else 0))
+                                + bmat.numel())
+                self._add(self.ops_bwd, OpRec(make(), "conv_dgrad", X, fl, nbytes, lane=si,
+                                              after=self._bwd_deps(si) + [stage_op]))
 
     def _build_wgrad(self, c: ConvSpec):
         g, B = self.graph, self.B
         S = lib.stream_ptr
-        du = self.dact[c.dst]
-        qc = c.cout
         if c.stem:
             segs = [(m, dh, dw) for (m, dh, dw, _ch) in P.stem_segments()]
-            p_views, pc = [self.E], 64
+            pc = 64
             oh, ow = g.shapes[c.dst][:2]
             n_rows = 4 * 64
             row_map = self._idx(P.stem_grad_row_map(3))
@@ -565,10 +645,11 @@ class Engine:
             h, w, _ = g.shapes[c.src]
             geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
             segs = P.wgrad_segments(geom)
-            p_views, pc = P.input_views(self.act[c.src], c.stride), c.cin
+            pc = c.cin
             oh, ow = geom.oh, geom.ow
             n_rows = c.k * c.k * c.cin
             row_map = None
+        qc = c.cout
         gkey = "G:" + c.name
         self._zero_specs.append((gkey, n_rows * c.cout))
         skey = "S:" + c.name
@@ -576,25 +657,36 @@ class Engine:
             self._zero_specs.append((skey, c.cout))
         swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout
         flat = (not c.stem) and c.k == 1 and c.stride == 1
-        box = {}
+        wg_ops = []
+        for si, (b0, b1) in enumerate(self.slices):
+            nb_ = b1 - b0
+            du = self.dact[c.dst][b0:b1]
+            p_views = [self.E[b0:b1]] if c.stem else P.input_views(self.act[c.src][b0:b1], c.stride)
+            box = {}
 
-        def bind():
-            G = self._zero_view(gkey)
-            if flat:
-                M = B * oh * ow
-                xv, dv = self.act[c.src].view(1, 1, M, c.cin), du.view(1, 1, M, du.shape[3])
-                if swap:   # wide side on the 128-row MMA M dimension; transposed accumulation into HWIO
-                    box["p"] = lib.Wgrad([dv], xv, [(0, 0, 0)], qc, c.cin, M, 1, 1, 64, 1, G, c.cin * c.cout, 1, c.cout)
+            def bind(box=box, du=du, p_views=p_views, nb_=nb_, b0=b0, b1=b1):
+                G = self._zero_view(gkey)
+                if flat:
+                    M = nb_ * oh * ow
+                    xv, dv = self.act[c.src][b0:b1].view(1, 1, M, c.cin), du.view(1, 1, M, du.shape[3])
+                    if swap:   # wide side on the 128-row MMA M dimension; transposed accumulation into HWIO
+                        box["p"] = lib.Wgrad([dv], xv, [(0, 0, 0)], qc, c.cin, M, 1, 1, 64, 1, G, c.cin * c.cout, 1, c.cout)
+                    else:
+                        box["p"] = lib.Wgrad([xv], dv, [(0, 0, 0)], c.cin, qc, M, 1, 1, 64, 1, G, c.cin * c.cout, c.cout, 1)
                 else:
-                    box["p"] = lib.Wgrad([xv], dv, [(0, 0, 0)], c.cin, qc, M, 1, 1, 64, 1, G, c.cin * c.cout, c.cout, 1)
+                    tw, th = P.pick_patch(oh, ow, 64)
+                    box["p"] = lib.Wgrad(p_views, du, segs, pc, qc, ow, oh, nb_, tw, th, G, pc * c.cout, c.cout, 1)
+            self._late_binds.append(bind)
+            fl = 2.0 * nb_ * oh * ow * c.cout * c.k * c.k * c.cin
+            nb = 2.0 * (sum(v.numel() for v in p_views) + du.numel()) + 4.0 * n_rows * c.cout
+            if self.wgrad_lanes:   # own lane: ordered behind the dgrad that produced du (the last op of the slice lane)
+                lane, deps = self.n_slices + si, [self._last.get(si), self._bwd_root]
             else:
-                tw, th = P.pick_patch(oh, ow, 64)
-                box["p"] = lib.Wgrad(p_views, du, segs, pc, qc, ow, oh, B, tw, th, G, pc * c.cout, c.cout, 1)
-        self._late_binds.append(bind)
-        fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
-        nb = 2.0 * (sum(v.numel() for v in p_views) + du.numel()) + 4.0 * n_rows * c.cout
-        self.ops_bwd.append(OpRec(lambda: box["p"].launch(), "conv_wgrad", c.name, fl, nb))
-        # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form)
+                lane, deps = si, self._bwd_deps(si)
+            wg_ops.append(self._add(self.ops_bwd, OpRec(lambda box=box: box["p"].launch(), "conv_wgrad", c.name, fl, nb,
+                                                        lane=lane, after=deps)))
+        # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form):
+        # aux lane, after the wgrad (and with it the d-beta column sums) of EVERY slice
         w, bias, bn = self._conv_weight_ptrs(c)
         pv = self.params.view
         dW = pv(c.name + "/kernel", self.grads)
@@ -611,30 +703,66 @@ class Engine:
                      lib.ptr(cs), sc.data_ptr(), lib.ptr(bn[0]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
                      dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta),
                      self._zero_view(skey).data_ptr() if c.bn else None, R, c.cout, S())
-        self.ops_bwd.append(OpRec(run, "param_grads", c.name, 0.0, 12.0 * R * c.cout, 2))
+        self._add(self.ops_bwd, OpRec(run, "param_grads", c.name, 0.0, 12.0 * R * c.cout, 2, lane=self.aux_lane,
+                                      after=wg_ops))
 
     def _build_update(self):
         S = lib.stream_ptr
         p = self.params
         n = p.n_train
         self.ops_update = []
-        self.ops_update.append(lambda: lib.call(
+        self.ops_update.append(OpRec(lambda: lib.call(
             "urso_add_reg_sumsq", self.grads.data_ptr(), p.flat.data_ptr(), p.chunk_coef.data_ptr(),
-            p.chunk_lr.data_ptr(), 1.0 / self.world, self.sumsq.data_ptr(), n, S()))
+            p.chunk_lr.data_ptr(), 1.0 / self.world, self.sumsq.data_ptr(), n, S()), "update", "reg_sumsq"))
         if self.cfg.OPTIMIZER == "SGD":
-            self.ops_update.append(lambda: lib.call(
+            self.ops_update.append(OpRec(lambda: lib.call(
                 "urso_sgd_step", p.flat.data_ptr(), self.opt_state[0].data_ptr(), self.grads.data_ptr(),
-                p.chunk_lr.data_ptr(), self.sumsq.data_ptr(), self.hyper.data_ptr(), n, S()))
+                p.chunk_lr.data_ptr(), self.sumsq.data_ptr(), self.hyper.data_ptr(), n, S()), "update", "sgd"))
         else:
-            self.ops_update.append(lambda: lib.call(
+            self.ops_update.append(OpRec(lambda: lib.call(
                 "urso_amsgrad_step", p.flat.data_ptr(), self.opt_state[0].data_ptr(), self.opt_state[1].data_ptr(),
                 self.opt_state[2].data_ptr(), self.grads.data_ptr(), p.chunk_lr.data_ptr(), self.sumsq.data_ptr(),
-                self.hyper.data_ptr(), n, S()))
+                self.hyper.data_ptr(), n, S()), "update", "amsgrad"))
 
     # ------------------------------------------------------------------ running
+    def _fork(self):
+        """Start of a multi-lane phase: every lane stream waits for what the current (main) stream has been given."""
+        self._main = torch.cuda.current_stream()
+        if self.aux_lane == 0:
+            return
+        if self._lane_streams is None:
+            self._lane_streams = [None] + [torch.cuda.Stream(device=self.device) for _ in range(self.aux_lane)]
+        for st in self._lane_streams[1:]:
+            st.wait_stream(self._main)
+
+    def _join(self):
+        if self.aux_lane == 0:
+            return
+        for st in self._lane_streams[1:]:
+            self._main.wait_stream(st)
+
+    _serial = False      # profile_ops: issue everything on the current stream, in list order
+
     def _run(self, ops):
+        if self.aux_lane == 0 or self._serial:
+            for op in ops:
+                op()
+            return
+        main, streams = self._main, self._lane_streams
         for op in ops:
-            op()
+            st = main if op.lane == 0 else streams[op.lane]
+            for a in op.after:
+                if a.lane != op.lane:
+                    st.wait_event(a.event)
+            if op.lane == 0:
+                op()
+            else:
+                with torch.cuda.stream(st):
+                    op()
+            if op.signal:
+                if op.event is None:
+                    op.event = torch.cuda.Event()
+                op.event.record(st)
 
     def _stage_input(self):
         S = lib.stream_ptr
@@ -657,16 +785,26 @@ class Engine:
             self._graphs = {}
         self._input_kind = kind
 
-    def _phase_fwd(self):
+    def _fwd_body(self):
         self.zero_arena.zero_()
-        self._run(self.ops_stage)
         self._stage_input()
+        self._fork()
+        self._run(self.ops_stage)
         self._run(self.ops_fwd)
 
+    def _phase_fwd(self):
+        self._fwd_body()
+        self._join()
+
+    def _phase_update(self):
+        for op in self.ops_update:
+            op()
+
     def _phase_train(self):
-        self._phase_fwd()
+        self._fwd_body()
         self._run(self.ops_loss)
         self._run(self.ops_bwd)
+        self._join()
 
     def _replay(self, key, fn, use_graph=True):
         if not use_graph:
@@ -730,7 +868,7 @@ class Engine:
         self._replay("train", self._phase_train, use_graph)
         if allreduce is not None:
             allreduce(self.grads)
-        self._replay("update", lambda: self._run(self.ops_update), use_graph)
+        self._replay("update", self._phase_update, use_graph)
         self.opt_t += 1
 
     def count_launches(self, train=True):
@@ -751,6 +889,7 @@ class Engine:
         self._phase_train() if (train and self.training) else self._phase_fwd()    # valid buffers everywhere
         torch.cuda.synchronize()
         recs = {}
+        self._serial = True
         for _ in range(reps):
             self.zero_arena.zero_()
             self._run(self.ops_stage)
@@ -762,6 +901,7 @@ class Engine:
                 e1.record()
                 recs.setdefault(i, []).append((e0, e1))
         torch.cuda.synchronize()
+        self._serial = False
         out = []
         for i, op in enumerate(ops):
             if not isinstance(op, OpRec):
