@@ -36,6 +36,23 @@ struct PixDev {
   long long sn, sh, sw;
 };
 
+// Division of a 31-bit unsigned value by a launch-time constant (Granlund-Montgomery, round-up variant): 3 instructions
+// instead of the ~30 of a runtime integer division.  The tile decode runs once per 64-channel chunk in every epilogue
+// warp, so this is on the critical path of the memory-bound layers.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  f.shr = l;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
+
 struct ConvGemmParams {
   CUtensorMap a_maps[URSO_MAX_AMAPS];
   CUtensorMap b_map;
@@ -45,6 +62,7 @@ struct ConvGemmParams {
   int OW, OH, NB;
   int TW, TH, tw_shift;
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
+  FastDiv fd_ntn, fd_tw, fd_th;
   int ncols;
   int stages;        // mainloop ring depth (runtime: depends on how much smem the epilogue needs)
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
@@ -84,12 +102,13 @@ constexpr int kSmemBudget = 227 * 1024 - 1024;      // minus alignment slack
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
-  n_tile = tile % p.n_tiles_n;
-  int m_tile = tile / p.n_tiles_n;
-  int twi = m_tile % p.tiles_w;
-  int rest = m_tile / p.tiles_w;
-  int thi = rest % p.tiles_h;
-  img = rest / p.tiles_h;
+  const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntn);
+  n_tile = tile - (int)m_tile * p.n_tiles_n;
+  const uint32_t rest = fdiv(m_tile, p.fd_tw);
+  const int twi = (int)(m_tile - rest * (uint32_t)p.tiles_w);
+  const uint32_t im = fdiv(rest, p.fd_th);
+  const int thi = (int)(rest - im * (uint32_t)p.tiles_h);
+  img = (int)im;
   h0 = thi * p.TH;
   w0 = twi * p.TW;
 }
@@ -101,7 +120,8 @@ __device__ __forceinline__ int work_end(const ConvGemmParams& p) { return p.clus
 __device__ __forceinline__ int work_tile(const ConvGemmParams& p, int wk) {
   if (!p.cluster) return wk;
   const int ntn = p.n_tiles_n;
-  return (2 * (wk / ntn) + (int)(blockIdx.x & 1)) * ntn + wk % ntn;   // may lie beyond the last tile: an all-OOB dummy
+  const int q = (int)fdiv((uint32_t)wk, p.fd_ntn);
+  return (2 * q + (int)(blockIdx.x & 1)) * ntn + (wk - q * ntn);   // may lie beyond the last tile: an all-OOB dummy
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -122,7 +142,7 @@ struct ChunkIter {
       tile = work_tile(p, wk);
       decode_tile(p, tile, n_tile, img, h0, w0);
       const int rem = p.ncols - n_tile * BLOCK_N;
-      nch = (rem < BLOCK_N ? rem : BLOCK_N) / 64;
+      nch = (rem < BLOCK_N ? rem : BLOCK_N) >> 6;
     }
   }
   __device__ __forceinline__ void init(const ConvGemmParams& p) {
@@ -381,21 +401,24 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       uint8_t* ei = smem + p.ei_off + wslot * kEiDepth * slot_bytes;
       uint8_t* eo = smem + p.eo_off + wslot * kEoDepth * kSlabBytes;
       uint64_t* my_bar = ei_bar + wslot * kMaxEiDepth;
-      const int swz = lane & 7;
+      // byte offsets of this lane's eight 16-byte units inside a 128-byte swizzled row (unit u of row r sits at u ^ (r & 7))
+      int uoff[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) uoff[u] = lane * 128 + ((u ^ (lane & 7)) << 4);
       ChunkIter<BLOCK_N> cur, pf;
       cur.init(p);
       if (half == 1 && cur.valid) cur.next(p);     // set 1 starts at the second chunk of the stream
       pf = cur;
-      int n_pf = 0;                                // my chunks prefetched so far
+      int pf_slot = 0;                             // ring slot of the next prefetch
       auto issue_prefetch = [&]() {                // lane 0 only
-        const int slot = n_pf % kEiDepth;
+        const int slot = pf_slot;
+        if (++pf_slot == kEiDepth) pf_slot = 0;
         uint8_t* dst = ei + slot * slot_bytes;
         mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
         const int c = pf.n_tile * BLOCK_N + pf.j * 64;
         if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         if (p.has_mask)
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
-        ++n_pf;
         pf.next(p);
         if (pf.valid) pf.next(p);                  // my chunks are every other one
       };
@@ -403,8 +426,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
       }
       int n_done = 0;        // my chunks consumed so far
+      int in_slot = 0, out_slot = 0;   // ring positions (kept incrementally: no runtime modulo on the critical path)
+      uint32_t in_phase = 0;
       int it = 0;            // tiles of this CTA visited
-      int tile_seen = -1;    // last tile whose accumulator this warp has waited for
       // every tile of the CTA is visited by BOTH warp sets (each must release the accumulator stage exactly once)
       for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
@@ -413,12 +437,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         tc_fence_after();
         while (cur.valid && cur.wk == wk) {
           const int j = cur.j;
-          const int h = cur.h0 + rh, w = cur.w0 + rw;
-          const bool valid = (h < p.OH) && (w < p.OW) && (cur.img < p.NB);
           const int col0 = cur.n_tile * BLOCK_N + j * 64;
-          const int slot = n_done % kEiDepth;
-          const uint8_t* in_slab = ei + slot * slot_bytes + lane * 128;
-          uint8_t* out_slab = eo + (n_done % kEoDepth) * kSlabBytes;
+          const uint8_t* in_slab = ei + in_slot * slot_bytes;
+          uint8_t* out_slab = eo + out_slot * kSlabBytes;
+          // rows outside the image are clipped by the TMA store; they only have to be zeroed for the column sums
+          const bool valid = p.colsum == nullptr ||
+                             ((cur.h0 + rh < p.OH) && (cur.w0 + rw < p.OW) && (cur.img < p.NB));
           if (n_done >= kEoDepth) {   // the TMA store that last used this output slab must have drained it
             if (lane == 0) {
               if (kEoDepth >= 3) tma_store_wait_read<2>();
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             }
             __syncwarp();
           }
-          if (n_in > 0) mbar_wait(&my_bar[slot], (n_done / kEiDepth) & 1);
+          if (n_in > 0) mbar_wait(&my_bar[in_slot], in_phase);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint32_t acc[32];
@@ -450,7 +474,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             if (p.has_add) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(in_slab + (((hf * 4 + i) ^ swz) << 4));
+                const uint4 u = *reinterpret_cast<const uint4*>(in_slab + uoff[hf * 4 + i]);
                 v[8 * i + 0] += bf16_lo(u.x);
                 v[8 * i + 1] += bf16_hi(u.x);
                 v[8 * i + 2] += bf16_lo(u.y);
@@ -478,20 +502,21 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(ms + (((hf * 4 + i) ^ swz) << 4));
+                const uint4 u = *reinterpret_cast<const uint4*>(ms + uoff[hf * 4 + i]);
                 pk[4 * i + 0] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.x), z2);
                 pk[4 * i + 1] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.y), z2);
                 pk[4 * i + 2] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.z), z2);
                 pk[4 * i + 3] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&u.w), z2);
               }
             }
-            // rows outside the image are clipped by the TMA store; zero them so the column sums ignore them
+            if (!valid) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-              if (!valid) o = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(out_slab + lane * 128 + (((hf * 4 + i) ^ swz) << 4)) = o;
+              for (int i = 0; i < 16; ++i) pk[i] = 0u;
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(out_slab + uoff[hf * 4 + i]) =
+                  make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();          // all lanes have finished reading the input slot and writing the output slab
@@ -515,10 +540,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1);
           }
           ++n_done;
+          if (++in_slot == kEiDepth) {
+            in_slot = 0;
+            in_phase ^= 1;
+          }
+          if (++out_slot == kEoDepth) out_slot = 0;
           cur.next(p);
           if (cur.valid) cur.next(p);   // skip the other warp set's chunk
         }
-        (void)tile_seen;
         // all of this warp's TMEM reads of the tile are complete: release the accumulator stage (8 arrivals)
         tc_fence_before();
         __syncwarp();
@@ -850,6 +879,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.tiles_w = (d->OW + d->TW - 1) / d->TW;
   p.tiles_h = (d->OH + d->TH - 1) / d->TH;
   p.n_tiles_n = (d->b_rows + bn - 1) / bn;
+  p.fd_ntn = make_fastdiv((uint32_t)p.n_tiles_n);
+  p.fd_tw = make_fastdiv((uint32_t)p.tiles_w);
+  p.fd_th = make_fastdiv((uint32_t)p.tiles_h);
   long long total = (long long)p.tiles_w * p.tiles_h * d->NB * p.n_tiles_n;
   if (total <= 0 || total > 0x7fffffffLL) {
     set_error("bad tile count %lld", total);
