@@ -163,8 +163,9 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   constexpr int kTmemCols = 2 * BLOCK_N;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte aligned by declaration (SWIZZLE_128B atoms): no integer round trip on the base pointer, so the compiler
+  // keeps the shared address space and emits LDS/STS/ATOMS with 32-bit addresses instead of generic accesses
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int kStages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.a_ring_bytes;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     }
     fence_barrier_init();
   }
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled layouts assume it
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   if (p.colsum != nullptr) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;

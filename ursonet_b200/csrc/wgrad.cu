@@ -45,8 +45,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int BLOCK_Q>
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   constexpr int QA = BLOCK_Q / 64;  // 64-channel atoms in the Q tile
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B atoms need 1 KB alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
@@ -81,6 +80,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled layouts assume it
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();

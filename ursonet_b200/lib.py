@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liburso_b200.so")
+LIB_PATH = os.environ.get("URSO_LIB_PATH") or os.path.join(_HERE, "liburso_b200.so")   # override: A/B experiments
 
 MAX_AMAPS = 8
 MAX_SEGS = 32
