@@ -75,6 +75,7 @@ struct ConvGemmParams {
   const float* shift;
   float* colsum;
   int dbg_row_shift, dbg_base_offset;   // descriptor experiments (scripts/exp_desc_shift.py)
+  int dbg_no_tma, dbg_no_mma;            // bottleneck isolation (URSO_DBG_NO_TMA / URSO_DBG_NO_MMA): results are garbage
   // halo mode (3x3-style taps on one stride-1 view, TW == 8): ONE TMA box per channel chunk holds the whole
   // (TH+dh range) x (TW+dw range) pixel halo; every tap's A operand is a row-shifted window of it (UMMA descriptors
   // swizzle on absolute smem address bits, so a start shifted by whole 128-byte rows reads what TMA wrote).
@@ -279,7 +280,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           for (int c = 0; c < sg.c_chunks; ++c, ++g) {
             if ((g & 1) == par) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (elect_one()) {
+              if (p.dbg_no_tma && g >= kStages) {
+                if (elect_one()) mbar_arrive(&full_bar[stage]);
+              } else if (elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
                 tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
                             h0 + sg.dh, img);
@@ -366,9 +369,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (elect_one()) {
             const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
             const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
-            umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
+            if (!p.dbg_no_mma) {
+              umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
 #pragma unroll
-            for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            }
             // smem slot reusable once these MMAs retire (cluster: tell the peer too -- it multicasts into my stage)
             if (p.cluster) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
             else umma_commit(&empty_bar[stage]);
@@ -914,6 +919,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.relu = d->relu;
   p.shift = d->shift;
   p.colsum = d->colsum;
+  if (const char* e = getenv("URSO_DBG_NO_TMA")) p.dbg_no_tma = atoi(e);
+  if (const char* e = getenv("URSO_DBG_NO_MMA")) p.dbg_no_mma = atoi(e);
   if (const char* e = getenv("URSO_DBG_ROW_SHIFT")) p.dbg_row_shift = atoi(e);
   if (const char* e = getenv("URSO_DBG_BASE_OFFSET")) p.dbg_base_offset = atoi(e);
   int sms = num_sms();

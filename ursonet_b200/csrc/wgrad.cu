@@ -25,6 +25,7 @@ struct WgradParams {
   CUtensorMap q_map;
   WSegDev seg[URSO_MAX_SEGS];
   int n_seg, taps_per_cta, n_seg_groups;
+  int order;       // work-item decode order (see kernel)
   int pair_mode;   // PC <= 64: the two 64-row halves of the MMA M dimension carry two different filter taps
   int PC, QC;
   int p_tiles, q_tiles;
@@ -57,10 +58,18 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   // work item decode: blockIdx.x -> (split, q_tile, p_tile, seg_group); split fastest so that CTAs that run
   // concurrently stream different pixels of the same operand columns.
   int wi = blockIdx.x;
-  const int split = wi % p.split_k;  wi /= p.split_k;
-  const int q_tile = wi % p.q_tiles; wi /= p.q_tiles;
-  const int p_tile = wi % p.p_tiles; wi /= p.p_tiles;
-  const int seg_group = wi;
+  int split, q_tile, p_tile, seg_group;
+  if (p.order == 0) {   // split fastest
+    split = wi % p.split_k;  wi /= p.split_k;
+    q_tile = wi % p.q_tiles; wi /= p.q_tiles;
+    p_tile = wi % p.p_tiles; wi /= p.p_tiles;
+    seg_group = wi;
+  } else {              // output tiles fastest: co-resident CTAs stream the SAME pixels (operand tiles shared through L2)
+    q_tile = wi % p.q_tiles; wi /= p.q_tiles;
+    p_tile = wi % p.p_tiles; wi /= p.p_tiles;
+    seg_group = wi % p.n_seg_groups; wi /= p.n_seg_groups;
+    split = wi;
+  }
   // "units" = taps (normal) or tap pairs (pair mode)
   const int n_units = p.pair_mode ? (p.n_seg + 1) / 2 : p.n_seg;
   const int seg0 = seg_group * p.taps_per_cta;
@@ -319,6 +328,8 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   if (split > p.n_pix_blocks) split = p.n_pix_blocks;
   if (split < 1) split = 1;
   p.split_k = split;
+  p.order = 1;
+  if (const char* e = getenv("URSO_WGRAD_ORDER")) p.order = atoi(e);
   p.g = d->g;
   p.g_seg_stride = d->g_seg_stride;
   p.g_sp = d->g_sp;
