@@ -167,6 +167,8 @@ class Engine:
         if not multi:
             self.n_slices, self.slices = 1, [(0, self.B)]
         self._lane_streams = None
+        self.sparse_bwd = training and int(os.environ.get("URSO_SPARSE_BWD", "1")) != 0
+        self.sparse = set()      # buffers whose gradient lives on the even-even pixels only
         self.H, self.W = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
         self.params = ParamStore(self.graph, device, cfg.WEIGHT_DECAY)
         self.params.init_keras_defaults(seed)
@@ -532,6 +534,16 @@ class Engine:
             if X in producers:
                 self._build_wgrad(producers[X])
 
+    @staticmethod
+    def _bwd_geom(c, h, w, sparse_dst):
+        """Geometry of conv c for its gradient launches; with a sparse (even-even only) output gradient it acts as the
+        same filter at twice the stride on the decimated output grid."""
+        gm = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
+        if not sparse_dst:
+            return gm
+        assert c.stride == 1
+        return P.ConvGeom(gm.kh, gm.kw, 2, gm.pad_t, gm.pad_l, gm.cin, gm.cout, h, w, (gm.oh + 1) // 2, (gm.ow + 1) // 2)
+
     def _bwd_deps(self, lane):
         """Cross-lane dependency of the FIRST backward op of a slice lane: the whole-batch head backward (lane 0).
         Later ops of the lane are ordered behind it by the stream."""
@@ -547,16 +559,23 @@ class Engine:
         S = lib.stream_ptr
         h, w, cin = g.shapes[X]
         assert len(adds) <= 1 and convs, (X, len(adds), len(convs))
-        stride = convs[0].stride
-        assert all(c.stride == stride for c in convs)
-        assert not (adds and stride != 1)
+        # Structural sparsity: a buffer consumed only by 1x1/stride-2 convolutions (the Keras-v1 block puts the stride on
+        # the first 1x1, net.py:138,152) has a gradient that is non-zero on the even-even pixels only, and so has
+        # everything it feeds through 1x1 convolutions.  For such a consumer the gradient launches treat the conv as a
+        # stride-2 conv on the decimated gradient grid: 4x less work for a 1x1 (and X is sparse again), 9 -> 2.25 taps
+        # on average for a 3x3.  The never-written odd phases stay zero from allocation (torch.zeros), so any launch
+        # that reads such a buffer densely (e.g. as the gradient fan-in addend) is still exact.
+        sparse_in = self.sparse_bwd and all(c.dst in self.sparse and c.stride == 1 for c in convs)
+        stride = convs[0].stride * (2 if sparse_in else 1)
+        assert all(c.stride == convs[0].stride for c in convs)
+        assert not (adds and convs[0].stride != 1)
         self.dact[X] = self._new((B, h, w, cin))
         key = colsum_for(X) if need_cs else None
         self.colsum[X] = key
         # pool1 = max of post-ReLU values: masking its gradient by (pool1 > 0) IS the stem's ReLU mask (a window's max
         # is 0 only when all its inputs are 0), so the max-pool backward does not have to read the stem output
         mask_all = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
-        geoms = [P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w) for c in convs]
+        geoms = [self._bwd_geom(c, h, w, sparse_in) for c in convs]
         phases = [P.dgrad_phases(gm) for gm in geoms]
         need_zero = False
         flat_ok = stride == 1 and all(c.k == 1 for c in convs)
@@ -592,12 +611,14 @@ class Engine:
             dX = self.dact[X][b0:b1]
             mask = mask_all[b0:b1] if mask_all is not None else None
             addend = self.dact[adds[0].dst][b0:b1] if adds else None
-            if need_zero:
+            if need_zero and not self.sparse_bwd:
                 self._add(self.ops_bwd, OpRec(lambda dX=dX: dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(), lane=si,
                                               after=self._bwd_deps(si)))
             for pi, segs, bmat in staged:
                 oph, opw = phases[0][pi][0], phases[0][pi][1]
                 a_views = [self.dact[c.dst][b0:b1] for c in convs]
+                if sparse_in:
+                    a_views = [v[:, ::2, ::2, :] for v in a_views]
                 tgt = dX[:, oph::stride, opw::stride, :]
                 m_v = mask[:, oph::stride, opw::stride, :] if mask is not None else None
                 if flat_ok:
@@ -626,24 +647,29 @@ class Engine:
                     self._late_binds.append(bind)
                     return lambda: plan_box["p"].launch()
                 fl = sum(2.0 * nb_ * gm.oh * gm.ow * cv.cout * cv.k * cv.k * cv.cin for gm, cv in zip(geoms, convs)) \
-                    / len(staged)
+                    / len(staged)      # executed work (decimated grid when the consumer gradient is sparse)
                 nbytes = 2.0 * (sum(v.numel() for v in L["a"]) + L["out"].numel() * (2 + (1 if addend is not None else 0))
                                 + bmat.numel())
                 self._add(self.ops_bwd, OpRec(make(), "conv_dgrad", X, fl, nbytes, lane=si,
                                               after=self._bwd_deps(si) + [stage_op]))
+        if self.sparse_bwd and not adds and stride == 2 and [pi for pi, _, _ in staged] == [0] and h % 2 == 0 and w % 2 == 0:
+            self.sparse.add(X)
 
     def _build_wgrad(self, c: ConvSpec):
         g, B = self.graph, self.B
         S = lib.stream_ptr
+        sparse_du = False
         if c.stem:
             segs = [(m, dh, dw) for (m, dh, dw, _ch) in P.stem_segments()]
             pc = 64
+            geom = None
             oh, ow = g.shapes[c.dst][:2]
             n_rows = 4 * 64
             row_map = self._idx(P.stem_grad_row_map(3))
         else:
             h, w, _ = g.shapes[c.src]
-            geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
+            sparse_du = self.sparse_bwd and c.dst in self.sparse and c.stride == 1
+            geom = self._bwd_geom(c, h, w, sparse_du)
             segs = P.wgrad_segments(geom)
             pc = c.cin
             oh, ow = geom.oh, geom.ow
@@ -655,13 +681,15 @@ class Engine:
         skey = "S:" + c.name
         if c.bn:
             self._zero_specs.append((skey, c.cout))
-        swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout
-        flat = (not c.stem) and c.k == 1 and c.stride == 1
+        swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout and not sparse_du
+        flat = (not c.stem) and c.k == 1 and c.stride == 1 and not sparse_du
         wg_ops = []
         for si, (b0, b1) in enumerate(self.slices):
             nb_ = b1 - b0
             du = self.dact[c.dst][b0:b1]
-            p_views = [self.E[b0:b1]] if c.stem else P.input_views(self.act[c.src][b0:b1], c.stride)
+            if sparse_du:
+                du = du[:, ::2, ::2, :]
+            p_views = [self.E[b0:b1]] if c.stem else P.input_views(self.act[c.src][b0:b1], geom.stride if geom else 1)
             box = {}
 
             def bind(box=box, du=du, p_views=p_views, nb_=nb_, b0=b0, b1=b1):
