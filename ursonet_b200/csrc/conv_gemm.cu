@@ -70,6 +70,7 @@ struct ConvGemmParams {
   int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
   int eo_depth;      // per-warp output slabs (TMA stores in flight)
   int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
+  int colacc_bytes;    // per-CTA column-sum accumulator (0 when the launch has no colsum: the space goes to stages)
   PixDev out, addend, mask;
   int out_fp32, relu;
   const float* shift;
@@ -99,7 +100,7 @@ constexpr int kSlabBytes = 32 * 128;                // 32 pixel rows x 64 bf16 c
 constexpr int kMaxEiDepth = 3;                      // per-warp prefetch ring depth (chunks ahead), runtime <= this
 constexpr int kTrStride = 36;                       // legacy colsum transpose scratch (floats per row)
 constexpr int kLegacyScratchBytes = 4 * 32 * kTrStride * 4;
-constexpr int kSmemBudget = 227 * 1024 - 1024;      // minus alignment slack
+constexpr int kSmemBudget = 227 * 1024;             // the dynamic smem base is 1 KB aligned by declaration: no slack
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* aempty_bar = afull_bar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
-  float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + kColsumAccBytes);   // legacy epilogue only
+  float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes);   // legacy epilogue only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -780,6 +781,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     return 2;
   }
   // epilogue flavour and shared-memory plan
+  const int kColAcc = d->colsum != nullptr ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
+  p.colacc_bytes = kColAcc;
   p.has_add = d->addend.ptr != nullptr;
   p.has_mask = d->mask.ptr != nullptr;
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
@@ -796,7 +799,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
     const int ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
     epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
-    if (bn == 256 && kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes < 3 * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
+    if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 3 * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
   } else {
     epi_bytes = kLegacyScratchBytes;
   }
@@ -832,7 +835,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       return rc;
     }
     const int btile = bn * kBlockK * 2;
-    stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes - p.a_ring_bytes) / btile;
+    stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes - p.a_ring_bytes) / btile;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 3) {
       set_error("halo mode: not enough shared memory for the B ring (BLOCK_N=%d)", bn);
@@ -841,8 +844,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     }
   } else {
     const int stage_bytes = kATileBytes + bn * kBlockK * 2;
-    stages = (kSmemBudget - kCtrlBytes - kColsumAccBytes - epi_bytes) / stage_bytes;
-    if (stages > 6) stages = 6;
+    stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) {
       set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
       delete h;
@@ -851,13 +854,13 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     p.a_ring_bytes = stages * kATileBytes;
   }
   p.stages = stages;
-  const int fixed = p.a_ring_bytes + stages * bn * kBlockK * 2 + kCtrlBytes + kColsumAccBytes;
+  const int fixed = p.a_ring_bytes + stages * bn * kBlockK * 2 + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
     p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
-    h->smem_bytes = p.eo_off + 8 * p.eo_depth * kSlabBytes + 1024;
+    h->smem_bytes = p.eo_off + 8 * p.eo_depth * kSlabBytes;
   } else {
-    h->smem_bytes = fixed + kLegacyScratchBytes + 1024;
+    h->smem_bytes = fixed + kLegacyScratchBytes;
   }
   if (h->smem_bytes > 227 * 1024) {
     set_error("internal: shared memory plan %d bytes exceeds 227 KB", h->smem_bytes);

@@ -113,21 +113,37 @@ __global__ void bn_param_finalize_kernel(const float* __restrict__ S, const floa
   }
 }
 
-// g <- (trainable ? g * grad_scale + coef * p : 0) ; sumsq += sum g^2.   chunk = 256 elements.
+// g <- (trainable ? g * grad_scale + coef * p : 0) ; sumsq += sum g^2.   chunk = 256 elements (arena alignment).
+// 16-byte accesses: a 256-thread block covers 4 chunks per iteration, thread t owns elements [4t, 4t+4) of that span
+// (n is a multiple of 256 by construction of the arenas; a ragged tail falls back to scalars).
 __global__ void __launch_bounds__(256) add_reg_sumsq_kernel(float* __restrict__ grad, const float* __restrict__ param,
                                                             const float* __restrict__ chunk_coef,
                                                             const float* __restrict__ chunk_lr, float grad_scale,
                                                             float* __restrict__ sumsq, long long n) {
   __shared__ float sh[8];
   float acc = 0.f;
-  const long long nchunks = (n + 255) / 256;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const long long i = ch * 256 + threadIdx.x;
-    if (i < n) {
-      float g = 0.f;
-      if (chunk_lr[ch] != 0.f) g = grad[i] * grad_scale + chunk_coef[ch] * param[i];
-      grad[i] = g;
-      acc += g * g;
+  const long long nspans = (n + 1023) / 1024;
+  for (long long sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+    const long long i = sp * 1024 + 4 * threadIdx.x;
+    const long long ch = i >> 8;
+    if (i + 4 <= n) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (chunk_lr[ch] != 0.f) {
+        const float4 g0 = *reinterpret_cast<const float4*>(grad + i);
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(param + i));
+        const float c = chunk_coef[ch];
+        g = make_float4(g0.x * grad_scale + c * p0.x, g0.y * grad_scale + c * p0.y, g0.z * grad_scale + c * p0.z,
+                        g0.w * grad_scale + c * p0.w);
+      }
+      *reinterpret_cast<float4*>(grad + i) = g;
+      acc += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+    } else {
+      for (long long k = i; k < n; ++k) {
+        float g = 0.f;
+        if (chunk_lr[k >> 8] != 0.f) g = grad[k] * grad_scale + chunk_coef[k >> 8] * param[k];
+        grad[k] = g;
+        acc += g * g;
+      }
     }
   }
   acc = warp_sum_p(acc);
@@ -156,14 +172,26 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ param
                                                        long long n) {
   const float cf = clip_factor(sumsq, hyper);
   const float lr = hyper[0], mom = hyper[1];
-  const long long nchunks = (n + 255) / 256;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    if (chunk_lr[ch] == 0.f) continue;
-    const long long i = ch * 256 + threadIdx.x;
-    if (i < n) {
-      const float v = mom * vel[i] - lr * (grad[i] * cf);
-      vel[i] = v;
-      param[i] += v;
+  const float lrc = lr * cf;
+  const long long nspans = (n + 1023) / 1024;
+  for (long long sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+    const long long i = sp * 1024 + 4 * threadIdx.x;
+    if (i + 4 <= n) {
+      if (chunk_lr[i >> 8] == 0.f) continue;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(grad + i));
+      float4 v = *reinterpret_cast<const float4*>(vel + i);
+      float4 w = *reinterpret_cast<const float4*>(param + i);
+      v = make_float4(mom * v.x - lrc * g.x, mom * v.y - lrc * g.y, mom * v.z - lrc * g.z, mom * v.w - lrc * g.w);
+      w = make_float4(w.x + v.x, w.y + v.y, w.z + v.z, w.w + v.w);
+      *reinterpret_cast<float4*>(vel + i) = v;
+      *reinterpret_cast<float4*>(param + i) = w;
+    } else {
+      for (long long k = i; k < n; ++k) {
+        if (chunk_lr[k >> 8] == 0.f) continue;
+        const float v = mom * vel[k] - lrc * grad[k];
+        vel[k] = v;
+        param[k] += v;
+      }
     }
   }
 }
@@ -176,19 +204,44 @@ __global__ void __launch_bounds__(256) amsgrad_step_kernel(float* __restrict__ p
                                                            const float* __restrict__ hyper, long long n) {
   const float cf = clip_factor(sumsq, hyper);
   const float lr_t = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
-  const long long nchunks = (n + 255) / 256;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    if (chunk_lr[ch] == 0.f) continue;
-    const long long i = ch * 256 + threadIdx.x;
-    if (i < n) {
-      const float g = grad[i] * cf;
-      const float mi = b1 * m[i] + (1.f - b1) * g;
-      const float vi = b2 * v[i] + (1.f - b2) * g * g;
-      const float vh = fmaxf(vhat[i], vi);
-      m[i] = mi;
-      v[i] = vi;
-      vhat[i] = vh;
-      param[i] -= lr_t * mi / (sqrtf(vh) + eps);
+  const long long nspans = (n + 1023) / 1024;
+  for (long long sp = blockIdx.x; sp < nspans; sp += gridDim.x) {
+    const long long i0 = sp * 1024 + 4 * threadIdx.x;
+    if (i0 >= n || chunk_lr[i0 >> 8] == 0.f) continue;
+    if (i0 + 4 <= n) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grad + i0));
+      float4 m4 = *reinterpret_cast<const float4*>(m + i0);
+      float4 v4 = *reinterpret_cast<const float4*>(v + i0);
+      float4 h4 = *reinterpret_cast<const float4*>(vhat + i0);
+      float4 w4 = *reinterpret_cast<const float4*>(param + i0);
+      float* gm = reinterpret_cast<float*>(&m4);
+      float* gv = reinterpret_cast<float*>(&v4);
+      float* gh = reinterpret_cast<float*>(&h4);
+      float* gw = reinterpret_cast<float*>(&w4);
+      const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g = gg[k] * cf;
+        gm[k] = b1 * gm[k] + (1.f - b1) * g;
+        gv[k] = b2 * gv[k] + (1.f - b2) * g * g;
+        gh[k] = fmaxf(gh[k], gv[k]);
+        gw[k] -= lr_t * gm[k] / (sqrtf(gh[k]) + eps);
+      }
+      *reinterpret_cast<float4*>(m + i0) = m4;
+      *reinterpret_cast<float4*>(v + i0) = v4;
+      *reinterpret_cast<float4*>(vhat + i0) = h4;
+      *reinterpret_cast<float4*>(param + i0) = w4;
+    } else {
+      for (long long i = i0; i < n; ++i) {
+        const float g = grad[i] * cf;
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        const float vh = fmaxf(vhat[i], vi);
+        m[i] = mi;
+        v[i] = vi;
+        vhat[i] = vh;
+        param[i] -= lr_t * mi / (sqrtf(vh) + eps);
+      }
     }
   }
 }
@@ -332,7 +385,7 @@ int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef,
   URSO_REQUIRE(grad && param && chunk_coef && chunk_lr && sumsq_out, "null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   URSO_CUDA_OK(cudaMemsetAsync(sumsq_out, 0, sizeof(float), s));
-  add_reg_sumsq_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, s>>>(grad, param, chunk_coef, chunk_lr,
+  add_reg_sumsq_kernel<<<grid_for_p((n + 1023) / 1024, 1, num_sms() * 8), 256, 0, s>>>(grad, param, chunk_coef, chunk_lr,
                                                                                     grad_scale, sumsq_out, n);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
@@ -341,7 +394,7 @@ int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef,
 int urso_sgd_step(float* param, float* vel, const float* grad, const float* chunk_lr, const float* sumsq,
                   const float* hyper_dev, int64_t n, void* stream) {
   URSO_REQUIRE(param && vel && grad && chunk_lr && sumsq && hyper_dev, "null pointer");
-  sgd_step_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  sgd_step_kernel<<<grid_for_p((n + 1023) / 1024, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, vel, grad, chunk_lr, sumsq, hyper_dev, n);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
@@ -350,7 +403,7 @@ int urso_sgd_step(float* param, float* vel, const float* grad, const float* chun
 int urso_amsgrad_step(float* param, float* m, float* v, float* vhat, const float* grad, const float* chunk_lr,
                       const float* sumsq, const float* hyper_dev, int64_t n, void* stream) {
   URSO_REQUIRE(param && m && v && vhat && grad && chunk_lr && sumsq && hyper_dev, "null pointer");
-  amsgrad_step_kernel<<<grid_for_p((n + 255) / 256, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  amsgrad_step_kernel<<<grid_for_p((n + 1023) / 1024, 1, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, m, v, vhat, grad, chunk_lr, sumsq, hyper_dev, n);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
