@@ -19,8 +19,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+    os.environ.pop("NCCL_DEBUG", None)     # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 TRAIN_GFLOP_PER_IMG = 281.02      # BASELINE.md section 2 (cfg2/cfg5): fwd + dgrad + wgrad, 2 FLOP/MAC
 

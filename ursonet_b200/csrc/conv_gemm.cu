@@ -795,11 +795,28 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     int ksteps_total = 0;
     for (int s2 = 0; s2 < d->n_seg; ++s2) ksteps_total += d->seg[s2].c_chunks;
     const bool heavy = ksteps_total >= 4;
+    // A depth-1 input ring exposes the full TMA latency of every chunk, a depth-2 ring costs mainloop stages.  Launches
+    // with a short K loop (<= 6 K steps: the MMAs of a tile take less time than its epilogue) are epilogue bound and get
+    // the deeper ring; long-K launches keep their stages.  Measured per layer: gpurun_out s15 (profiles/r01_progress.md).
+    const bool epi_bound = ksteps_total <= 6;
+    int min_stages = 3;
     p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
     p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
-    const int ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
+    if (n_in > 0 && epi_bound) {
+      p.ei_depth = 2;
+      min_stages = 2;
+    }
+    int ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
     epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
-    if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 3 * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
+    {   // the narrowest tile this launch may fall back to must still get 2 mainloop stages
+      const int bn_min = bn == 256 ? 128 : bn;
+      if (p.ei_depth == 2 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
+        p.ei_depth = 1;
+        ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
+        epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
+      }
+    }
+    if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
   } else {
     epi_bytes = kLegacyScratchBytes;
   }
