@@ -162,8 +162,11 @@ class Engine:
         self.n_slices = 1 if self.parity else max(1, min(int(n_slices), self.B))
         self.slices = [(self.B * i // self.n_slices, self.B * (i + 1) // self.n_slices) for i in range(self.n_slices)]
         multi = (not self.parity) and int(os.environ.get("URSO_LANES", "1")) != 0
-        self.wgrad_lanes = multi and training and int(os.environ.get("URSO_WLANE", "1")) != 0
-        self.aux_lane = (self.n_slices * (2 if self.wgrad_lanes else 1)) if multi else 0
+        # URSO_WLANE = number of wgrad lanes per slice (0: wgrad stays in the slice's chain).  With 2, consecutive wgrad
+        # launches (independent of each other) alternate lanes, so the atomic-reduction tail of one overlaps the next.
+        self.wgrad_lanes = int(os.environ.get("URSO_WLANE", "1")) if (multi and training) else 0
+        self.aux_lane = (self.n_slices * (1 + self.wgrad_lanes)) if multi else 0
+        self._wgrad_rr = 0
         if not multi:
             self.n_slices, self.slices = 1, [(0, self.B)]
         self._lane_streams = None
@@ -708,11 +711,13 @@ class Engine:
             fl = 2.0 * nb_ * oh * ow * c.cout * c.k * c.k * c.cin
             nb = 2.0 * (sum(v.numel() for v in p_views) + du.numel()) + 4.0 * n_rows * c.cout
             if self.wgrad_lanes:   # own lane: ordered behind the dgrad that produced du (the last op of the slice lane)
-                lane, deps = self.n_slices + si, [self._last.get(si), self._bwd_root]
+                lane = self.n_slices * (1 + self._wgrad_rr % self.wgrad_lanes) + si
+                deps = [self._last.get(si), self._bwd_root]
             else:
                 lane, deps = si, self._bwd_deps(si)
             wg_ops.append(self._add(self.ops_bwd, OpRec(lambda box=box: box["p"].launch(), "conv_wgrad", c.name, fl, nb,
                                                         lane=lane, after=deps)))
+        self._wgrad_rr += 1
         # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form):
         # aux lane, after the wgrad (and with it the d-beta column sums) of EVERY slice
         w, bias, bn = self._conv_weight_ptrs(c)
