@@ -217,17 +217,25 @@ def main():
     t_ms = t_ms.item()
     value = world * args.batch * args.steps / (t_ms / 1e3)
     # ---------------- timed region 2: end to end through the public step API with host buffers
-    losses_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    losses_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_log = []
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(args.steps):
-        eng.img_u8.copy_(h_img, non_blocking=True)
-        eng.gt_loc.copy_(h_loc, non_blocking=True)
-        eng.gt_ori.copy_(h_ori, non_blocking=True)
+    eng.upload_async(h_img, h_loc, h_ori)               # first batch; every later upload overlaps the previous step
+    for i in range(args.steps):
+        eng.swap_in()                                   # uploaded batch -> the buffers the graphs read (waits for the H2D)
+        if i + 1 < args.steps:
+            eng.upload_async(h_img, h_loc, h_ori)       # next step's H2D (59 MB from pinned memory) on the copy stream
         eng.train_step(lr, allreduce, use_graph)
-        losses_host.copy_(eng.losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller reads the losses every step
+        losses_host[i & 1].copy_(eng.losses, non_blocking=True)      # D2H of this step's losses (pinned, async)
+        loss_ev[i & 1].record()
+        if i > 0:                                       # the host reads EVERY step's losses, one step behind the GPU,
+            loss_ev[(i - 1) & 1].synchronize()          # so that the launch latency of step i+1 is not exposed
+            loss_log.append(losses_host[(i - 1) & 1].tolist())
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    loss_log.append(losses_host[(args.steps - 1) & 1].tolist())
     e3.record()
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], device="cuda")
@@ -235,7 +243,8 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * args.batch * args.steps / (t2.item() / 1e3)
     h2d = h_img.numel() + 4 * h_loc.numel() + 4 * h_ori.numel()
-    loss_vals = losses_host.tolist()
+    loss_vals = loss_log[-1]
+    assert len(loss_log) == args.steps
 
     if rank != 0:
         if world > 1:

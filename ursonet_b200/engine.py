@@ -891,7 +891,42 @@ class Engine:
             t = self.opt_t + 1
             eps = 1e-4 if getattr(cfg, "F16", False) else 1e-7
             h = [lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t), 0.9, 0.999, eps, clipnorm, 0, 0, 0]
-        self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+        if h != getattr(self, "_hyper_host", None):      # unchanged hyper-parameters: no copy (SGD with a constant lr)
+            self.hyper.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+            self._hyper_host = h
+
+    # ------------------------------------------------------------------ host-fed steps: pipelined upload
+    _copy_stream = None
+
+    def upload_async(self, h_img, h_loc, h_ori):
+        """Start the host -> device copy of the NEXT batch (pinned host tensors: uint8 [B,H,W,3], fp32 labels) on a
+        dedicated copy stream into device staging buffers.  It overlaps with the step the compute stream is running;
+        `swap_in()` makes the batch current.  (The reference feeds every step through feed_dict, net.py:1152.)"""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._st = [torch.empty_like(self.img_u8), torch.empty_like(self.gt_loc), torch.empty_like(self.gt_ori)]
+            self._ev_uploaded, self._ev_free = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._ev_free)            # the previous swap_in has drained the staging buffers
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._st, (h_img, h_loc, h_ori)):
+                dst.copy_(src, non_blocking=True)
+            self._ev_uploaded.record(cs)
+
+    def wait_upload(self):
+        """Host-side wait until the last upload_async has finished reading its (pinned) source buffers."""
+        if self._copy_stream is not None:
+            self._ev_uploaded.synchronize()
+
+    def swap_in(self):
+        """Device -> device copy of the uploaded batch into the buffers the captured graphs read (compute stream)."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._ev_uploaded)
+        self.img_u8.copy_(self._st[0], non_blocking=True)
+        self.gt_loc.copy_(self._st[1], non_blocking=True)
+        self.gt_ori.copy_(self._st[2], non_blocking=True)
+        self._ev_free.record(main)
 
     def train_step(self, lr, allreduce=None, use_graph=True):
         """One optimisation step on the current input/label buffers: fwd + loss + bwd (graph A), optional

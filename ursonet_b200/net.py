@@ -172,6 +172,27 @@ class UrsoNet:
         e.gt_loc.copy_(torch.from_numpy(np.ascontiguousarray(gt_loc, dtype=np.float32)), non_blocking=True)
         e.gt_ori.copy_(torch.from_numpy(np.ascontiguousarray(gt_ori, dtype=np.float32)), non_blocking=True)
 
+    _pin = None
+
+    def _feed(self, inputs):
+        """Pipelined feed of a uint8 batch: numpy -> pinned host buffers -> asynchronous H2D on the engine's copy stream
+        (overlaps the step that is running); `engine.swap_in()` makes it current.  Returns False (and feeds
+        synchronously) for molded fp32 inputs."""
+        images, _meta, gt_loc, gt_ori = inputs
+        e = self.engine
+        if images.dtype != np.uint8:
+            self._put_batch(inputs)
+            return False
+        e.set_input_kind("u8")
+        if self._pin is None:
+            self._pin = [torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in (e.img_u8, e.gt_loc, e.gt_ori)]
+        e.wait_upload()                      # the previous H2D has finished reading the pinned buffers
+        self._pin[0].copy_(torch.from_numpy(images))
+        self._pin[1].copy_(torch.from_numpy(np.ascontiguousarray(gt_loc, dtype=np.float32)))
+        self._pin[2].copy_(torch.from_numpy(np.ascontiguousarray(gt_ori, dtype=np.float32)))
+        e.upload_async(*self._pin)
+        return True
+
     def _lr_at(self, it, base_lr):
         cfg = self.config
         if not getattr(cfg, "CLR", False):
@@ -206,10 +227,15 @@ class UrsoNet:
         it = self.epoch * cfg.STEPS_PER_EPOCH
         for epoch in range(self.epoch, epochs):
             t0 = time.time()
+            inputs, _ = next(train_gen)
+            piped = self._feed(inputs)
             for step in range(cfg.STEPS_PER_EPOCH):
-                inputs, _ = next(train_gen)
-                self._put_batch(inputs)
+                if piped:
+                    e.swap_in()
                 e.train_step(self._lr_at(it, learning_rate), allreduce, use_graph)
+                if step + 1 < cfg.STEPS_PER_EPOCH:      # next batch: generator work and H2D overlap the running step
+                    inputs, _ = next(train_gen)
+                    piped = self._feed(inputs)
                 loc_l, ori_l = e.losses.tolist()
                 history.loc_loss_acc.append(loc_l)
                 history.ori_loss_acc.append(ori_l)
