@@ -133,6 +133,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// fp32 pair -> packed bf16 with the ReLU folded into the conversion (cvt.rn.relu.bf16x2.f32: one F2FP instead of F2FP + HMNMX2)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
 template <int BLOCK_N>
 struct ChunkIter {
@@ -495,15 +502,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             }
             // pack to bf16 first; ReLU and the ReLU-backward mask are exact on the packed values
             uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             if (p.relu) {
-              const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                __nv_bfloat162 t = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[i]), z2);
-                pk[i] = *reinterpret_cast<uint32_t*>(&t);
-              }
+              for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(v[2 * i], v[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             }
             if (p.has_mask) {
               const uint8_t* ms = in_slab + p.has_add * kSlabBytes;
