@@ -22,10 +22,14 @@ out += [f"## Launch list: {sum(a[0] for a in agg.values())} launches, {tot:.2f} 
         "| kernel | launches | ms | share |", "|---|---:|---:|---:|"]
 for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{k[:80]}` | {n} | {ms:.3f} | {ms / tot:.1%} |")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-if len(rows) > 2:
-    hdr, units, data = rows[0], rows[1], rows[2:]
+data, hdr, units = [], None, None
+for one in rep.split(","):          # several reports may be given, comma separated
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) > 2:
+        hdr, units = rows[0], rows[1]
+        data += rows[2:]
+if data:
     idx = {h: i for i, h in enumerate(hdr)}
     keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
