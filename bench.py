@@ -264,9 +264,17 @@ def main():
     f_fl = agg.get("conv_fwd", {}).get("flops", 0) + agg.get("conv_dgrad", {}).get("flops", 0)
     f_n = agg.get("conv_fwd", {}).get("n", 0) + agg.get("conv_dgrad", {}).get("n", 0)
     achieved = f_fl / (f_ms * 1e-3) / 1e12 if f_ms else None
+    # DRAM bytes per Engine-F launch from the committed ncu pass over the same step (profiles/r01_traffic.json)
+    traffic, traffic_note = None, "no ncu traffic capture for this configuration"
+    tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tj) and args.backbone == "resnet50" and args.width == 960 and args.batch == 32 and not args.regress_ori:
+        t = json.load(open(tj))["engines"]["conv_gemm"]
+        traffic = t["dram_bytes_per_launch"]
+        traffic_note = ("ncu dram__bytes_read+write per conv_gemm launch (avg of %d launches); algorithmic bytes per launch %.4g"
+                        % (t["launches"], t["algorithmic_bytes_per_launch"]))
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (Engine F: conv fprop + dgrad, %d launches/step)" % f_n,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if achieved else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "flops_per_launch_avg": f_fl / f_n if f_n else None, "ms_per_launch_avg": f_ms / f_n if f_n else None,
                 "by_kind": {k: {"ms": round(v["ms"], 4), "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] and v["flops"] else None),
                                 "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] and v["bytes"] else None), "launches": v["n"]}
