@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--ori_resolution", type=int, default=16)
     ap.add_argument("--regress_ori", action="store_true", help="quaternion regression head (BASELINE configs[2])")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one blocking all-reduce after backward (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
     args = ap.parse_args()
@@ -188,7 +189,10 @@ def main():
     eng.img_u8.copy_(h_img)
     eng.gt_loc.copy_(h_loc)
     eng.gt_ori.copy_(h_ori)
-    allreduce = (lambda g: dist.all_reduce(g)) if world > 1 else None
+    allreduce = None
+    ar_async = (lambda g: dist.all_reduce(g, async_op=True)) if world > 1 and not args.no_overlap else None
+    if world > 1 and args.no_overlap:
+        allreduce = lambda g: dist.all_reduce(g)
     use_graph = not args.no_graph
     lr = cfg.LEARNING_RATE
 
@@ -198,7 +202,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        eng.train_step(lr, allreduce, use_graph)
+        eng.train_step(lr, allreduce, use_graph, ar_async)
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     barrier()
@@ -207,7 +211,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.train_step(lr, allreduce, use_graph)
+        eng.train_step(lr, allreduce, use_graph, ar_async)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -228,7 +232,7 @@ def main():
         eng.swap_in()                                   # uploaded batch -> the buffers the graphs read (waits for the H2D)
         if i + 1 < args.steps:
             eng.upload_async(h_img, h_loc, h_ori)       # next step's H2D (59 MB from pinned memory) on the copy stream
-        eng.train_step(lr, allreduce, use_graph)
+        eng.train_step(lr, allreduce, use_graph, ar_async)
         losses_host[i & 1].copy_(eng.losses, non_blocking=True)      # D2H of this step's losses (pinned, async)
         loss_ev[i & 1].record()
         if i > 0:                                       # the host reads EVERY step's losses, one step behind the GPU,

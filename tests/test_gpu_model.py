@@ -255,3 +255,40 @@ def test_set_trainable_freezes_layers():
         layer = k.split("/")[0]
         is_head = layer.startswith(("ori_", "loc_")) or layer == "bottleneck_layer"
         assert changed == is_head or (is_head and k.endswith("bias")), k
+
+
+class _Done:
+    def wait(self):
+        pass
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_split_backward_for_overlapped_allreduce(use_graph):
+    """The overlapped all-reduce schedule replays backward in two graphs (arena tail first).  With an identity
+    'all-reduce' it must give the same step as the single-graph schedule (up to fp32 atomic summation order)."""
+    from ursonet_b200.engine import Engine
+    cfg = make_cfg("resnet50", True)
+    B, lr = 2, 1e-3
+    p64 = O.init_weights(cfg, seed=5, pretrained_like=True)
+    img, gt_loc, gt_ori = make_batch(cfg, B, seed=6)
+    outs = []
+    for split in (False, True):
+        eng = Engine(cfg, B, training=True)
+        load_oracle_weights(eng, p64)
+        eng.img_u8.copy_(img); eng.gt_loc.copy_(gt_loc); eng.gt_ori.copy_(gt_ori)
+        assert eng._bwd_split is not None and 0 < eng._bwd_split[1] < eng.params.n_train
+        seen = []
+        ar = (lambda g: (seen.append(g.numel()), _Done())[1]) if split else None
+        eng.train_step(lr, use_graph=use_graph, allreduce_async=ar)
+        torch.cuda.synchronize()
+        first = eng.params.flat.clone()
+        eng.train_step(lr, use_graph=use_graph, allreduce_async=ar)
+        torch.cuda.synchronize()
+        if split:   # two pieces per step that tile the arena, tail (>= 90 % of it) first
+            assert len(seen) == 4 and seen[0] + seen[1] == eng.params.n_train and seen[0] >= 0.9 * eng.params.n_train
+        outs.append((first, eng.losses.clone()))
+    (p0, l0), (p1, l1) = outs
+    # after ONE step the weights agree to fp32 atomic-order noise; the second step's losses (a chaotic random net
+    # amplifies that noise) only have to agree loosely -- a double-counted accumulation would be off by far more
+    assert (p0 - p1).abs().max().item() <= 2e-6 * p0.abs().max().item() + 1e-7
+    assert torch.allclose(l0, l1, rtol=3e-2, atol=1e-3)

@@ -126,11 +126,12 @@ class ParamStore:
 class OpRec:
     """One entry of a launch list: the callable plus what it is (for profiling / launch accounting), the LANE (CUDA
     stream) it is issued on and the ops of other lanes it must wait for (-> CUDA events / graph edges)."""
-    __slots__ = ("fn", "kind", "name", "flops", "bytes", "launches", "lane", "after", "event", "signal")
+    __slots__ = ("fn", "kind", "name", "flops", "bytes", "launches", "lane", "after", "event", "signal", "segment")
 
     def __init__(self, fn, kind, name, flops=0.0, nbytes=0.0, launches=1, lane=0, after=()):
         self.fn, self.kind, self.name, self.flops, self.bytes, self.launches = fn, kind, name, flops, nbytes, launches
         self.lane, self.after, self.event, self.signal = lane, [a for a in after if a is not None], None, False
+        self.segment = 0     # 1: the part of backward replayed after the first (overlapped) gradient all-reduce
         for a in self.after:
             a.signal = True
 
@@ -501,6 +502,7 @@ class Engine:
         order.insert(1, "pool1")
         self.Bd = {}
         self._bwd_root = None
+        self._bwd_split = None
         for X in reversed(order):
             if X == "bottleneck_layer":
                 key = colsum_for(X)
@@ -536,6 +538,15 @@ class Engine:
                     self._build_dgrad_group(X, convs, adds, colsum_for, need_cs)
             if X in producers:
                 self._build_wgrad(producers[X])
+                # split point for the overlapped gradient all-reduce: once >= 90 % of the parameters (the arena tail:
+                # heads, bottleneck, late stages) have their gradients, the rest of backward hides their all-reduce
+                if self._bwd_split is None:
+                    off = self.params.index[producers[X].name + "/kernel"][1]
+                    if self.params.n_train - off >= 0.9 * self.params.n_train and off > 0:
+                        self._bwd_split = (len(self.ops_bwd), off)
+        if self._bwd_split is not None:
+            for op in self.ops_bwd[self._bwd_split[0]:]:
+                op.segment = 1
 
     @staticmethod
     def _bwd_geom(c, h, w, sparse_dst):
@@ -785,7 +796,7 @@ class Engine:
         for op in ops:
             st = main if op.lane == 0 else streams[op.lane]
             for a in op.after:
-                if a.lane != op.lane:
+                if a.lane != op.lane and a.segment == op.segment:   # an earlier segment ended with a full join
                     st.wait_event(a.event)
             if op.lane == 0:
                 op()
@@ -839,13 +850,25 @@ class Engine:
         self._run(self.ops_bwd)
         self._join()
 
-    def _replay(self, key, fn, use_graph=True):
+    def _phase_train_a(self):      # forward + losses + the first part of backward (gradients of the arena tail)
+        self._fwd_body()
+        self._run(self.ops_loss)
+        self._run(self.ops_bwd[:self._bwd_split[0]])
+        self._join()
+
+    def _phase_train_b(self):      # the rest of backward; runs while the tail's all-reduce is in flight
+        self._fork()
+        self._run(self.ops_bwd[self._bwd_split[0]:])
+        self._join()
+
+    def _replay(self, key, fn, use_graph=True, warm=True):
         if not use_graph:
             fn()
             return
         gr = self._graphs.get(key)
         if gr is None:
-            fn()                                   # eager warm-up (sets function attributes, loads modules)
+            if warm:
+                fn()                               # eager warm-up (sets function attributes, loads modules)
             torch.cuda.synchronize()
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
@@ -928,14 +951,31 @@ class Engine:
         self.gt_ori.copy_(self._st[2], non_blocking=True)
         self._ev_free.record(main)
 
-    def train_step(self, lr, allreduce=None, use_graph=True):
-        """One optimisation step on the current input/label buffers: fwd + loss + bwd (graph A), optional
-        all-reduce of the flat gradient arena, regulariser + clip + update (graph B)."""
+    def train_step(self, lr, allreduce=None, use_graph=True, allreduce_async=None):
+        """One optimisation step on the current input/label buffers: fwd + loss + bwd (graph A), all-reduce of the flat
+        gradient arena, regulariser + clip + update (graph B).  `allreduce(t)` reduces in place on the current stream;
+        `allreduce_async(t)` returns a handle with .wait() (torch.distributed async_op=True) and enables the overlapped
+        schedule: backward is replayed in two graphs and the all-reduce of the arena tail (>= 90 % of the parameters,
+        whose gradients are complete first) runs on NCCL's stream while the rest of backward executes."""
         assert self.training
         self.set_hyper(lr)
-        self._replay("train", self._phase_train, use_graph)
-        if allreduce is not None:
-            allreduce(self.grads)
+        if allreduce_async is not None and self._bwd_split is not None:
+            off = self._bwd_split[1]
+            if use_graph and "train_a" not in self._graphs:
+                self._phase_train()    # eager warm-up of EVERY kernel; part B alone is not idempotent (it accumulates
+                #                        into the arena part A zeroed), so the two graphs are captured without one
+            self._replay("train_a", self._phase_train_a, use_graph, warm=False)
+            w1 = allreduce_async(self.grads[off:])
+            self._replay("train_b", self._phase_train_b, use_graph, warm=False)
+            w2 = allreduce_async(self.grads[:off])
+            w1.wait()
+            w2.wait()
+        else:
+            self._replay("train", self._phase_train, use_graph)
+            if allreduce_async is not None:
+                allreduce_async(self.grads).wait()
+            elif allreduce is not None:
+                allreduce(self.grads)
         self._replay("update", self._phase_update, use_graph)
         self.opt_t += 1
 

@@ -223,7 +223,8 @@ class UrsoNet:
         log("Checkpoint Path: {}".format(self.checkpoint_path))
         self.set_trainable(layers)
         self.compile(learning_rate, cfg.LEARNING_MOMENTUM)
-        allreduce = (lambda g: torch.distributed.all_reduce(g)) if self.world > 1 else None
+        allreduce = None
+        ar_async = (lambda g: torch.distributed.all_reduce(g, async_op=True)) if self.world > 1 else None
         it = self.epoch * cfg.STEPS_PER_EPOCH
         for epoch in range(self.epoch, epochs):
             t0 = time.time()
@@ -232,7 +233,7 @@ class UrsoNet:
             for step in range(cfg.STEPS_PER_EPOCH):
                 if piped:
                     e.swap_in()
-                e.train_step(self._lr_at(it, learning_rate), allreduce, use_graph)
+                e.train_step(self._lr_at(it, learning_rate), allreduce, use_graph, ar_async)
                 if step + 1 < cfg.STEPS_PER_EPOCH:      # next batch: generator work and H2D overlap the running step
                     inputs, _ = next(train_gen)
                     piped = self._feed(inputs)
