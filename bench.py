@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--ori_resolution", type=int, default=16)
     ap.add_argument("--regress_ori", action="store_true", help="quaternion regression head (BASELINE configs[2])")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="one blocking all-reduce after backward (N > 1)")
+    ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
     args = ap.parse_args()
@@ -190,8 +190,10 @@ def main():
     eng.gt_loc.copy_(h_loc)
     eng.gt_ori.copy_(h_ori)
     allreduce = None
-    ar_async = (lambda g: dist.all_reduce(g, async_op=True)) if world > 1 and not args.no_overlap else None
-    if world > 1 and args.no_overlap:
+    # measured on 2 x B200: the overlapped schedule is not faster (4005 vs 4015 img/s) -- the persistent conv CTAs leave
+    # NCCL's kernel no SM to run on until a launch boundary -- so one blocking all-reduce is the default
+    ar_async = (lambda g: dist.all_reduce(g, async_op=True)) if world > 1 and args.overlap else None
+    if world > 1 and not args.overlap:
         allreduce = lambda g: dist.all_reduce(g)
     use_graph = not args.no_graph
     lr = cfg.LEARNING_RATE
