@@ -194,6 +194,35 @@ int urso_encode_ori(const float* quats, const float* hquat, const uint8_t* redun
                     int32_t nbins, float var, void* stream);
 int urso_decode_ori_moments(const float* logits, const float* hquat, float* A, int32_t B, int32_t nbins, void* stream);
 
+/* ---- sim2real augmentation on the device (replaces net.py:390-406 = luma + imgaug pipeline on the host).
+ * One record per image, drawn on the host (ursonet_b200/augment.py):
+ *   apply        0: luma only (the reference augments with p = 0.5, net.py:395)
+ *   order[5]     the drawn order of the operations (iaa.Sequential(random_order=True)): 0 AdditiveGaussianNoise,
+ *                1 GaussianBlur, 2 Add, 3 Multiply, 4 CoarseDropout
+ *   noise_q      round(65536 * sigma / 147.8) (sigma = 0.01 * 255; Irwin-Hall(4) integer noise, see augment.cu)
+ *   blur_w[5]    normalised 5-tap Gaussian weights (cv2.getGaussianKernel(5, sigma)), blur_sigma < 1e-3 skips the blur
+ *   add, mul     Add / Multiply parameters;  drop_thresh = p * 2^32, drop_h x drop_w = low-resolution mask size
+ *   win[4]       (y1, x1, y2, x2) of the un-padded image inside the pad64 frame: only these pixels are augmented and
+ *                the blur reflects at its borders (the reference pads AFTER augmenting)
+ * src, dst: uint8 [B,H,W,3], out of place.  Bit-exact against oracle/sim2real_oracle.py. */
+typedef struct urso_aug_params {
+  int32_t apply;
+  int32_t order[5];
+  int32_t noise_q;
+  uint32_t noise_seed;
+  float blur_sigma;
+  float blur_w[5];
+  int32_t add;
+  float mul;
+  uint32_t drop_thresh;
+  int32_t drop_h, drop_w;
+  uint32_t drop_seed;
+  int32_t win[4];
+} urso_aug_params;
+int urso_sizeof_aug_params(void);
+int urso_sim2real_aug(const uint8_t* src, uint8_t* dst, const urso_aug_params* params_dev, int32_t B, int32_t H,
+                      int32_t W, void* stream);
+
 /* ---- small elementwise helpers */
 int urso_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int urso_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);

@@ -1,0 +1,26 @@
+"""Throughput of the sim2real augmentation kernel on the bench batch (32 x 640 x 960 x 3 uint8), CUDA events, L2-cold
+(working set 118 MB ~ L2 size; a 256 MB buffer is written between iterations).  HBM-bound: 3 B read + 3 B written per pixel."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ursonet_b200 import augment
+B, H, W = 32, 640, 960
+rng = np.random.RandomState(0)
+src = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda")
+dst = torch.empty_like(src)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+res = {}
+for name, p_apply in (("luma_only", 0.0), ("reference_mix_p0.5", 0.5), ("all_augmented", 1.0)):
+    prm = augment.draw_params(rng, np.tile([[20, 0, 620, 960]], (B, 1)), p_apply=p_apply)
+    ts = []
+    for it in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); keep = augment.sim2real_device(src, dst, prm); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts[3:])[len(ts[3:]) // 2]
+    res[name] = {"ms": ms, "GB/s": 2 * src.numel() / ms / 1e6, "images/s": B / ms * 1e3}
+peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
+for v in res.values():
+    v["frac_of_hbm_peak"] = v["GB/s"] / peaks["hbm_gbs"]
+print(json.dumps(res, indent=1))

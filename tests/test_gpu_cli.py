@@ -50,6 +50,24 @@ def test_config1_train_then_resume_then_evaluate(workdir, capsys):
     assert model3.mode == "inference"
 
 
+def test_train_with_device_sim2real(workdir):
+    """--sim2real (BASELINE configs[3] turns it on): the uploaded uint8 frames go through the augmentation kernel when
+    they are swapped in; what the network then sees is grey (3 equal channels) and matches the oracle for the drawn
+    parameters (net.py:390-406)."""
+    from oracle import sim2real_oracle as S
+    model = run_cli(workdir, "train", "--weights", "none", "--batch_size", "2", "--epochs", "1", "--steps_per_epoch", "2",
+                    "--sim2real")
+    assert model.config.SIM2REAL_AUG and model.epoch == 1
+    e = model.engine
+    torch.cuda.synchronize()
+    got = e.img_u8.cpu().numpy()
+    assert np.array_equal(got[..., 0], got[..., 1]) and np.array_equal(got[..., 1], got[..., 2])
+    # the batch now in the network's input buffer is the LAST one swapped in: staging buffer + its parameter records
+    src = e._st[0].cpu().numpy()
+    assert np.array_equal(got, S.augment_batch(src, model._aug))
+    assert np.isfinite(e.losses.cpu().numpy()).all()
+
+
 def test_detect_matches_oracle_and_asserts_batch_size(workdir):
     from ursonet_b200 import data as D, net, pose_estimator as PE
     args = PE.build_parser().parse_args(["evaluate", "--dataset", "synth", "--weights", "none", "--backbone", "resnet18",

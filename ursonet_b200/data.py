@@ -10,7 +10,8 @@ Differences, all deliberate and documented in INTEGRATION.md:
   * the generator can yield RAW uint8 frames (`raw_uint8=True`): mean subtraction then happens on the GPU inside the
     stem staging kernel, which cuts the per-step host->device copy 4x (59 MB instead of 236 MB at 640x960x32);
   * pd.read_csv(header=-1) (urso.py:42) is invalid on pandas >= 1.0: header=None is used;
-  * sim2real / camera-rotation augmentation (net.py:390-438) are not built yet and raise if requested.
+  * sim2real augmentation (net.py:390-406) runs on the device (augment.py / csrc/augment.cu) for uint8 feeds; the
+    camera-rotation augmentations (net.py:409-438) are not built yet and raise if requested.
 """
 import json
 import logging
@@ -212,15 +213,17 @@ def write_synthetic_urso(dataset_dir, n_train=4, n_val=2, n_test=2, width=1280, 
 
 
 # ------------------------------------------------------------------------------------------------ batch generator
-def load_image_gt(dataset, config, image_id):
+def load_image_gt(dataset, config, image_id, device_aug=False):
     """(image uint8 [H,W,3] resized+padded, image_meta, loc, ori) -- net.py:358-456 without the augmentations."""
     if getattr(config, "ROT_AUG", False) or getattr(config, "ROT_IMAGE_AUG", False):
         raise NotImplementedError("camera / in-plane rotation augmentation (net.py:409-438) is not built yet")
     image = dataset.load_image(image_id)
     loc = dataset.load_location(image_id)
     ori = dataset.load_quaternion(image_id) if config.REGRESS_ORI else dataset.load_orientation_encoded(image_id)
-    if getattr(config, "SIM2REAL_AUG", False):
-        # luma written back into the uint8 image (net.py:391-394); the stochastic imgaug pipeline is a 'next' row
+    if getattr(config, "SIM2REAL_AUG", False) and not device_aug:
+        # luma written back into the uint8 image (net.py:391-394).  The stochastic imgaug pipeline (net.py:395-406) only
+        # exists on the device (csrc/augment.cu, applied when the uploaded batch is swapped in): with device_aug the
+        # frame is left untouched here and the kernel does the luma step too
         gray = (0.2126 * image[:, :, 0] + 0.7152 * image[:, :, 1] + 0.0722 * image[:, :, 2]).astype(np.uint8)
         image = np.stack([gray] * 3, -1)
     original_shape = image.shape
@@ -230,7 +233,7 @@ def load_image_gt(dataset, config, image_id):
     return image, meta, loc, ori
 
 
-def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False):
+def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False, device_aug=False):
     """Infinite generator of ([images, image_meta, gt_locs, gt_oris], []) like net.data_generator (net.py:458-559).
     raw_uint8=True yields un-molded uint8 images (the engine subtracts MEAN_PIXEL on the GPU)."""
     b, image_index, error_count = 0, -1, 0
@@ -242,7 +245,7 @@ def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False)
             if shuffle and image_index == 0:
                 np.random.shuffle(image_ids)
             image_id = image_ids[image_index]
-            image, meta, loc, ori = load_image_gt(dataset, config, image_id)
+            image, meta, loc, ori = load_image_gt(dataset, config, image_id, device_aug=device_aug and raw_uint8)
             if b == 0:
                 metas = np.zeros((batch_size,) + meta.shape, dtype=meta.dtype)
                 images = np.zeros((batch_size,) + image.shape, dtype=np.uint8 if raw_uint8 else np.float32)

@@ -942,11 +942,17 @@ class Engine:
         if self._copy_stream is not None:
             self._ev_uploaded.synchronize()
 
-    def swap_in(self):
-        """Device -> device copy of the uploaded batch into the buffers the captured graphs read (compute stream)."""
+    def swap_in(self, aug_params=None):
+        """Device -> device copy of the uploaded batch into the buffers the captured graphs read (compute stream).
+        With `aug_params` (ursonet_b200.augment.draw_params records, one per image) the image copy IS the sim2real
+        augmentation kernel (net.py:390-406 on the device: staging buffer -> network input, out of place)."""
         main = torch.cuda.current_stream()
         main.wait_event(self._ev_uploaded)
-        self.img_u8.copy_(self._st[0], non_blocking=True)
+        if aug_params is not None:
+            from . import augment
+            self._aug_keep = augment.sim2real_device(self._st[0], self.img_u8, aug_params)
+        else:
+            self.img_u8.copy_(self._st[0], non_blocking=True)
         self.gt_loc.copy_(self._st[1], non_blocking=True)
         self.gt_ori.copy_(self._st[2], non_blocking=True)
         self._ev_free.record(main)

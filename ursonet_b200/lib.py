@@ -77,6 +77,8 @@ SIGNATURES = {
     "urso_maxpool_fwd_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_encode_ori": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
     "urso_decode_ori_moments": [_vp, _vp, _vp, _i32, _i32, _vp],
+    "urso_sizeof_aug_params": [],
+    "urso_sim2real_aug": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "urso_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "urso_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "urso_pad_cast_rows": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],

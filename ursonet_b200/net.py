@@ -173,6 +173,8 @@ class UrsoNet:
         e.gt_ori.copy_(torch.from_numpy(np.ascontiguousarray(gt_ori, dtype=np.float32)), non_blocking=True)
 
     _pin = None
+    _aug = None
+    _aug_rng = None
 
     def _feed(self, inputs):
         """Pipelined feed of a uint8 batch: numpy -> pinned host buffers -> asynchronous H2D on the engine's copy stream
@@ -191,6 +193,14 @@ class UrsoNet:
         self._pin[1].copy_(torch.from_numpy(np.ascontiguousarray(gt_loc, dtype=np.float32)))
         self._pin[2].copy_(torch.from_numpy(np.ascontiguousarray(gt_ori, dtype=np.float32)))
         e.upload_async(*self._pin)
+        # sim2real augmentation runs on the device when the batch is swapped in: draw this batch's parameters now
+        self._aug = None
+        if getattr(self.config, "SIM2REAL_AUG", False):
+            from . import augment
+            if self._aug_rng is None:
+                self._aug_rng = np.random.RandomState(getattr(self.config, "AUG_SEED", None))
+            wins = np.asarray(_meta)[:, 7:11].astype(np.int32)      # image_meta: window (y1, x1, y2, x2), net.py:1278-1301
+            self._aug = augment.draw_params(self._aug_rng, wins)
         return True
 
     def _lr_at(self, it, base_lr):
@@ -216,8 +226,9 @@ class UrsoNet:
         layers = layer_regex.get(layers, layers)
         cfg, e = self.config, self.engine
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
-        train_gen = D.data_generator(train_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8)
-        val_gen = D.data_generator(val_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8)
+        dev_aug = bool(raw_uint8 and getattr(cfg, "SIM2REAL_AUG", False))
+        train_gen = D.data_generator(train_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8, device_aug=dev_aug)
+        val_gen = D.data_generator(val_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8, device_aug=dev_aug)
         history = BatchLogger()
         log("\nStarting at epoch {}. LR={}\n".format(self.epoch, learning_rate))
         log("Checkpoint Path: {}".format(self.checkpoint_path))
@@ -232,7 +243,7 @@ class UrsoNet:
             piped = self._feed(inputs)
             for step in range(cfg.STEPS_PER_EPOCH):
                 if piped:
-                    e.swap_in()
+                    e.swap_in(self._aug)
                 e.train_step(self._lr_at(it, learning_rate), allreduce, use_graph, ar_async)
                 if step + 1 < cfg.STEPS_PER_EPOCH:      # next batch: generator work and H2D overlap the running step
                     inputs, _ = next(train_gen)
@@ -244,7 +255,8 @@ class UrsoNet:
             val = []
             for _ in range(min(cfg.VALIDATION_STEPS, max(1, len(val_dataset.image_ids) // e.B)) if len(val_dataset.image_ids) else 0):
                 inputs, _ = next(val_gen)
-                self._put_batch(inputs)
+                if self._feed(inputs):       # same feed as training: the reference's val generator augments too
+                    e.swap_in(self._aug)
                 val.append(e.eval_losses())
             if rank == 0:
                 n = cfg.STEPS_PER_EPOCH
