@@ -56,13 +56,22 @@ def check_layout():
         raise lib.UrsoError("AUG_DTYPE does not match struct urso_aug_params (rebuild the library)")
 
 
+def params_to_device(params, device):
+    """AUG_DTYPE records -> uint8 CUDA tensor (pinned staging, asynchronous copy on the current stream)."""
+    import torch
+    host = torch.from_numpy(np.frombuffer(params.tobytes(), dtype=np.uint8).copy()).pin_memory()
+    return host.to(device, non_blocking=True)
+
+
 def sim2real_device(src_u8, dst_u8, params):
-    """src_u8, dst_u8: uint8 CUDA tensors [B,H,W,3] (distinct); params: AUG_DTYPE records [B] (host).  Asynchronous on the
-    current stream; returns the device copy of the parameter table (keep it alive until the kernel has run)."""
+    """src_u8, dst_u8: uint8 CUDA tensors [B,H,W,3] (distinct); params: AUG_DTYPE records [B] (host) or their device copy
+    from params_to_device.  Asynchronous on the current stream; returns the device parameter table (keep it alive until
+    the kernel has run)."""
     import torch
     check_layout()
     B, H, W, _ = src_u8.shape
-    assert src_u8.dtype == torch.uint8 and dst_u8.shape == src_u8.shape and len(params) == B
-    p_dev = torch.from_numpy(np.frombuffer(params.tobytes(), dtype=np.uint8).copy()).to(src_u8.device, non_blocking=True)
+    assert src_u8.dtype == torch.uint8 and dst_u8.shape == src_u8.shape
+    p_dev = params if isinstance(params, torch.Tensor) else params_to_device(params, src_u8.device)
+    assert p_dev.numel() == B * AUG_DTYPE.itemsize
     lib.call("urso_sim2real_aug", src_u8.data_ptr(), dst_u8.data_ptr(), p_dev.data_ptr(), B, H, W, lib.stream_ptr())
     return p_dev

@@ -38,6 +38,18 @@ __device__ __forceinline__ int reflect101(int i, int lo, int hi) {   // cv2.BORD
   return lo + i;
 }
 
+// trunc(0.2126 R + 0.7152 G + 0.0722 B) as numpy evaluates it in float64 (net.py:391).  The exact value is n / 10000 with
+// n = 2126 R + 7152 G + 722 B; float64 rounding (a few 1e-14) can only move the truncation when n is a multiple of 10000,
+// so everything else is integer arithmetic and only those rare triples take the (slow on this part) FP64 path.
+__device__ __forceinline__ float luma_u8(uint32_t r, uint32_t g, uint32_t b) {
+  const uint32_t n = 2126u * r + 7152u * g + 722u * b;
+  const uint32_t q = n / 10000u;
+  if (n - q * 10000u != 0u) return (float)q;
+  const double v = __dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)r), __dmul_rn(0.7152, (double)g)),
+                             __dmul_rn(0.0722, (double)b));
+  return (float)(int)v;
+}
+
 // pointwise operations (everything except the blur) on one grey value at absolute pixel (y, x)
 __device__ __forceinline__ float apply_pointwise(int op, float v, const urso_aug_params& a, int y, int x, int W) {
   if (op == 0) {          // additive noise: Irwin-Hall(4) integer approximation of N(0, sigma), exact in integers
@@ -59,12 +71,18 @@ __device__ __forceinline__ float apply_pointwise(int op, float v, const urso_aug
 }
 
 __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                       const urso_aug_params* __restrict__ params, int H, int W) {
+                                                       const urso_aug_params* __restrict__ params, int H, int W,
+                                                       int n_tiles) {
   __shared__ float s0[kSH][kSW + 1];
   __shared__ float s1[kSH][kSW + 1];
-  const int b = blockIdx.z;
-  const urso_aug_params a = params[b];
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  // persistent CTAs (grid = a multiple of the SM count) walk the (image, tile row, tile column) space
+  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int b = tile / tiles_per_img;
+  const int tr = tile - b * tiles_per_img;
+  const urso_aug_params a = params[b];   // (staging the record in shared memory measured slower: 76 registers)
+  const int x0 = (tr % tiles_x) * kTileW, y0 = (tr / tiles_x) * kTileH;
   const uint8_t* img = src + (size_t)b * H * W * 3;
   uint8_t* out = dst + (size_t)b * H * W * 3;
   const int wy0 = a.win[0], wx0 = a.win[1], wy1 = a.win[2], wx1 = a.win[3];
@@ -81,12 +99,36 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
   // window: the reference pads AFTER augmenting, so the blur never sees padding).
   auto luma_at = [&](int y, int x) -> float {
     const uint8_t* p = img + ((size_t)y * W + x) * 3;
-    // float64 expression of net.py:391, truncated by the uint8 store (explicitly un-fused: numpy evaluates it with
-    // separately rounded multiplies and adds)
-    const double g = __dadd_rn(__dadd_rn(__dmul_rn(0.2126, (double)p[0]), __dmul_rn(0.7152, (double)p[1])),
-                               __dmul_rn(0.0722, (double)p[2]));
-    return (float)(int)g;
+    return luma_u8(p[0], p[1], p[2]);
   };
+  // ---- fast path (no blur: luma-only images, or the drawn sigma is below the cutoff): 4 pixels = 12 bytes = three
+  // aligned 32-bit words per thread, no shared memory
+  if (!need_halo && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+    const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < H && x < W) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(img + ((size_t)y * W + x) * 3);
+      const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+      const uint32_t px[4][3] = {{w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u},
+                                 {w0 >> 24, w1 & 255u, (w1 >> 8) & 255u},
+                                 {(w1 >> 16) & 255u, w1 >> 24, w2 & 255u},
+                                 {(w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24}};
+      uint32_t g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = luma_u8(px[j][0], px[j][1], px[j][2]);
+        if (a.apply && y >= wy0 && y < wy1 && x + j >= wx0 && x + j < wx1) {
+          for (int k = 0; k < 5; ++k) v = apply_pointwise(a.order[k], v, a, y, x + j, W);
+        }
+        g[j] = (uint32_t)v;
+      }
+      uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)y * W + x) * 3);
+      o[0] = g[0] * 0x010101u | (g[1] << 24);
+      o[1] = g[1] * 0x0101u | (g[2] * 0x0101u << 16);
+      o[2] = g[2] | (g[3] * 0x010101u << 8);
+    }
+    continue;
+  }
   if (need_halo) {
     for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
       const int sy = i / kSW, sx = i % kSW;
@@ -139,6 +181,8 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
     uint8_t* p = out + ((size_t)y * W + x) * 3;
     p[0] = g; p[1] = g; p[2] = g;
   }
+  __syncthreads();   // the shared tiles are reused by the next iteration
+  }
 }
 
 }  // namespace urso
@@ -153,8 +197,12 @@ int urso_sim2real_aug(const uint8_t* src, uint8_t* dst, const urso_aug_params* p
   URSO_REQUIRE(src && dst && params_dev, "null pointer");
   URSO_REQUIRE(src != dst, "sim2real_aug is out of place (the blur reads neighbours)");
   URSO_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "bad shape");
-  dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B);
-  sim2real_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, params_dev, H, W);
+  const long long n_tiles = (long long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * B;
+  URSO_REQUIRE(n_tiles < 0x7fffffffLL, "too many tiles");
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  const int grid = (int)(n_tiles < (long long)sms * 8 ? n_tiles : (long long)sms * 8);
+  sim2real_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, params_dev, H, W, (int)n_tiles);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
