@@ -377,28 +377,34 @@ __global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restric
 
 // dx[b, k] = sum_n dy[b,n] w[k,n].  Block = 8 warps = 8 k rows; dy is staged through shared memory in [32 b][128 n]
 // tiles shared by the 8 warps (8x fewer L2 reads than one warp per row reading dy on its own).
+// blockIdx.y splits the n range (n_per_split columns each, a multiple of 128) so that small-K layers still fill the chip
+// and no block walks more than a few serialised chunks; with more than one split the partial sums are added atomically
+// into a dx the host zeroed.
 __global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                          float* __restrict__ dx, int B, int K, int N) {
+                                                          float* __restrict__ dx, int B, int K, int N, int n_per_split) {
   __shared__ float dys[32][128 + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + warp;
   const float* wr = w + (long long)(k < K ? k : 0) * N;
+  const int n_begin = blockIdx.y * n_per_split;
+  const int n_end = min(N, n_begin + n_per_split);
+  const bool atomic = gridDim.y > 1;
   for (int b0 = 0; b0 < B; b0 += 32) {
     float acc[32];
 #pragma unroll
     for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-    for (int n0 = 0; n0 < N; n0 += 128) {
+    for (int n0 = n_begin; n0 < n_end; n0 += 128) {
       __syncthreads();
       for (int i = threadIdx.x; i < 32 * 128; i += 256) {
         const int bb = i >> 7, nn = i & 127;
-        dys[bb][nn] = (b0 + bb < B && n0 + nn < N) ? dy[(long long)(b0 + bb) * N + n0 + nn] : 0.f;
+        dys[bb][nn] = (b0 + bb < B && n0 + nn < n_end) ? dy[(long long)(b0 + bb) * N + n0 + nn] : 0.f;
       }
       __syncthreads();
       if (k < K) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int nn = t * 32 + lane;
-          const float wv = (n0 + nn < N) ? __ldg(wr + n0 + nn) : 0.f;
+          const float wv = (n0 + nn < n_end) ? __ldg(wr + n0 + nn) : 0.f;
 #pragma unroll
           for (int b = 0; b < 32; ++b) acc[b] += wv * dys[b][nn];
         }
@@ -408,7 +414,10 @@ __global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restric
 #pragma unroll
       for (int b = 0; b < 32; ++b) {
         const float sres = warp_sum(acc[b]);
-        if (lane == 0 && b0 + b < B) dx[(long long)(b0 + b) * K + k] = sres;
+        if (lane == 0 && b0 + b < B) {
+          if (atomic) atomicAdd(&dx[(long long)(b0 + b) * K + k], sres);
+          else dx[(long long)(b0 + b) * K + k] = sres;
+        }
       }
     }
   }
@@ -589,7 +598,18 @@ int urso_dense_bwd(const float* x, const float* w, const float* y, float* dy, fl
     dim3 grid((N + 127) / 128, (K + 7) / 8);
     dense_wgrad_kernel<<<grid, 128, 0, s>>>(x, dy, dw, B, K, N);
   }
-  if (dx != nullptr) dense_dgrad_kernel<<<(K + 7) / 8, 256, 0, s>>>(dy, w, dx, B, K, N);
+  if (dx != nullptr) {
+    const int kblocks = (K + 7) / 8, chunks = (N + 127) / 128;
+    int sms = num_sms();
+    if (sms <= 0) sms = 148;
+    int nsplit = (4 * sms + kblocks - 1) / kblocks;          // aim for >= 4 blocks per SM
+    if (nsplit > chunks) nsplit = chunks;
+    if (nsplit < 1) nsplit = 1;
+    const int n_per_split = ((chunks + nsplit - 1) / nsplit) * 128;
+    nsplit = (N + n_per_split - 1) / n_per_split;
+    if (nsplit > 1) URSO_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * K, s));
+    dense_dgrad_kernel<<<dim3(kblocks, nsplit), 256, 0, s>>>(dy, w, dx, B, K, N, n_per_split);
+  }
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
