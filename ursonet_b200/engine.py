@@ -465,13 +465,22 @@ class Engine:
             gb = self.params.view(d.name + "/bias", self.grads)
             w = self.params.view(d.name + "/kernel")
 
-            def run(d=d, w=w, gw=gw, gb=gb, branch=branch):
+            def run(d=d, w=w, gb=gb, branch=branch):
+                # critical path (lane 0): ReLU mask + bias gradient + input gradient
                 x = self.act["bottleneck_layer"] if d.src == "bottleneck_layer" else self.head[d.src]
                 dx = self.dfeat[branch] if d.src == "bottleneck_layer" else self.dhead[d.src]
                 lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), self.head[d.name].data_ptr(),
-                         self.dhead[d.name].data_ptr(), dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), B, d.cin, d.cout,
+                         self.dhead[d.name].data_ptr(), dx.data_ptr(), None, gb.data_ptr(), B, d.cin, d.cout,
                          d.act, S())
-            self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 4.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 3))
+
+            def run_w(d=d, w=w, gw=gw):
+                # weight gradient: nothing downstream waits for it -> aux lane, behind the (already masked) dy
+                x = self.act["bottleneck_layer"] if d.src == "bottleneck_layer" else self.head[d.src]
+                lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), None, self.dhead[d.name].data_ptr(), None,
+                         gw.data_ptr(), None, B, d.cin, d.cout, 0, S())
+            op_d = self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
+            self._add(self.ops_bwd, OpRec(run_w, "dense_wgrad", d.name, 2.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 2,
+                                          lane=self.aux_lane, after=[op_d]))
         if cfg.NR_DENSE_LAYERS == 0:
             raise NotImplementedError("NR_DENSE_LAYERS=0 backward")   # CLI fixes it to 1 (pose_estimator.py:820)
 
