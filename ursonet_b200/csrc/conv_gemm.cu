@@ -25,6 +25,12 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Bottleneck-isolation knobs (URSO_DBG_NO_TMA / URSO_DBG_NO_MMA, scripts/bench_isolate.py) are compiled in only with
+// `make DEBUG_KNOBS=1`: they put a branch into the producer and MMA-issue loops.
+#ifndef URSO_DEBUG_KNOBS
+#define URSO_DEBUG_KNOBS 0
+#endif
+
 namespace urso {
 
 struct SegDev {
@@ -288,9 +294,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           for (int c = 0; c < sg.c_chunks; ++c, ++g) {
             if ((g & 1) == par) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
+#if URSO_DEBUG_KNOBS
               if (p.dbg_no_tma && g >= kStages) {
                 if (elect_one()) mbar_arrive(&full_bar[stage]);
-              } else if (elect_one()) {
+              } else
+#endif
+              if (elect_one()) {
                 mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
                 tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
                             h0 + sg.dh, img);
@@ -377,7 +386,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (elect_one()) {
             const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
             const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
-            if (!p.dbg_no_mma) {
+#if URSO_DEBUG_KNOBS
+            if (!p.dbg_no_mma)
+#endif
+            {
               umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
 #pragma unroll
               for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
