@@ -10,9 +10,7 @@
 // (seed, pixel / cell index), so the numpy restatement (oracle/sim2real_oracle.py) reproduces the kernel BIT-EXACTLY.
 // The image is grey after the luma step, so one channel is processed and written three times.
 //
-// One CTA = one 64 x 16 pixel tile of one image; the tile plus a 2-pixel halo is staged in shared memory so that the blur
-// (wherever it falls in the drawn order) sees neighbours that already went through the operations before it.
-// HBM-bound: reads 3 B + writes 3 B per pixel.
+// One CTA = one strip of 16 rows of one image (see the kernel).  HBM-bound: reads 3 B + writes 3 B per pixel.
 #include "common.cuh"
 
 namespace urso {
@@ -63,73 +61,107 @@ __device__ __forceinline__ float apply_pointwise(int op, float v, const urso_aug
     return round_clip_u8(__fmul_rn(v, a.mul));
   } else if (op == 4) {   // coarse dropout: one Bernoulli(p) draw per low-resolution cell, nearest upsampling
     const int wy0 = a.win[0], wx0 = a.win[1], wh = a.win[2] - a.win[0], ww = a.win[3] - a.win[1];
-    const int cy = (int)(((long long)(y - wy0) * a.drop_h) / wh), cx = (int)(((long long)(x - wx0) * a.drop_w) / ww);
+    // 32-bit arithmetic is exact here: coordinates < 2^16, grid sizes < 2^15 (a 64-bit division costs ~100 instructions)
+    const int cy = (int)(((uint32_t)(y - wy0) * (uint32_t)a.drop_h) / (uint32_t)wh);
+    const int cx = (int)(((uint32_t)(x - wx0) * (uint32_t)a.drop_w) / (uint32_t)ww);
     const uint32_t h = hash_u32(a.drop_seed, (uint32_t)(cy * a.drop_w + cx));
     return h < a.drop_thresh ? 0.f : v;
   }
   return v;
 }
 
+// Grid = (strips of 16 rows, images).  The image's parameter record is staged in shared memory once per CTA.
+//   * images without blur (not selected, or sigma below imgaug's cutoff): every thread owns one 4-pixel group (12 bytes =
+//     three aligned 32-bit words) per row and walks the 16 rows of the strip, four rows of loads in flight -- no shared
+//     tiles, no integer divisions;
+//   * blurred images: the strip is processed as 64-pixel-wide tiles with a 2-pixel halo staged in shared memory, so the
+//     5x5 separable Gaussian sees neighbours that already went through the augmenters drawn before it.
 __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                       const urso_aug_params* __restrict__ params, int H, int W,
-                                                       int n_tiles) {
+                                                       const urso_aug_params* __restrict__ params, int H, int W) {
   __shared__ float s0[kSH][kSW + 1];
   __shared__ float s1[kSH][kSW + 1];
-  // persistent CTAs (grid = a multiple of the SM count) walk the (image, tile row, tile column) space
-  const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-  const int tiles_per_img = tiles_x * tiles_y;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-  const int b = tile / tiles_per_img;
-  const int tr = tile - b * tiles_per_img;
-  const urso_aug_params a = params[b];   // (staging the record in shared memory measured slower: 76 registers)
-  const int x0 = (tr % tiles_x) * kTileW, y0 = (tr / tiles_x) * kTileH;
+  __shared__ urso_aug_params s_a;
+  const int b = blockIdx.y;
+  if (threadIdx.x < sizeof(urso_aug_params) / 4)
+    reinterpret_cast<uint32_t*>(&s_a)[threadIdx.x] = reinterpret_cast<const uint32_t*>(params + b)[threadIdx.x];
+  __syncthreads();
+  const urso_aug_params& a = s_a;
+  // blockIdx.x = strip * tiles_x + tile column: a blurred image uses every CTA (one 64-wide tile each, independent CTAs
+  // hide the staging latency best); an image without blur is done by the tile-column-0 CTA of each strip, the rest exit
+  const int tiles_x = (W + kTileW - 1) / kTileW;
+  const int strip = blockIdx.x / tiles_x, tcol = blockIdx.x - strip * tiles_x;
+  const int y0 = strip * kTileH;
   const uint8_t* img = src + (size_t)b * H * W * 3;
   uint8_t* out = dst + (size_t)b * H * W * 3;
   const int wy0 = a.win[0], wx0 = a.win[1], wy1 = a.win[2], wx1 = a.win[3];
+  const int apply = a.apply;
   // position of the blur in the drawn order (5 = none: sigma below imgaug's 1e-3 cutoff, or image not augmented)
   int blur_at = 5;
-  if (a.apply) {
+  if (apply) {
 #pragma unroll
     for (int k = 0; k < 5; ++k)
       if (a.order[k] == 1 && a.blur_sigma >= 1e-3f) blur_at = k;
   }
-  const bool need_halo = blur_at < 5;
-  // ---- stage 1 (only when blurring): the blur's input -- luma + the operations before the blur -- for the tile and its
-  // halo.  Positions outside the image window take the value of the pixel they reflect to (BORDER_REFLECT_101 on the
-  // window: the reference pads AFTER augmenting, so the blur never sees padding).
   auto luma_at = [&](int y, int x) -> float {
     const uint8_t* p = img + ((size_t)y * W + x) * 3;
     return luma_u8(p[0], p[1], p[2]);
   };
-  // ---- fast path (no blur: luma-only images, or the drawn sigma is below the cutoff): 4 pixels = 12 bytes = three
-  // aligned 32-bit words per thread, no shared memory
-  if (!need_halo && (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
-    const int ty = threadIdx.x >> 4, tx = (threadIdx.x & 15) * 4;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y < H && x < W) {
-      const uint32_t* p = reinterpret_cast<const uint32_t*>(img + ((size_t)y * W + x) * 3);
-      const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-      const uint32_t px[4][3] = {{w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u},
-                                 {w0 >> 24, w1 & 255u, (w1 >> 8) & 255u},
-                                 {(w1 >> 16) & 255u, w1 >> 24, w2 & 255u},
-                                 {(w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24}};
-      uint32_t g[4];
+
+  if (blur_at == 5) {
+    // ------------------------------------------------------------------ no blur: pointwise only
+    if (tcol != 0) return;
+    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+      const int groups = W >> 2;
+      for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int x = g * 4;
+#pragma unroll 4
+        for (int r = 0; r < kTileH; ++r) {
+          const int y = y0 + r;
+          if (y >= H) continue;
+          const uint32_t* p = reinterpret_cast<const uint32_t*>(img + ((size_t)y * W + x) * 3);
+          const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+          float v[4];
+          v[0] = luma_u8(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+          v[1] = luma_u8(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+          v[2] = luma_u8((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+          v[3] = luma_u8((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+          if (apply && y >= wy0 && y < wy1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = luma_u8(px[j][0], px[j][1], px[j][2]);
-        if (a.apply && y >= wy0 && y < wy1 && x + j >= wx0 && x + j < wx1) {
-          for (int k = 0; k < 5; ++k) v = apply_pointwise(a.order[k], v, a, y, x + j, W);
+            for (int j = 0; j < 4; ++j) {
+              if (x + j >= wx0 && x + j < wx1) {
+                for (int k = 0; k < 5; ++k) v[j] = apply_pointwise(a.order[k], v[j], a, y, x + j, W);
+              }
+            }
+          }
+          const uint32_t g0 = (uint32_t)v[0], g1 = (uint32_t)v[1], g2 = (uint32_t)v[2], g3 = (uint32_t)v[3];
+          uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)y * W + x) * 3);
+          o[0] = g0 * 0x010101u | (g1 << 24);
+          o[1] = g1 * 0x0101u | (g2 * 0x0101u << 16);
+          o[2] = g2 | (g3 * 0x010101u << 8);
         }
-        g[j] = (uint32_t)v;
       }
-      uint32_t* o = reinterpret_cast<uint32_t*>(out + ((size_t)y * W + x) * 3);
-      o[0] = g[0] * 0x010101u | (g[1] << 24);
-      o[1] = g[1] * 0x0101u | (g[2] * 0x0101u << 16);
-      o[2] = g[2] | (g[3] * 0x010101u << 8);
+    } else {   // odd widths / unaligned bases: one pixel at a time
+      for (int i = threadIdx.x; i < kTileH * W; i += blockDim.x) {
+        const int y = y0 + i / W, x = i % W;
+        if (y >= H) break;
+        float v = luma_at(y, x);
+        if (apply && y >= wy0 && y < wy1 && x >= wx0 && x < wx1) {
+          for (int k = 0; k < 5; ++k) v = apply_pointwise(a.order[k], v, a, y, x, W);
+        }
+        const uint8_t g = (uint8_t)v;
+        uint8_t* p = out + ((size_t)y * W + x) * 3;
+        p[0] = g; p[1] = g; p[2] = g;
+      }
     }
-    continue;
+    return;
   }
-  if (need_halo) {
+
+  // -------------------------------------------------------------------- blurred image: this CTA's 64-wide tile
+  {
+    const int x0 = tcol * kTileW;
+    // stage 1: the blur's input -- luma + the operations before the blur -- for the tile and its halo.  Positions outside
+    // the image window take the value of the pixel they reflect to (BORDER_REFLECT_101 on the window: the reference pads
+    // AFTER augmenting, so the blur never sees padding).
     for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
       const int sy = i / kSW, sx = i % kSW;
       const int y = reflect101(y0 + sy - kHalo, wy0, wy1), x = reflect101(x0 + sx - kHalo, wx0, wx1);
@@ -137,10 +169,8 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
       for (int k = 0; k < blur_at; ++k) v = apply_pointwise(a.order[k], v, a, y, x, W);
       s0[sy][sx] = v;
     }
-  }
-  __syncthreads();
-  if (need_halo) {
-    // ---- 5-tap separable Gaussian in float32 with un-fused multiply-adds in a fixed order (matches numpy float32)
+    __syncthreads();
+    // 5-tap separable Gaussian in float32 with un-fused multiply-adds in a fixed order (matches numpy float32)
     for (int i = threadIdx.x; i < kSH * kTileW; i += blockDim.x) {
       const int sy = i / kTileW, sx = i % kTileW + kHalo;
       float acc = __fmul_rn(s0[sy][sx - 2], a.blur_w[0]);
@@ -151,37 +181,28 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
       s1[sy][sx] = acc;
     }
     __syncthreads();
-  }
-  // ---- stage 2: vertical pass + the operations after the blur (or all of them when there is no blur); write 3 channels
-  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
-    const int ty = i / kTileW, tx = i % kTileW;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= H || x >= W) continue;
-    const int sy = ty + kHalo, sx = tx + kHalo;
-    const bool inside = y >= wy0 && y < wy1 && x >= wx0 && x < wx1;
-    float v;
-    if (a.apply && inside) {
-      int k0 = 0;
-      if (need_halo) {
+    // stage 2: vertical pass + the operations after the blur; write the three channels
+    for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
+      const int ty = i / kTileW, tx = i % kTileW;
+      const int y = y0 + ty, x = x0 + tx;
+      if (y >= H || x >= W) continue;
+      const int sy = ty + kHalo, sx = tx + kHalo;
+      float v;
+      if (y >= wy0 && y < wy1 && x >= wx0 && x < wx1) {
         float acc = __fmul_rn(s1[sy - 2][sx], a.blur_w[0]);
         acc = __fadd_rn(acc, __fmul_rn(s1[sy - 1][sx], a.blur_w[1]));
         acc = __fadd_rn(acc, __fmul_rn(s1[sy][sx], a.blur_w[2]));
         acc = __fadd_rn(acc, __fmul_rn(s1[sy + 1][sx], a.blur_w[3]));
         acc = __fadd_rn(acc, __fmul_rn(s1[sy + 2][sx], a.blur_w[4]));
         v = round_clip_u8(acc);
-        k0 = blur_at + 1;
+        for (int k = blur_at + 1; k < 5; ++k) v = apply_pointwise(a.order[k], v, a, y, x, W);
       } else {
-        v = luma_at(y, x);
+        v = luma_at(y, x);      // padding: luma only
       }
-      for (int k = k0; k < 5; ++k) v = apply_pointwise(a.order[k], v, a, y, x, W);
-    } else {
-      v = luma_at(y, x);      // padding, or an image the host did not select: luma only
+      const uint8_t g = (uint8_t)v;
+      uint8_t* p = out + ((size_t)y * W + x) * 3;
+      p[0] = g; p[1] = g; p[2] = g;
     }
-    const uint8_t g = (uint8_t)v;
-    uint8_t* p = out + ((size_t)y * W + x) * 3;
-    p[0] = g; p[1] = g; p[2] = g;
-  }
-  __syncthreads();   // the shared tiles are reused by the next iteration
   }
 }
 
@@ -197,12 +218,8 @@ int urso_sim2real_aug(const uint8_t* src, uint8_t* dst, const urso_aug_params* p
   URSO_REQUIRE(src && dst && params_dev, "null pointer");
   URSO_REQUIRE(src != dst, "sim2real_aug is out of place (the blur reads neighbours)");
   URSO_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "bad shape");
-  const long long n_tiles = (long long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * B;
-  URSO_REQUIRE(n_tiles < 0x7fffffffLL, "too many tiles");
-  int sms = num_sms();
-  if (sms <= 0) sms = 148;
-  const int grid = (int)(n_tiles < (long long)sms * 8 ? n_tiles : (long long)sms * 8);
-  sim2real_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, params_dev, H, W, (int)n_tiles);
+  dim3 grid(((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW), B);
+  sim2real_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, params_dev, H, W);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
