@@ -11,7 +11,7 @@ Differences, all deliberate and documented in INTEGRATION.md:
     stem staging kernel, which cuts the per-step host->device copy 4x (59 MB instead of 236 MB at 640x960x32);
   * pd.read_csv(header=-1) (urso.py:42) is invalid on pandas >= 1.0: header=None is used;
   * sim2real augmentation (net.py:390-406) runs on the device (augment.py / csrc/augment.cu) for uint8 feeds; the
-    camera-rotation augmentations (net.py:409-438) are not built yet and raise if requested.
+    camera-rotation augmentations (net.py:409-438, utils.py:30-86) run on the host with cv2 like the reference's.
 """
 import json
 import logging
@@ -212,20 +212,94 @@ def write_synthetic_urso(dataset_dir, n_train=4, n_val=2, n_test=2, width=1280, 
             f.write("x,y,z,q1,q2,q3,q4\n" + "\n".join(",".join(repr(float(v)) for v in r) for r in rows) + "\n")
 
 
+# ------------------------------------------------------------------------------------------------ rotation augmentation
+def _rot_xyz_deg(pitch, yaw, roll):
+    """R = Rz(roll) Ry(yaw) Rx(pitch), angles in degrees (the matrix of se3lib.euler2SO3_left, se3lib.py:38-51)."""
+    a, b, c = np.deg2rad([pitch, yaw, roll])
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def _rot_to_quat_jpl(R):
+    """Rotation matrix -> JPL (left-handed) quaternion [x, y, z, w], the four-branch formula of Trawny & Roumeliotis that
+    se3lib.SO32quat (se3lib.py:77-115) uses; written around the largest diagonal term."""
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        z = np.sqrt(tr + 1.0) * 2
+        return np.array([(R[1, 2] - R[2, 1]) / z, (R[2, 0] - R[0, 2]) / z, (R[0, 1] - R[1, 0]) / z, 0.25 * z])
+    i = 0 if (R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]) else (1 if R[1, 1] > R[2, 2] else 2)
+    j, k = (i + 1) % 3, (i + 2) % 3
+    z = np.sqrt(1.0 + 2 * R[i, i] - tr) * 2
+    q = np.zeros(4)
+    q[i] = 0.25 * z
+    q[j] = (R[i, j] + R[j, i]) / z
+    q[k] = (R[i, k] + R[k, i]) / z
+    q[3] = (R[j, k] - R[k, j]) / z
+    return q
+
+
+def _quat_mult_jpl(a, b):
+    """a (x) b in the JPL convention of se3lib.quat_mult (se3lib.py:164-179), normalised."""
+    ax, ay, az, aw = a
+    L = np.array([[aw, az, -ay, ax], [-az, aw, ax, ay], [ay, -ax, aw, az], [-ax, -ay, -az, aw]])
+    r = L @ np.asarray(b, dtype=np.float64)
+    return r / np.linalg.norm(r)
+
+
+def warp_by_camera_rotation(image, t, q, K, pitch_yaw_roll_deg):
+    """The image / pose update shared by utils.rotate_cam and utils.rotate_image (utils.py:30-86): the camera is rotated by
+    R, the image is re-projected with the homography K R K^-1 and the pose becomes t R^T, q_R (x) q.
+    Parity trap: the reference passes cv2.WARP_INVERSE_MAP as the FOURTH positional argument of cv2.warpPerspective
+    (utils.py:47,76), which is `dst`, not `flags` -- so the flag is never set and M is applied as a forward map with
+    bilinear interpolation.  That behaviour is what the golden vectors (tests/golden/rotaug_golden.npz) pin."""
+    R = _rot_xyz_deg(*pitch_yaw_roll_deg)
+    K = np.asarray(K, dtype=np.float64)
+    M = K @ R @ np.linalg.inv(K)
+    h, w = image.shape[:2]
+    warped = cv2.warpPerspective(image, M, (w, h))
+    t_new = np.asarray(t, dtype=np.float64) @ R.T
+    q_new = _quat_mult_jpl(_rot_to_quat_jpl(R), q)
+    return warped, t_new, q_new
+
+
+def rotate_cam(image, t, q, K, magnitude, rng=np.random):
+    """Random camera-orientation perturbation, +-magnitude/2 degrees per Euler angle (utils.py:30-57)."""
+    return warp_by_camera_rotation(image, t, q, K, (rng.rand(3) - 0.5) * magnitude)
+
+
+def rotate_image(image, t, q, K, rng=np.random):
+    """Random in-plane (roll) rotation of +-85 degrees (utils.py:59-86)."""
+    return warp_by_camera_rotation(image, t, q, K, (0.0, 0.0, (rng.rand(1) - 0.5)[0] * 170))
+
+
 # ------------------------------------------------------------------------------------------------ batch generator
 def load_image_gt(dataset, config, image_id, device_aug=False):
     """(image uint8 [H,W,3] resized+padded, image_meta, loc, ori) -- net.py:358-456 without the augmentations."""
-    if getattr(config, "ROT_AUG", False) or getattr(config, "ROT_IMAGE_AUG", False):
-        raise NotImplementedError("camera / in-plane rotation augmentation (net.py:409-438) is not built yet")
     image = dataset.load_image(image_id)
     loc = dataset.load_location(image_id)
     ori = dataset.load_quaternion(image_id) if config.REGRESS_ORI else dataset.load_orientation_encoded(image_id)
+    rot_aug, rot_img = getattr(config, "ROT_AUG", False), getattr(config, "ROT_IMAGE_AUG", False)
     if getattr(config, "SIM2REAL_AUG", False) and not device_aug:
         # luma written back into the uint8 image (net.py:391-394).  The stochastic imgaug pipeline (net.py:395-406) only
         # exists on the device (csrc/augment.cu, applied when the uploaded batch is swapped in): with device_aug the
         # frame is left untouched here and the kernel does the luma step too
         gray = (0.2126 * image[:, :, 0] + 0.7152 * image[:, :, 1] + 0.0722 * image[:, :, 2]).astype(np.uint8)
         image = np.stack([gray] * 3, -1)
+    if rot_aug or rot_img:
+        # net.py:409-438: one of the two warps, mutually exclusive on a coin flip; the pose follows the camera and the
+        # orientation soft label is re-encoded from the rotated quaternion
+        assert config.REGRESS_LOC and getattr(config, "ORIENTATION_PARAM", "quaternion") == "quaternion"
+        dice = np.random.rand(1)
+        warp = None
+        if rot_aug and dice > 0.5:
+            warp = lambda im, t, q: rotate_cam(im, t, q, dataset.camera.K, 20)
+        elif rot_img and dice <= 0.5:
+            warp = lambda im, t, q: rotate_image(im, t, q, dataset.camera.K)
+        if warp is not None:
+            image, loc, q_new = warp(image, loc, dataset.load_quaternion(image_id))
+            ori = q_new if config.REGRESS_ORI else dataset.encoder.encode(np.asarray(q_new)[None])[0]
     original_shape = image.shape
     image, window, scale, _padding, _crop = resize_image(image, min_dim=config.IMAGE_MIN_DIM, min_scale=config.IMAGE_MIN_SCALE,
                                                          max_dim=config.IMAGE_MAX_DIM, mode=config.IMAGE_RESIZE_MODE)
