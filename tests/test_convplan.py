@@ -69,6 +69,40 @@ def test_wgrad_segments_match_autograd(kh, stride, padding, cin, cout, h, w):
     assert torch.allclose(G.reshape(kh, kh, cin, cout), ref, atol=1e-9)
 
 
+@pytest.mark.parametrize("kh,padding,cin,cout,h,w", [(1, "valid", 64, 128, 8, 12), (3, "same", 64, 64, 8, 12),
+                                                     (3, 1, 128, 64, 6, 10)])
+def test_sparse_output_gradient_uses_decimated_geometry(kh, padding, cin, cout, h, w):
+    """Backward of a stride-1 conv whose output gradient lives on the even-even pixels only (engine.py, structural
+    sparsity behind 1x1/stride-2 convs): dgrad / wgrad on the decimated grid with the stride-2 geometry equal autograd
+    with the zero-filled dense gradient; for a 1x1 conv only phase (0,0) of dx is written (it is sparse again)."""
+    x = torch.randn(2, h, w, cin, dtype=DT, requires_grad=True)
+    wk = torch.randn(kh, kh, cin, cout, dtype=DT, requires_grad=True)
+    scale = torch.rand(cout, dtype=DT) + 0.5
+    y = O.conv2d(x, wk, None, 1, padding)
+    du = torch.zeros_like(y)
+    du[:, ::2, ::2, :] = torch.randn_like(du[:, ::2, ::2, :])          # what a 1x1/s2 consumer sends back
+    ref_dx, ref_dw = torch.autograd.grad(y * scale, (x, wk), du)
+    g = P.decimated_geom(P.make_geom(kh, 1, padding, cin, cout, h, w))
+    du_dec = du[:, ::2, ::2, :]
+    assert (g.oh, g.ow) == tuple(du_dec.shape[1:3])
+    # dgrad: four phase launches over the decimated gradient
+    dx = torch.zeros_like(ref_dx)
+    du_p = torch.zeros(*du_dec.shape[:3], P.ceil64(cout), dtype=DT)
+    du_p[..., :cout] = du_dec
+    written = []
+    for oph, opw, segs, tap_map in P.dgrad_phases(g):
+        tgt = dx[:, oph::2, opw::2, :]
+        if not segs:
+            continue
+        written.append((oph, opw))
+        tgt.copy_(E.emu_convgemm([du_p], E.stage_cols(wk.detach(), scale, tap_map), segs, tgt.shape[1], tgt.shape[2]))
+    assert torch.allclose(dx, ref_dx, atol=1e-10)
+    assert written == ([(0, 0)] if kh == 1 else [(0, 0), (0, 1), (1, 0), (1, 1)])
+    # wgrad: the four parity views of x against the decimated gradient
+    G = E.emu_wgrad(P.input_views(x.detach(), 2), du_dec, P.wgrad_segments(g), cin, cout)
+    assert torch.allclose(G.reshape(kh, kh, cin, cout) * scale, ref_dw, atol=1e-9)
+
+
 def test_stem_space_to_depth_matches_7x7_s2():
     B, H, W = 2, 16, 24
     img = torch.rand(B, H, W, 3, dtype=DT) * 255

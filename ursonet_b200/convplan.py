@@ -72,6 +72,14 @@ def make_geom(kh, stride, padding, cin, cout, h, w) -> ConvGeom:
     return ConvGeom(kh, kh, stride, pt, pl, cin, cout, h, w, oh, ow)
 
 
+def decimated_geom(g: ConvGeom) -> ConvGeom:
+    """Geometry of a stride-1 conv whose OUTPUT GRADIENT is non-zero on the even-even pixels only (it sits behind a
+    1x1/stride-2 conv): for its dgrad / wgrad it acts as the same filter at stride 2 on the decimated output grid
+    du[:, ::2, ::2, :]."""
+    assert g.stride == 1
+    return ConvGeom(g.kh, g.kw, 2, g.pad_t, g.pad_l, g.cin, g.cout, g.h, g.w, (g.oh + 1) // 2, (g.ow + 1) // 2)
+
+
 # ------------------------------------------------------------------------------------------------ forward / wgrad
 def n_phase_views(stride: int) -> int:
     return 1 if stride == 1 else 4

@@ -562,10 +562,7 @@ class Engine:
         """Geometry of conv c for its gradient launches; with a sparse (even-even only) output gradient it acts as the
         same filter at twice the stride on the decimated output grid."""
         gm = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
-        if not sparse_dst:
-            return gm
-        assert c.stride == 1
-        return P.ConvGeom(gm.kh, gm.kw, 2, gm.pad_t, gm.pad_l, gm.cin, gm.cout, h, w, (gm.oh + 1) // 2, (gm.ow + 1) // 2)
+        return P.decimated_geom(gm) if sparse_dst else gm
 
     def _bwd_deps(self, lane):
         """Cross-lane dependency of the FIRST backward op of a slice lane: the whole-batch head backward (lane 0).
