@@ -112,8 +112,24 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
     if (tcol != 0) return;
     if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
       const int groups = W >> 2;
+      // per-image values hoisted out of the pixel loops (all block-uniform)
+      int ops[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) ops[k] = a.order[k];
+      const int noise_q = a.noise_q, add_i = a.add, drop_h = a.drop_h, drop_w = a.drop_w;
+      const uint32_t noise_seed = a.noise_seed, drop_seed = a.drop_seed, drop_thresh = a.drop_thresh;
+      const float mul = a.mul;
+      const uint32_t wh = (uint32_t)(wy1 - wy0), ww = (uint32_t)(wx1 - wx0);
       for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         const int x = g * 4;
+        // column-only quantities: which of the 4 pixels lie inside the window, their dropout cell column
+        bool in_col[4];
+        uint32_t cx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          in_col[j] = x + j >= wx0 && x + j < wx1;
+          cx[j] = (apply && in_col[j] && drop_thresh != 0u) ? ((uint32_t)(x + j - wx0) * (uint32_t)drop_w) / ww : 0u;
+        }
 #pragma unroll 4
         for (int r = 0; r < kTileH; ++r) {
           const int y = y0 + r;
@@ -126,10 +142,31 @@ __global__ void __launch_bounds__(256) sim2real_kernel(const uint8_t* __restrict
           v[2] = luma_u8((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
           v[3] = luma_u8((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
           if (apply && y >= wy0 && y < wy1) {
+            // one (block-uniform) dispatch per operation for the four pixels, same arithmetic as apply_pointwise
+            const uint32_t cyw = drop_thresh != 0u ? (((uint32_t)(y - wy0) * (uint32_t)drop_h) / wh) * (uint32_t)drop_w : 0u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (x + j >= wx0 && x + j < wx1) {
-                for (int k = 0; k < 5; ++k) v[j] = apply_pointwise(a.order[k], v[j], a, y, x + j, W);
+            for (int k = 0; k < 5; ++k) {
+              const int op = ops[k];
+              if (op == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t h = hash_u32(noise_seed, (uint32_t)(y * W + x + j));
+                  const int z = (int)(h & 255u) + (int)((h >> 8) & 255u) + (int)((h >> 16) & 255u) + (int)(h >> 24) - 510;
+                  const int n = (z * noise_q + (z >= 0 ? 32768 : -32768)) / 65536;
+                  if (in_col[j]) v[j] = fminf(fmaxf(v[j] + (float)n, 0.f), 255.f);
+                }
+              } else if (op == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (in_col[j]) v[j] = fminf(fmaxf(v[j] + (float)add_i, 0.f), 255.f);
+              } else if (op == 3) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (in_col[j]) v[j] = round_clip_u8(__fmul_rn(v[j], mul));
+              } else if (op == 4 && drop_thresh != 0u) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (in_col[j] && hash_u32(drop_seed, cyw + cx[j]) < drop_thresh) v[j] = 0.f;
               }
             }
           }
