@@ -93,6 +93,7 @@ struct ConvGemmParams {
   // and multicasts it to both (halves the L2 -> SM traffic of B, which bounds the large-N tiles)
   CUtensorMap b_half_map;
   int cluster, total_pairs;
+  int cta2;   // CTA pairs with tcgen05.mma.cta_group::2 (BLOCK_N = 256 only; see the kernel)
 };
 
 constexpr int kBlockM = 128;
@@ -174,10 +175,15 @@ struct ChunkIter {
   }
 };
 
-template <int BLOCK_N>
+// CTA2 = true: CTA pairs (cluster of 2) issue ONE tcgen05.mma.cta_group::2 per K = 16 slice over two adjacent M tiles of the
+// same N tile (M = 256): each CTA stages its own A tile and HALF of the weight tile, so the per-SM operand ingest of a
+// 128x256 tile drops from 48 to 32 KB per K step.  The leader CTA (cluster rank 0) owns the full / tempty barriers and
+// issues the MMAs; TMA loads of both CTAs signal the leader's full barrier; commits arrive on both CTAs' barriers.
+template <int BLOCK_N, bool CTA2>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kBTileBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
   constexpr int kTmemCols = 2 * BLOCK_N;
+  const uint32_t pair_rank = CTA2 ? cluster_ctarank() : 0u;
   // 1024-byte aligned by declaration (SWIZZLE_128B atoms): no integer round trip on the base pointer, so the compiler
   // keeps the shared address space and emits LDS/STS/ATOMS with 32-bit addresses instead of generic accesses
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -211,12 +217,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.cluster ? 2 : 1);   // cluster: both CTAs' MMAs must have consumed the stage
+      mbar_init(&full_bar[i], CTA2 ? 2 : 1);         // CTA2: one expect_tx arrival per CTA of the pair (leader's barrier)
+      mbar_init(&empty_bar[i], (p.cluster && !CTA2) ? 2 : 1);   // multicast mode: both CTAs' MMAs must have consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
+      mbar_init(&tempty_bar[i], CTA2 ? 16 : (p.epi_tma ? 8 : 4));   // CTA2: the epilogue warps of BOTH CTAs (leader's barrier)
     }
     for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     for (int i = 0; i < 4; ++i) {
@@ -226,7 +232,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     fence_barrier_init();
   }
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled layouts assume it
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_alloc_2cta(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   if (p.colsum != nullptr) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
   }
@@ -294,6 +303,17 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           for (int c = 0; c < sg.c_chunks; ++c, ++g) {
             if ((g & 1) == par) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
+              if constexpr (CTA2) {
+                if (elect_one()) {
+                  // both CTAs signal the LEADER's full barrier (shared::cluster address of rank 0)
+                  const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                  mbar_arrive_expect_tx_cluster(fb, kATileBytes + kBTileBytes);
+                  tma_load_4d_2cta(sA + stage * kATileBytes, &p.a_maps[sg.map_id], fb, c * kBlockK, w0 + sg.dw, h0 + sg.dh,
+                                   img);
+                  tma_load_2d_2cta(sB + stage * kBTileBytes, &p.b_half_map, fb, kcol,
+                                   n_tile * BLOCK_N + (int)pair_rank * (BLOCK_N / 2));
+                }
+              } else
 #if URSO_DEBUG_KNOBS
               if (p.dbg_no_tma && g >= kStages) {
                 if (elect_one()) mbar_arrive(&full_bar[stage]);
@@ -369,11 +389,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (elect_one()) umma_commit(&tfull_bar[as]);
         __syncwarp();
       }
-    } else {
+    } else if (!CTA2 || pair_rank == 0) {     // CTA pairs: the leader issues for both CTAs
       int stage = 0;
       uint32_t phase = 0;
       int ksteps = 0;
       for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
+      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kBlockM, BLOCK_N, 0, 0);   // M = 256 across the pair
       int it = 0;
       for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
         const int as = it & 1;
@@ -386,17 +407,24 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (elect_one()) {
             const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
             const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
-#if URSO_DEBUG_KNOBS
-            if (!p.dbg_no_mma)
-#endif
-            {
-              umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
+            if constexpr (CTA2) {
+              umma_bf16_2cta(d_tmem, ad, bd, idesc2, ks != 0);
 #pragma unroll
-              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, 1u);
+              umma_commit_2cta(&empty_bar[stage]);      // the slot is free in BOTH CTAs once these MMAs retire
+            } else {
+#if URSO_DEBUG_KNOBS
+              if (!p.dbg_no_mma)
+#endif
+              {
+                umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
+#pragma unroll
+                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              }
+              // smem slot reusable once these MMAs retire (cluster: tell the peer too -- it multicasts into my stage)
+              if (p.cluster) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
+              else umma_commit(&empty_bar[stage]);
             }
-            // smem slot reusable once these MMAs retire (cluster: tell the peer too -- it multicasts into my stage)
-            if (p.cluster) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
-            else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -404,7 +432,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (elect_one()) {                              // accumulator complete -> epilogue (of both CTAs of a pair)
+          if constexpr (CTA2) umma_commit_2cta(&tfull_bar[as]);
+          else umma_commit(&tfull_bar[as]);
+        }
         __syncwarp();
       }
     }
@@ -575,7 +606,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         // all of this warp's TMEM reads of the tile are complete: release the accumulator stage (8 arrivals)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's barrier
+          else mbar_arrive(&tempty_bar[as]);
+        }
       }
       if (lane == 0) tma_store_wait_all();
     } else {
@@ -695,7 +729,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -709,11 +744,11 @@ struct urso_convgemm {
   int smem_bytes;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CTA2 = false>
 static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
@@ -730,9 +765,9 @@ static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::conv_gemm_kernel<BLOCK_N>, h->params));
+    URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::conv_gemm_kernel<BLOCK_N, CTA2>, h->params));
   } else {
-    urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
+    urso::conv_gemm_kernel<BLOCK_N, CTA2><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
   }
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
@@ -837,6 +872,10 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     epi_bytes = kLegacyScratchBytes;
   }
   h->block_n = bn;
+  // CTA pairs (cta_group::2): each CTA stages half of the weight tile.  Opt-in (URSO_CTA2=1) while it is being evaluated.
+  p.cta2 = 0;
+  if (const char* e = getenv("URSO_CTA2")) p.cta2 = (atoi(e) && bn == 256 && !d->halo && p.epi_tma) ? 1 : 0;
+  const int b_rows_cta = p.cta2 ? bn / 2 : bn;      // rows of B resident per CTA
   int stages;
   if (d->halo) {
     // validate + plan the halo ring: one box per channel chunk, B tiles in their own ring
@@ -876,7 +915,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       return 2;
     }
   } else {
-    const int stage_bytes = kATileBytes + bn * kBlockK * 2;
+    const int stage_bytes = kATileBytes + b_rows_cta * kBlockK * 2;
     stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) {
@@ -887,7 +926,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     p.a_ring_bytes = stages * kATileBytes;
   }
   p.stages = stages;
-  const int fixed = p.a_ring_bytes + stages * bn * kBlockK * 2 + kCtrlBytes + kColAcc;
+  const int fixed = p.a_ring_bytes + stages * (d->halo ? bn : b_rows_cta) * kBlockK * 2 + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
     p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
@@ -937,6 +976,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     // L2 -> SM traffic (the L2 already de-duplicates near-simultaneous unicast requests), see profiles/r01_progress.md
     int want = 0;
     if (const char* e = getenv("URSO_CLUSTER")) want = atoi(e) && !p.halo && total >= 64;
+    if (p.cta2) want = 1;
     if (want) {
       const long long mt = (long long)p.tiles_w * p.tiles_h * d->NB;
       p.cluster = 1;
@@ -977,7 +1017,7 @@ extern "C" int urso_convgemm_launch(urso_convgemm_t* h, void* stream) {
     case 32: return launch_conv_gemm<32>(h, s);
     case 64: return launch_conv_gemm<64>(h, s);
     case 128: return launch_conv_gemm<128>(h, s);
-    case 256: return launch_conv_gemm<256>(h, s);
+    case 256: return h->params.cta2 ? launch_conv_gemm<256, true>(h, s) : launch_conv_gemm<256>(h, s);
   }
   urso::set_error("unsupported BLOCK_N %d", h->block_n);
   return 2;
