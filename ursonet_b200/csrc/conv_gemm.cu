@@ -94,6 +94,8 @@ struct ConvGemmParams {
   CUtensorMap b_half_map;
   int cluster, total_pairs;
   int cta2;   // CTA pairs with tcgen05.mma.cta_group::2 (BLOCK_N = 256 only; see the kernel)
+  int kpack;  // K steps (of 64) per pipeline stage / barrier round: 2 halves the per-K-step issue overhead of the MMA warp
+              // (wait + fence + elect + commit ~ 190 cycles, scripts/umma_rate.cu), which bounds the N <= 128 launches
 };
 
 constexpr int kBlockM = 128;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const int kStages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.a_ring_bytes;
-  uint8_t* ctrl = sB + kStages * kBTileBytes;
+  uint8_t* ctrl = sB + kStages * p.kpack * kBTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -290,6 +292,43 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
+    } else if (p.kpack == 2) {
+      // two K steps per stage: the owning producer warp (stage groups alternate between the two) arms the barrier once
+      // with the bytes of both K steps (one at the odd end of a tile) and issues their four tile loads
+      int stage = 0, gg = 0;
+      uint32_t phase = 0;
+      int ksteps = 0;
+      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
+        int n_tile, img, h0, w0;
+        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
+        int kcol = 0, ks = 0;
+        for (int s = 0; s < p.n_seg; ++s) {
+          const SegDev sg = p.seg[s];
+          for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
+            const int slot = ks & 1;
+            if ((gg & 1) == par) {
+              if (slot == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (elect_one()) {
+                if (slot == 0)
+                  mbar_arrive_expect_tx(&full_bar[stage], (ks + 1 < ksteps ? 2 : 1) * (kATileBytes + kBTileBytes));
+                tma_load_4d(sA + (stage * 2 + slot) * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK,
+                            w0 + sg.dw, h0 + sg.dh, img);
+                tma_load_2d(sB + (stage * 2 + slot) * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+              }
+              __syncwarp();
+            }
+            kcol += kBlockK;
+            if (slot == 1 || ks + 1 == ksteps) {
+              ++gg;
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
     } else {
       int stage = 0;
       uint32_t phase = 0;
@@ -384,6 +423,40 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (++a_stage == p.a_stages) {
             a_stage = 0;
             a_phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&tfull_bar[as]);
+        __syncwarp();
+      }
+    } else if (p.kpack == 2) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int ksteps = 0;
+      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
+      int it = 0;
+      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int ks = 0; ks < ksteps; ks += 2) {
+          const int n = ksteps - ks >= 2 ? 2 : 1;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int j = 0; j < n; ++j) {
+              const uint64_t ad = kDescHiB | ((a_base + (stage * 2 + j) * kATileBytes) >> 4);
+              const uint64_t bd = kDescHiB | ((b_base + (stage * 2 + j) * kBTileBytes) >> 4);
+              umma_bf16(d_tmem, ad, bd, idesc, (ks + j) != 0);
+#pragma unroll
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);   // one commit per TWO K steps
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
         if (elect_one()) umma_commit(&tfull_bar[as]);
@@ -876,6 +949,18 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.cta2 = 0;
   if (const char* e = getenv("URSO_CTA2")) p.cta2 = (atoi(e) && bn == 256 && !d->halo && p.epi_tma) ? 1 : 0;
   const int b_rows_cta = p.cta2 ? bn / 2 : bn;      // rows of B resident per CTA
+  p.kpack = 1;
+  {
+    int kst = 0;
+    for (int s2 = 0; s2 < d->n_seg; ++s2) kst += d->seg[s2].c_chunks;
+    // measured per layer (gpurun_out kp_*, profiles/r01_progress.md): a win for launches WITHOUT epilogue inputs and a
+    // long enough K loop (stem -9 %, stage-2 3x3 -10 %, bottleneck conv -26 %), a loss where the epilogue rings already
+    // squeeze the stage count (dgrad with mask / addend).  URSO_KPACK=0 disables, =2 forces it for every N <= 128 launch.
+    const bool no_epi_inputs = d->addend.ptr == nullptr && d->mask.ptr == nullptr;
+    int want = (no_epi_inputs && kst >= 4) ? 2 : 1;
+    if (const char* e = getenv("URSO_KPACK")) want = atoi(e);
+    if (want == 2 && bn <= 128 && !d->halo && !p.cta2 && kst >= 2 && getenv("URSO_CLUSTER") == nullptr) p.kpack = 2;
+  }
   int stages;
   if (d->halo) {
     // validate + plan the halo ring: one box per channel chunk, B tiles in their own ring
@@ -915,18 +1000,23 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       return 2;
     }
   } else {
-    const int stage_bytes = kATileBytes + b_rows_cta * kBlockK * 2;
+    int stage_bytes = p.kpack * (kATileBytes + b_rows_cta * kBlockK * 2);
     stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
+    if (stages < 2 && p.kpack == 2) {     // not enough room for two double stages: fall back to one K step per stage
+      p.kpack = 1;
+      stage_bytes = kATileBytes + b_rows_cta * kBlockK * 2;
+      stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
+    }
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) {
       set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
       delete h;
       return 2;
     }
-    p.a_ring_bytes = stages * kATileBytes;
+    p.a_ring_bytes = stages * p.kpack * kATileBytes;
   }
   p.stages = stages;
-  const int fixed = p.a_ring_bytes + stages * (d->halo ? bn : b_rows_cta) * kBlockK * 2 + kCtrlBytes + kColAcc;
+  const int fixed = p.a_ring_bytes + stages * p.kpack * (d->halo ? bn : b_rows_cta) * kBlockK * 2 + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
     p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
