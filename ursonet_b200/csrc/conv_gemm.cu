@@ -292,34 +292,37 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
-    } else if (p.kpack == 2) {
-      // two K steps per stage: the owning producer warp (stage groups alternate between the two) arms the barrier once
+    } else if (p.kpack >= 2) {
+      // kpack (2 or 4) K steps per stage: the owning producer warp (stage groups alternate between the two) arms the barrier once
       // with the bytes of both K steps (one at the odd end of a tile) and issues their four tile loads
       int stage = 0, gg = 0;
       uint32_t phase = 0;
+      const int kp = p.kpack;
       int ksteps = 0;
       for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
       for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
         int n_tile, img, h0, w0;
         decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
-        int kcol = 0, ks = 0;
+        int kcol = 0, ks = 0, slot = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
-            const int slot = ks & 1;
             if ((gg & 1) == par) {
               if (slot == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
               if (elect_one()) {
-                if (slot == 0)
-                  mbar_arrive_expect_tx(&full_bar[stage], (ks + 1 < ksteps ? 2 : 1) * (kATileBytes + kBTileBytes));
-                tma_load_4d(sA + (stage * 2 + slot) * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK,
+                if (slot == 0) {
+                  const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
+                  mbar_arrive_expect_tx(&full_bar[stage], n_grp * (kATileBytes + kBTileBytes));
+                }
+                tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK,
                             w0 + sg.dw, h0 + sg.dh, img);
-                tma_load_2d(sB + (stage * 2 + slot) * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
               }
               __syncwarp();
             }
             kcol += kBlockK;
-            if (slot == 1 || ks + 1 == ksteps) {
+            if (++slot == kp || ks + 1 == ksteps) {
+              slot = 0;
               ++gg;
               if (++stage == kStages) {
                 stage = 0;
@@ -428,9 +431,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (elect_one()) umma_commit(&tfull_bar[as]);
         __syncwarp();
       }
-    } else if (p.kpack == 2) {
+    } else if (p.kpack >= 2) {
       int stage = 0;
       uint32_t phase = 0;
+      const int kp = p.kpack;
       int ksteps = 0;
       for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
       int it = 0;
@@ -439,19 +443,19 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int ks = 0; ks < ksteps; ks += 2) {
-          const int n = ksteps - ks >= 2 ? 2 : 1;
+        for (int ks = 0; ks < ksteps; ks += kp) {
+          const int n = ksteps - ks < kp ? ksteps - ks : kp;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
             for (int j = 0; j < n; ++j) {
-              const uint64_t ad = kDescHiB | ((a_base + (stage * 2 + j) * kATileBytes) >> 4);
-              const uint64_t bd = kDescHiB | ((b_base + (stage * 2 + j) * kBTileBytes) >> 4);
+              const uint64_t ad = kDescHiB | ((a_base + (stage * kp + j) * kATileBytes) >> 4);
+              const uint64_t bd = kDescHiB | ((b_base + (stage * kp + j) * kBTileBytes) >> 4);
               umma_bf16(d_tmem, ad, bd, idesc, (ks + j) != 0);
 #pragma unroll
               for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
             }
-            umma_commit(&empty_bar[stage]);   // one commit per TWO K steps
+            umma_commit(&empty_bar[stage]);   // one commit per kpack K steps
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -957,9 +961,11 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     // long enough K loop (stem -9 %, stage-2 3x3 -10 %, bottleneck conv -26 %), a loss where the epilogue rings already
     // squeeze the stage count (dgrad with mask / addend).  URSO_KPACK=0 disables, =2 forces it for every N <= 128 launch.
     const bool no_epi_inputs = d->addend.ptr == nullptr && d->mask.ptr == nullptr;
+    // (4 K steps per round, URSO_KPACK=4, measured worse for the 9-K-step 3x3 layers: rounds of 4,4,1 on a 2-deep ring)
     int want = (no_epi_inputs && kst >= 4) ? 2 : 1;
     if (const char* e = getenv("URSO_KPACK")) want = atoi(e);
-    if (want == 2 && bn <= 128 && !d->halo && !p.cta2 && kst >= 2 && getenv("URSO_CLUSTER") == nullptr) p.kpack = 2;
+    if ((want == 2 || want == 4) && bn <= 128 && !d->halo && !p.cta2 && kst >= 2 && getenv("URSO_CLUSTER") == nullptr)
+      p.kpack = want;
   }
   int stages;
   if (d->halo) {
@@ -1002,9 +1008,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   } else {
     int stage_bytes = p.kpack * (kATileBytes + b_rows_cta * kBlockK * 2);
     stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
-    if (stages < 2 && p.kpack == 2) {     // not enough room for two double stages: fall back to one K step per stage
-      p.kpack = 1;
-      stage_bytes = kATileBytes + b_rows_cta * kBlockK * 2;
+    while (stages < 2 && p.kpack > 1) {   // not enough room for two packed stages: fewer K steps per stage
+      p.kpack /= 2;
+      stage_bytes = p.kpack * (kATileBytes + b_rows_cta * kBlockK * 2);
       stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
     }
     if (stages > kMaxStages) stages = kMaxStages;
