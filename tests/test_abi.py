@@ -38,3 +38,10 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(lib.UrsoError):
         lib.call("urso_dense_fwd", None, None, None, 1, 1, 1, None)      # null pointers -> rc != 0 + message
     assert b"null" in lib.load().urso_last_error()
+
+
+def test_aug_params_layout_matches_header():
+    """ursonet_b200.augment.AUG_DTYPE is the numpy image of struct urso_aug_params (include/urso_b200.h)."""
+    from ursonet_b200 import augment, lib
+    assert lib.load().urso_sizeof_aug_params() == augment.AUG_DTYPE.itemsize
+    augment.check_layout()
