@@ -1,6 +1,7 @@
 """Bottleneck isolation for Engine F: per-layer forward times with the TMA loads or the MMAs switched off
 (URSO_DBG_NO_TMA=1 / URSO_DBG_NO_MMA=1; outputs are garbage, timing only).  Needs a library built with
-`make -C ursonet_b200/csrc clean all DEBUG_KNOBS=1`.  Run under gpurun."""
+`make -C ursonet_b200/csrc clean all DEBUG_KNOBS=1`.  Run under gpurun.  The knobs also exist in the CTA-pair kernel:
+`URSO_CTA2=1 python scripts/bench_isolate.py` isolates the cta_group::2 path (first measurement planned for round 2)."""
 import json, os, subprocess, sys
 out = {}
 for tag, env in (("normal", {}), ("no_tma", {"URSO_DBG_NO_TMA": "1"}), ("no_mma", {"URSO_DBG_NO_MMA": "1"})):

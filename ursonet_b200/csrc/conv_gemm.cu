@@ -349,11 +349,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 if (elect_one()) {
                   // both CTAs signal the LEADER's full barrier (shared::cluster address of rank 0)
                   const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+#if URSO_DEBUG_KNOBS
+                  if (p.dbg_no_tma && g >= kStages) {
+                    mbar_arrive_cluster(fb);      // isolation: keep the handshake, skip the loads
+                  } else
+#endif
+                  {
                   mbar_arrive_expect_tx_cluster(fb, kATileBytes + kBTileBytes);
                   tma_load_4d_2cta(sA + stage * kATileBytes, &p.a_maps[sg.map_id], fb, c * kBlockK, w0 + sg.dw, h0 + sg.dh,
                                    img);
                   tma_load_2d_2cta(sB + stage * kBTileBytes, &p.b_half_map, fb, kcol,
                                    n_tile * BLOCK_N + (int)pair_rank * (BLOCK_N / 2));
+                  }
                 }
               } else
 #if URSO_DEBUG_KNOBS
@@ -485,9 +492,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
             const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
             if constexpr (CTA2) {
-              umma_bf16_2cta(d_tmem, ad, bd, idesc2, ks != 0);
+#if URSO_DEBUG_KNOBS
+              if (!p.dbg_no_mma)
+#endif
+              {
+                umma_bf16_2cta(d_tmem, ad, bd, idesc2, ks != 0);
 #pragma unroll
-              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, 1u);
+                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, 1u);
+              }
               umma_commit_2cta(&empty_bar[stage]);      // the slot is free in BOTH CTAs once these MMAs retire
             } else {
 #if URSO_DEBUG_KNOBS
