@@ -116,7 +116,6 @@ def local_backward_check(eng, p64, cfg):
     flips chaotically, so END-TO-END gradients can only be compared loosely; instead every layer's gradients are
     recomputed in fp64 FROM THE ENGINE'S OWN stored tensors (its bf16 input activation and its bf16 output gradient)
     and must match tightly.  This pins the wiring: which buffer feeds which launch, masks, fan-in, strides, phases."""
-    from ursonet_b200.graph import build_graph
     g = eng.graph
     P64 = {k: v.double() for k, v in p64.items()}
     cons = {}

@@ -6,7 +6,6 @@
 kernel on the uploaded uint8 batch (csrc/augment.cu).  Deviation from the reference, by construction of a device-side
 pipeline: the reference augments the full-size image BEFORE resize + pad64; here the network-resolution frame is augmented
 (inside the image window only, so the padding stays zero as in the reference)."""
-import ctypes as C
 
 import numpy as np
 
