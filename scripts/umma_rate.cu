@@ -64,6 +64,90 @@ __global__ void __launch_bounds__(128, 1) loop_kernel(long long* out, int iters,
   }
 }
 
+// The same loop for a CTA pair (cta_group::2, M = 256): the leader issues 4 MMAs + one multicast commit per K step and waits for
+// the commit of `depth` steps ago; the peer only allocates TMEM and waits for the end.  NOT RUN YET (written at the end of
+// round 1 to isolate why the pair kernel of Engine F is slower than the single-CTA one: is it the multicast commit?).
+template <int N>
+__global__ void __launch_bounds__(128, 1) loop_kernel_2cta(long long* out, int iters, int mode, int depth) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t ring[16];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (16384 + N * 64) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&ring[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && rank == 0) {
+    constexpr uint64_t hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
+    const uint64_t ad = hi | (smem_u32(smem) >> 4), bd = hi | ((smem_u32(smem) + 16384) >> 4);
+    constexpr uint32_t idesc = umma_idesc_bf16(256, N, 0, 0);
+    const long long t0 = clock64();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (mode == 2 && it >= depth) mbar_wait(&ring[stage], phase ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_2cta(tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+        umma_commit_2cta(&ring[stage]);
+      }
+      __syncwarp();
+      if (++stage == depth) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit_2cta(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  } else if (warp == 0) {
+    mbar_wait(&bar, 0);      // the leader's final multicast commit
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem, 512);
+  }
+}
+
+template <int N>
+static void run_loop_2cta(const char* name, int mode, int depth) {
+  long long* d;
+  const int grid = 148;
+  cudaMalloc(&d, grid * sizeof(long long));
+  cudaMemset(d, 0, grid * sizeof(long long));
+  const int iters = 4096, smem = 16384 + N * 64 + 1024;
+  cudaFuncSetAttribute(loop_kernel_2cta<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, loop_kernel_2cta<N>, d, iters, mode, depth);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+  long long mx = 0;
+  for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+  printf("%-40s %s  cycles per K step (4 pair MMAs) %7.1f\n", name, cudaGetErrorString(e), (double)mx / iters);
+  cudaFree(d);
+}
+
 template <int N>
 static void run_loop(const char* name, int mode, int depth) {
   long long* d;
@@ -174,5 +258,7 @@ int main() {
   run_loop<64>("N64  commit + wait depth 2", 2, 2);
   run_loop<128>("N128 commit + wait depth 6", 2, 6);
   run_loop<256>("N256 commit + wait depth 4", 2, 4);
+  run_loop_2cta<256>("pair N256 commit per K step", 1, 6);
+  run_loop_2cta<256>("pair N256 commit + wait depth 6", 2, 6);
   return 0;
 }
