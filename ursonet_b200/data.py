@@ -177,10 +177,11 @@ class Speed(Urso):
     camera = SpeedCamera()
 
     def load_dataset(self, dataset_dir, config, subset):
+        assert subset in ["train", "train_no_val", "val", "test", "real", "real_test", "train_total"]   # speed.py:35
         self.name = "Speed"
         with open(os.path.join(dataset_dir, subset + ".json")) as f:
             items = json.load(f)
-        folder = "real_test" if subset == "real_test" else ("test" if subset == "test" else "train")
+        folder = "train" if subset in ("train_no_val", "val") else subset      # speed.py:92-95
         files = [os.path.join("images", folder, it["filename"]) for it in items]
         if items and "q_vbs2tango" in items[0]:
             q = np.stack([_hemisphere([it["q_vbs2tango"][1], it["q_vbs2tango"][2], it["q_vbs2tango"][3],
@@ -307,17 +308,36 @@ def load_image_gt(dataset, config, image_id, device_aug=False):
     return image, meta, loc, ori
 
 
-def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False, device_aug=False):
+def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False, device_aug=False, rank=0, world=1,
+                   seed=0):
     """Infinite generator of ([images, image_meta, gt_locs, gt_oris], []) like net.data_generator (net.py:458-559).
-    raw_uint8=True yields un-molded uint8 images (the engine subtracts MEAN_PIXEL on the GPU)."""
-    b, image_index, error_count = 0, -1, 0
-    image_ids = np.copy(dataset.image_ids)
+    raw_uint8=True yields un-molded uint8 images (the engine subtracts MEAN_PIXEL on the GPU).
+    world > 1 (one process per GPU): every pass over the dataset uses ONE permutation shared by all ranks
+    (dp.shard_indices, seeded by `seed` and the pass number) and each rank takes its strided share, so an epoch visits
+    every image once across the job instead of `world` overlapping private shuffles."""
+    if getattr(config, "SIM2REAL_AUG", False) and not (raw_uint8 and device_aug):
+        # the stochastic imgaug pipeline (net.py:395-406) exists only in the device kernel (csrc/augment.cu), which
+        # needs the raw uint8 feed: refuse to train silently without it
+        raise ValueError("SIM2REAL_AUG needs the raw uint8 feed with the on-device augmentation "
+                         "(data_generator(raw_uint8=True, device_aug=True))")
+    b, image_index, error_count, n_pass = 0, -1, 0, 0
+    all_ids = np.copy(dataset.image_ids)
+    if world > 1:
+        from .dp import shard_indices
+        image_ids = all_ids[shard_indices(len(all_ids), rank, world, seed, 0)] if shuffle else all_ids[rank::world]
+        assert len(image_ids) > 0, "fewer images than ranks"
+    else:
+        image_ids = all_ids
     n_ori = 4 if config.REGRESS_ORI else config.ORI_BINS_PER_DIM ** 3
     while True:
         try:
             image_index = (image_index + 1) % len(image_ids)
             if shuffle and image_index == 0:
-                np.random.shuffle(image_ids)
+                if world > 1:
+                    image_ids = all_ids[shard_indices(len(all_ids), rank, world, seed, n_pass)]
+                    n_pass += 1
+                else:
+                    np.random.shuffle(image_ids)
             image_id = image_ids[image_index]
             image, meta, loc, ori = load_image_gt(dataset, config, image_id, device_aug=device_aug and raw_uint8)
             if b == 0:

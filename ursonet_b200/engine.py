@@ -792,6 +792,7 @@ class Engine:
             self._main.wait_stream(st)
 
     _serial = False      # profile_ops: issue everything on the current stream, in list order
+    _split_run = False   # True while the two-graph (overlapped all-reduce) schedule is being issued / captured
 
     def _run(self, ops):
         if self.aux_lane == 0 or self._serial:
@@ -802,7 +803,9 @@ class Engine:
         for op in ops:
             st = main if op.lane == 0 else streams[op.lane]
             for a in op.after:
-                if a.lane != op.lane and a.segment == op.segment:   # an earlier segment ended with a full join
+                # Only in the split schedule does an earlier segment end with a full join (and live in another captured
+                # graph, whose events cannot be waited on); the single-graph schedule keeps every cross-lane edge.
+                if a.lane != op.lane and not (self._split_run and a.segment != op.segment):
                     st.wait_event(a.event)
             if op.lane == 0:
                 op()
@@ -857,29 +860,42 @@ class Engine:
         self._join()
 
     def _phase_train_a(self):      # forward + losses + the first part of backward (gradients of the arena tail)
-        self._fwd_body()
-        self._run(self.ops_loss)
-        self._run(self.ops_bwd[:self._bwd_split[0]])
-        self._join()
+        self._split_run = True
+        try:
+            self._fwd_body()
+            self._run(self.ops_loss)
+            self._run(self.ops_bwd[:self._bwd_split[0]])
+            self._join()
+        finally:
+            self._split_run = False
 
     def _phase_train_b(self):      # the rest of backward; runs while the tail's all-reduce is in flight
-        self._fork()
-        self._run(self.ops_bwd[self._bwd_split[0]:])
-        self._join()
+        self._split_run = True
+        try:
+            self._fork()
+            self._run(self.ops_bwd[self._bwd_split[0]:])
+            self._join()
+        finally:
+            self._split_run = False
 
     def _replay(self, key, fn, use_graph=True, warm=True):
+        """Run `fn`'s launches through a captured CUDA graph.  On the first call with warm=True the launches run eagerly
+        (sets function attributes, loads modules) and THAT eager run is the execution: the graph is captured afterwards
+        and not replayed, so a non-idempotent fn (the optimizer update) runs exactly once per call."""
         if not use_graph:
             fn()
             return
         gr = self._graphs.get(key)
         if gr is None:
             if warm:
-                fn()                               # eager warm-up (sets function attributes, loads modules)
+                fn()
             torch.cuda.synchronize()
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
                 fn()
             self._graphs[key] = gr
+            if warm:
+                return
         gr.replay()
 
     def forward(self, use_graph=True):

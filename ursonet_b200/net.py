@@ -227,8 +227,11 @@ class UrsoNet:
         cfg, e = self.config, self.engine
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         dev_aug = bool(raw_uint8 and getattr(cfg, "SIM2REAL_AUG", False))
-        train_gen = D.data_generator(train_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8, device_aug=dev_aug)
-        val_gen = D.data_generator(val_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8, device_aug=dev_aug)
+        shard = dict(rank=rank, world=self.world, seed=int(getattr(cfg, "DATA_SEED", 0)))
+        train_gen = D.data_generator(train_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8,
+                                     device_aug=dev_aug, **shard)
+        val_gen = D.data_generator(val_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8,
+                                   device_aug=dev_aug, **shard)
         history = BatchLogger()
         log("\nStarting at epoch {}. LR={}\n".format(self.epoch, learning_rate))
         log("Checkpoint Path: {}".format(self.checkpoint_path))
@@ -236,7 +239,7 @@ class UrsoNet:
         self.compile(learning_rate, cfg.LEARNING_MOMENTUM)
         allreduce = (lambda g: torch.distributed.all_reduce(g)) if self.world > 1 else None
         ar_async = None      # Engine.train_step(allreduce_async=...) overlaps the all-reduce; measured no gain at 2 GPUs
-        it = self.epoch * cfg.STEPS_PER_EPOCH
+        it = 0       # the reference creates a fresh CyclicLR per train() call: its iteration counter restarts (net.py:1126-1130)
         for epoch in range(self.epoch, epochs):
             t0 = time.time()
             inputs, _ = next(train_gen)
@@ -253,7 +256,8 @@ class UrsoNet:
                 history.ori_loss_acc.append(ori_l)
                 it += 1
             val = []
-            for _ in range(min(cfg.VALIDATION_STEPS, max(1, len(val_dataset.image_ids) // e.B)) if len(val_dataset.image_ids) else 0):
+            # fit_generator(validation_steps=VALIDATION_STEPS) on an infinite generator (net.py:1158-1159)
+            for _ in range(cfg.VALIDATION_STEPS if len(val_dataset.image_ids) else 0):
                 inputs, _ = next(val_gen)
                 if self._feed(inputs):       # same feed as training: the reference's val generator augments too
                     e.swap_in(self._aug)
