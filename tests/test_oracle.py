@@ -126,3 +126,63 @@ def test_clr_triangular():
     assert math.isclose(O.clr_triangular(4000, 1e-4, 5e-4, 4000), 5e-4)
     assert math.isclose(O.clr_triangular(6000, 1e-4, 5e-4, 4000), 3e-4)
     assert math.isclose(O.clr_triangular(8000, 1e-4, 5e-4, 4000), 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ oracle hedge
+# The network oracle is unpinned (no TF/Keras here).  oracle/direct_oracle.py is a second restatement written
+# independently (numpy, direct loops over output pixels, its own walk through net.py's builder functions); both must
+# agree on the same random weights.  A semantic slip (TF-SAME offsets, Keras-v1 stride placement, the one-BN shallow
+# block, ReLU'd logits, flatten order) would have to be made twice to survive.
+@pytest.mark.parametrize("backbone,classify", [("resnet18", True), ("resnet34", False), ("resnet50", True),
+                                               ("resnet101", False)])
+def test_two_independent_restatements_agree(backbone, classify):
+    import numpy as np
+    from oracle import direct_oracle as D2
+    cfg = small_cfg(backbone, classify)
+    cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM = 64, 128
+    cfg.update()
+    p = O.init_weights(cfg, seed=3, pretrained_like=True)
+    img, gt_loc, gt_ori = batch(cfg, B=2, seed=4)
+    with torch.no_grad():
+        loc, ori = O.forward(p, img, cfg)
+    loc2, ori2 = D2.forward({k: v.numpy() for k, v in p.items()}, img.numpy(), cfg)
+    assert np.abs(loc.numpy() - loc2).max() <= 1e-10 * max(1.0, np.abs(loc2).max())
+    assert np.abs(ori.numpy() - ori2).max() <= 1e-10 * max(1.0, np.abs(ori2).max())
+    # losses
+    if classify:
+        assert math.isclose(O.softmax_loss(gt_ori, ori).item(), D2.softmax_loss(gt_ori.numpy(), ori2), rel_tol=1e-10)
+    else:
+        assert math.isclose(O.one_minus_dot_prod(gt_ori, ori).item(), D2.one_minus_dot_prod(gt_ori.numpy(), ori2),
+                            rel_tol=1e-10, abs_tol=1e-12)
+    assert math.isclose(O.rel_loss(gt_loc, loc).item(), D2.rel_loss(gt_loc.numpy(), loc2), rel_tol=1e-10)
+
+
+def test_direct_oracle_primitives_against_hand_values():
+    import numpy as np
+    from oracle import direct_oracle as D2
+    x = np.arange(16, dtype=np.float64).reshape(1, 4, 4, 1)
+    assert D2.maxpool_3x3_s2_same_direct(x).reshape(-1).tolist() == [10.0, 11.0, 14.0, 15.0]
+    y = D2.conv_direct(x, np.ones((3, 3, 1, 1)), None, 2, "same")
+    assert y.reshape(-1).tolist() == [sum([0, 1, 2, 4, 5, 6, 8, 9, 10]), sum([2, 3, 6, 7, 10, 11]),
+                                      sum([8, 9, 10, 12, 13, 14]), sum([10, 11, 14, 15])]
+    assert D2.conv_direct(x, np.ones((1, 1, 1, 1)), None, 2, "valid").reshape(-1).tolist() == [0.0, 2.0, 8.0, 10.0]
+    # odd map: SAME pads symmetrically (1 before, 1 after for k=3, s=2, n=5)
+    assert D2.tf_same_pads(5, 3, 2) == (3, 1, 1) and D2.tf_same_pads(4, 3, 2) == (2, 0, 1)
+    assert D2.tf_same_pads(6, 3, 1) == (6, 1, 1) and D2.tf_same_pads(8, 7, 2) == (4, 2, 3)
+
+
+def test_fp32_oracle_gap_to_fp64_is_far_below_the_parity_gate():
+    """SURVEY 8c (last row): how far the SAME restatement run in fp32 (what TF-CPU computes in) sits from fp64 -- this
+    anchors the 1e-3 forward tolerance.  Measured here at 128x192 on RN-50: ~1e-6 relative."""
+    cfg = small_cfg("resnet50", True)
+    cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM = 128, 192
+    cfg.update()
+    p = O.init_weights(cfg, seed=5, pretrained_like=True)
+    img, _, _ = batch(cfg, B=1, seed=6)
+    with torch.no_grad():
+        loc64, ori64 = O.forward(p, img, cfg)
+        loc32, ori32 = O.forward({k: v.float() for k, v in p.items()}, img.float(), cfg)
+    e_loc = (loc32.double() - loc64).abs().max().item() / loc64.abs().max().item()
+    e_ori = (ori32.double() - ori64).abs().max().item() / ori64.abs().max().item()
+    print("fp32 vs fp64 oracle gap: loc %.2e ori %.2e" % (e_loc, e_ori))
+    assert e_loc < 1e-4 and e_ori < 1e-4
