@@ -26,6 +26,9 @@ int urso_num_sms(void);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);
+int urso_sizeof_conv2d_fwd_desc(void);
+int urso_sizeof_conv2d_dgrad_desc(void);
+int urso_sizeof_conv2d_wgrad_desc(void);
 
 /* A 4-D NHWC bf16 view (possibly strided): element (n,h,w,c) at base + n*stride_n + h*stride_h + w*stride_w + c.
  * C must be a multiple of 64 for MMA operands; strides are in ELEMENTS and must be multiples of 8. */
@@ -103,6 +106,103 @@ typedef struct urso_wgrad urso_wgrad_t;
 int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out);
 int urso_wgrad_launch(urso_wgrad_t* h, void* stream);
 void urso_wgrad_destroy(urso_wgrad_t* h);
+
+/* =====================================================================================================================
+ * Conv2D OPERATORS (the level a non-Python host binds): a Keras Conv2D (net.py:101-111,138-152,171,225-235,639), its
+ * input gradient and its weight gradient, described by tensor shapes, stride and explicit padding.  All planning --
+ * K-segments, tap shifts, stride-2 parity views, pixel-patch choice, N tile, weight-operand layout -- happens inside
+ * the library (csrc/conv_ops.cu); the Engine-F / Engine-W entry points above are what these operators are built from.
+ *
+ * Tensors: x bf16 NHWC dense [N,H,W,C]; w fp32 Keras HWIO master weights [k,k,C,K]; y / dy bf16 NHWC
+ * [N,OH,OW,ceil64(K)] (fp32 when out_fp32); OH = (H + pad_t + pad_b - k) / stride + 1.
+ * The frozen-BatchNorm scale[K] = gamma/sqrt(var+eps) is folded into the staged bf16 weight operand; shift[K] is added
+ * in the epilogue (urso_bn_fold produces both).  Each operator owns no device memory: the caller passes a workspace of
+ * *_workspace_bytes() bytes (staged operand + gather indices), which must stay valid while the handle lives.
+ * `*_stage_weights` re-stages the operand from the fp32 masters (call it after every weight update, any stream order
+ * before the launch); `*_launch` is graph-capturable and never synchronises.
+ * The 7x7/stride-2 stem (net.py:170-171,254-255) is the same operator with ksize = 7: x is then the staged tensor E of
+ * urso_stem_stage ([N, H/2+3, W/2, 64]) and H, W are the IMAGE dimensions. */
+typedef struct {
+  int32_t N, H, W, C; /* input activation */
+  int32_t K;          /* output channels */
+  int32_t ksize;      /* 1, 3 (or 7 for the stem) */
+  int32_t stride;     /* 1 or 2 */
+  int32_t pad_t, pad_l, pad_b, pad_r;
+} urso_conv2d_shape;
+
+/* TF 'SAME' padding of one dimension (out = ceil(n/s), total = max((out-1)*s + k - n, 0), before = total/2). */
+void urso_same_pad(int32_t n, int32_t k, int32_t s, int32_t* before, int32_t* after);
+
+typedef struct {
+  urso_conv2d_shape shape;
+  const void* x;
+  const float* w;      /* fp32 HWIO */
+  const float* scale;  /* fp32 [K] or NULL (= 1) */
+  const float* shift;  /* fp32 [K] or NULL */
+  const void* addend;  /* bf16 [N,OH,OW,K] residual input or NULL */
+  void* y;
+  int32_t relu;
+  int32_t out_fp32;
+  void* workspace;
+} urso_conv2d_fwd_desc;
+
+typedef struct urso_conv2d_fwd urso_conv2d_fwd_t;
+int64_t urso_conv2d_fwd_workspace_bytes(const urso_conv2d_shape* s);
+int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d_fwd_t** out);
+int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream);
+int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream);
+void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h);
+
+/* Input gradient with fused fan-in: dx = mask( sum_i dgrad_i(dy_i, w_i) + addend ), one launch per output phase
+ * (stride^2 phases), the convolutions' reduction ranges concatenated.  All consumers share x's shape and stride.
+ *   mask    bf16 [N,H,W,C]: the forward activation x (ReLU backward: dx = 0 where x <= 0) or NULL
+ *   addend  bf16 [N,H,W,C]: gradient arriving through an identity shortcut, or NULL
+ *   colsum  fp32 [C]: += per-channel sums of dx (d beta / d bias of the layer that produced x), or NULL
+ *   dy_sparse: every dy_i is non-zero on its even-even pixels only (it sits behind a 1x1/stride-2 convolution, the
+ *           Keras-v1 bottleneck block); stride-1 consumers then run at stride 2 on the decimated gradient grid.
+ * Phases that receive no filter tap (e.g. the odd pixels of a 1x1/stride-2 conv) are NOT written: dx must have been
+ * zero-filled once at allocation (urso_conv2d_dgrad_untouched_phases reports them as a bit mask, bit = oph*stride+opw). */
+#define URSO_MAX_FANIN 4
+typedef struct {
+  int32_t n_convs;
+  urso_conv2d_shape shape[URSO_MAX_FANIN];
+  const void* dy[URSO_MAX_FANIN];
+  const float* w[URSO_MAX_FANIN];
+  const float* scale[URSO_MAX_FANIN];
+  int32_t dy_sparse;
+  const void* mask;
+  const void* addend;
+  void* dx;
+  float* colsum;
+  void* workspace;
+} urso_conv2d_dgrad_desc;
+
+typedef struct urso_conv2d_dgrad urso_conv2d_dgrad_t;
+int64_t urso_conv2d_dgrad_workspace_bytes(const urso_conv2d_dgrad_desc* d);
+int urso_conv2d_dgrad_create(const urso_conv2d_dgrad_desc* d, urso_conv2d_dgrad_t** out);
+int urso_conv2d_dgrad_stage_weights(urso_conv2d_dgrad_t* h, void* stream);
+int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream);
+int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h);
+int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h);
+void urso_conv2d_dgrad_destroy(urso_conv2d_dgrad_t* h);
+
+/* Raw weight gradient G[k*k*C, K] (fp32, HWIO order, accumulated with atomics: the caller zeroes it) of the UNSCALED
+ * convolution; urso_conv_param_grads turns it into dW / dbias / dgamma / dbeta.  Stem (ksize 7): G is [4*64, K] in the
+ * staged K order (urso_conv_param_grads takes the row map). */
+typedef struct {
+  urso_conv2d_shape shape;
+  const void* x;
+  const void* dy;
+  int32_t dy_sparse;
+  float* G;
+} urso_conv2d_wgrad_desc;
+
+typedef struct urso_conv2d_wgrad urso_conv2d_wgrad_t;
+int urso_conv2d_wgrad_create(const urso_conv2d_wgrad_desc* d, urso_conv2d_wgrad_t** out);
+int urso_conv2d_wgrad_launch(urso_conv2d_wgrad_t* h, void* stream);
+void urso_conv2d_wgrad_destroy(urso_conv2d_wgrad_t* h);
+/* HWIO row (r*7+s)*3+c -> row of the staged stem gradient G[4*64, K]; fills map[147]. */
+void urso_stem_grad_row_map(int32_t* map147);
 
 /* ---- Stem input staging (replaces mold_image net.py:1337-1348 + ZeroPadding2D(3) net.py:170,254 + the im2col TF does
  * internally): uint8 or fp32 RGB [B,H,W,3] -> bf16 E[B, H/2+3, W/2, 64], E[b,h2,wo,(s2,ph,pw,c)] =

@@ -1,0 +1,213 @@
+"""GPU parity of the Conv2D OPERATORS of the C-ABI (urso_conv2d_{fwd,dgrad,wgrad}_*: include/urso_b200.h): the level a
+non-Python host binds.  Each case passes only shapes, stride, padding and device pointers through ctypes -- all
+planning (segments, parity views, tiles, operand layout) happens in csrc/conv_ops.cu -- and is compared with the fp64
+oracle convolution / its autograd on bf16-exact inputs.  Tolerance: fp32 accumulation order + bf16 rounding of the
+folded weights (exact in the reference here, see `staged`) and of the stored output (2^-8 relative)."""
+import pytest
+import torch
+
+from oracle import ursonet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16_exact(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(torch.float64)
+
+
+def staged(wk, scale):
+    """the bf16-rounded, scale-folded kernel the engine multiplies with"""
+    return (wk * scale).to(torch.bfloat16).to(torch.float64)
+
+
+def relerr(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+CASES = [  # k, stride, padding, cin, cout, h, w
+    (1, 1, "valid", 64, 64, 16, 24),
+    (1, 1, "valid", 256, 128, 12, 20),
+    (1, 1, "valid", 64, 256, 16, 24),
+    (1, 2, "valid", 128, 64, 16, 24),        # Keras-v1 block: stride on the 1x1 (net.py:138,152)
+    (3, 1, "same", 64, 64, 16, 24),
+    (3, 1, "same", 128, 128, 20, 30),
+    (3, 2, "same", 128, 32, 20, 30),         # bottleneck_layer: TF SAME on an even map pads bottom/right only (net.py:639)
+    (3, 2, 1, 64, 128, 16, 24),              # shallow block: ZeroPadding2D(1) + VALID stride 2 (net.py:225-226)
+    (3, 1, 1, 64, 64, 10, 14),               # shallow block conv2
+]
+
+
+@pytest.mark.parametrize("k,stride,padding,cin,cout,h,w", CASES)
+def test_conv2d_fwd_operator(k, stride, padding, cin, cout, h, w):
+    from ursonet_b200 import lib
+    N = 2
+    x = bf16_exact(N, h, w, cin, seed=1)
+    wk = bf16_exact(k, k, cin, cout, scale=0.05, seed=2)
+    scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+    shift = torch.randn(cout, dtype=torch.float64)
+    shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)
+    oh, ow = lib.out_hw(shape)
+    out_fp32 = cout % 64 != 0
+    addend = bf16_exact(N, oh, ow, cout, seed=3) if (k == 1 and not out_fp32) else None
+    relu = k != 3 or stride == 1
+    xd = x.to(torch.bfloat16).to(DEV)
+    wd, sd, hd = wk.float().to(DEV), scale.float().to(DEV), shift.float().to(DEV)
+    ad = addend.to(torch.bfloat16).to(DEV) if addend is not None else None
+    y = torch.full((N, oh, ow, cout), float("nan"), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=DEV)
+    op = lib.Conv2dFwd(shape, xd, wd, sd, hd, y, addend=ad, relu=relu and not out_fp32)
+    op.stage()
+    op.launch()
+    torch.cuda.synchronize()
+    ref = O.conv2d(x, staged(wk, scale.float().double()), None, stride, padding) + shift.float().double()
+    assert tuple(ref.shape) == (N, oh, ow, cout)
+    if addend is not None:
+        ref = ref + addend
+    if relu and not out_fp32:
+        ref = torch.relu(ref)
+    assert relerr(y.double().cpu(), ref) <= (1e-5 if out_fp32 else 6e-3)
+
+
+def test_conv2d_fwd_stem_operator():
+    """ksize 7: the stem over the staged tensor E of urso_stem_stage (net.py:170-171: ZeroPadding2D(3) + 7x7/s2 VALID)."""
+    from ursonet_b200 import lib
+    N, H, W = 2, 32, 48
+    g = torch.Generator().manual_seed(4)
+    img = torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(O.MEAN_PIXEL, dtype=torch.float32)
+    wk = bf16_exact(7, 7, 3, 64, scale=0.05, seed=5)
+    scale = 0.5 + torch.rand(64, dtype=torch.float64)
+    shift = torch.randn(64, dtype=torch.float64)
+    E = torch.zeros(N, H // 2 + 3, W // 2, 64, dtype=torch.bfloat16, device=DEV)
+    imgd = img.to(DEV)
+    lib.call("urso_stem_stage", imgd.data_ptr(), 1, 1, mean.to(DEV).data_ptr(), E.data_ptr(), N, H, W, 0, lib.stream_ptr())
+    shape = lib.conv_shape(N, H, W, 3, 64, 7, 2, 3)
+    y = torch.zeros(N, H // 2, W // 2, 64, dtype=torch.bfloat16, device=DEV)
+    op = lib.Conv2dFwd(shape, E, wk.float().to(DEV), scale.float().to(DEV), shift.float().to(DEV), y, relu=True)
+    op.stage()
+    op.launch()
+    torch.cuda.synchronize()
+    x = (img.double() - mean.double()).to(torch.bfloat16).double()
+    ref = torch.relu(O.conv2d(x, staged(wk, scale.float().double()), None, 2, 3) + shift.float().double())
+    assert relerr(y.double().cpu(), ref) <= 6e-3
+    # weight gradient of the stem through the operator + the row map
+    dy = bf16_exact(N, H // 2, W // 2, 64, seed=6)
+    G = torch.zeros(4 * 64, 64, dtype=torch.float32, device=DEV)
+    wg = lib.Conv2dWgrad(shape, E, dy.to(torch.bfloat16).to(DEV), G)
+    wg.launch()
+    torch.cuda.synchronize()
+    wr = wk.clone().requires_grad_(True)
+    (gref,) = torch.autograd.grad(O.conv2d(x, wr, None, 2, 3), wr, dy)
+    got = G.double().cpu()[torch.tensor(lib.stem_grad_row_map())].reshape(7, 7, 3, 64)
+    assert relerr(got, gref) <= 2e-3
+
+
+DGRAD_CASES = [  # list of consumers (k, stride, padding, cout), cin, h, w, sparse, mask, addend
+    ([(1, 1, "valid", 64)], 256, 16, 24, False, True, True),             # identity block 2a + shortcut fan-in
+    ([(3, 1, "same", 64)], 64, 16, 24, False, True, False),
+    ([(1, 2, "valid", 128), (1, 2, "valid", 512)], 256, 16, 24, False, True, False),   # conv block: 2a + shortcut, stride 2
+    ([(3, 2, "same", 32)], 128, 20, 30, False, True, False),             # bottleneck conv
+    ([(3, 2, 1, 128), (1, 2, "valid", 128)], 64, 16, 24, False, True, False),          # shallow block: conv1 + 'post' shortcut
+    ([(1, 1, "valid", 256)], 64, 16, 24, True, True, False),             # sparse gradient behind a 1x1/s2
+    ([(3, 1, "same", 64)], 64, 16, 24, True, True, False),               # sparse gradient through a 3x3
+    ([(1, 1, "valid", 64), (1, 1, "valid", 256)], 64, 12, 20, False, False, False),    # stage-2 conv block on pool1
+]
+
+
+@pytest.mark.parametrize("consumers,cin,h,w,sparse,use_mask,use_addend", DGRAD_CASES)
+def test_conv2d_dgrad_operator(consumers, cin, h, w, sparse, use_mask, use_addend):
+    from ursonet_b200 import lib
+    N = 2
+    shapes, dys, ws, scs, ref_terms = [], [], [], [], []
+    x = bf16_exact(N, h, w, cin, seed=10)
+    xr = x.clone().requires_grad_(True)
+    total = torch.zeros_like(x)
+    for i, (k, stride, padding, cout) in enumerate(consumers):
+        shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)
+        oh, ow = lib.out_hw(shape)
+        wk = bf16_exact(k, k, cin, cout, scale=0.05, seed=20 + i)
+        scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+        dy = bf16_exact(N, oh, ow, cout, seed=30 + i)
+        if sparse:
+            keep = torch.zeros(1, oh, ow, 1, dtype=torch.float64)
+            keep[:, ::2, ::2, :] = 1
+            dy = dy * keep
+        y = O.conv2d(xr, staged(wk, scale.float().double()), None, stride, padding)
+        total = total + torch.autograd.grad(y, xr, dy)[0]
+        cp = (cout + 63) // 64 * 64
+        dyp = torch.zeros(N, oh, ow, cp, dtype=torch.bfloat16)
+        dyp[..., :cout] = dy.to(torch.bfloat16)
+        shapes.append(shape)
+        dys.append(dyp.to(DEV))
+        ws.append(wk.float().to(DEV))
+        scs.append(scale.float().to(DEV))
+    mask = bf16_exact(N, h, w, cin, seed=40) if use_mask else None
+    addend = bf16_exact(N, h, w, cin, seed=41) if use_addend else None
+    if addend is not None:
+        total = total + addend
+    if mask is not None:
+        total = total * (mask > 0)
+    dx = torch.zeros(N, h, w, cin, dtype=torch.bfloat16, device=DEV)       # zero-filled once (untouched phases)
+    cs = torch.zeros(cin, dtype=torch.float32, device=DEV)
+    op = lib.Conv2dDgrad(shapes, dys, ws, scs, dx, mask=mask.to(torch.bfloat16).to(DEV) if use_mask else None,
+                         addend=addend.to(torch.bfloat16).to(DEV) if use_addend else None, colsum=cs, dy_sparse=sparse)
+    op.stage()
+    op.launch()
+    torch.cuda.synchronize()
+    got = dx.double().cpu()
+    assert relerr(got, total) <= 6e-3, (op.n_launches, op.untouched)
+    assert torch.allclose(cs.double().cpu(), got.sum((0, 1, 2)), rtol=1e-3, atol=1e-2 * got.abs().max().item())
+    eff_stride = consumers[0][1] * (2 if sparse else 1)
+    if eff_stride == 2 and all(c[0] == 1 for c in consumers):
+        assert op.untouched == 0b1110 and op.n_launches == 1
+    else:
+        assert op.untouched == 0 and op.n_launches == eff_stride ** 2
+
+
+WGRAD_CASES = [  # k, stride, padding, cin, cout, h, w, sparse
+    (1, 1, "valid", 64, 256, 16, 24, False),      # swapped roles (wide side on M)
+    (1, 1, "valid", 256, 64, 16, 24, False),
+    (1, 2, "valid", 128, 64, 16, 24, False),
+    (3, 1, "same", 64, 64, 16, 24, False),        # tap pairing
+    (3, 1, "same", 128, 128, 12, 20, False),
+    (3, 2, "same", 128, 32, 20, 30, False),
+    (3, 2, 1, 64, 128, 16, 24, False),
+    (1, 1, "valid", 64, 256, 16, 24, True),
+    (3, 1, "same", 64, 64, 16, 24, True),
+]
+
+
+@pytest.mark.parametrize("k,stride,padding,cin,cout,h,w,sparse", WGRAD_CASES)
+def test_conv2d_wgrad_operator(k, stride, padding, cin, cout, h, w, sparse):
+    from ursonet_b200 import lib
+    N = 2
+    shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)
+    oh, ow = lib.out_hw(shape)
+    x = bf16_exact(N, h, w, cin, seed=50)
+    dy = bf16_exact(N, oh, ow, cout, seed=51)
+    if sparse:
+        keep = torch.zeros(1, oh, ow, 1, dtype=torch.float64)
+        keep[:, ::2, ::2, :] = 1
+        dy = dy * keep
+    wr = torch.zeros(k, k, cin, cout, dtype=torch.float64, requires_grad=True)
+    (gref,) = torch.autograd.grad(O.conv2d(x, wr, None, stride, padding), wr, dy)
+    cp = (cout + 63) // 64 * 64
+    dyp = torch.zeros(N, oh, ow, cp, dtype=torch.bfloat16)
+    dyp[..., :cout] = dy.to(torch.bfloat16)
+    G = torch.zeros(k * k * cin, cout, dtype=torch.float32, device=DEV)
+    op = lib.Conv2dWgrad(shape, x.to(torch.bfloat16).to(DEV), dyp.to(DEV), G, dy_sparse=sparse)
+    op.launch()
+    torch.cuda.synchronize()
+    assert relerr(G.double().cpu().reshape(k, k, cin, cout), gref) <= 2e-3
+
+
+def test_operator_errors_are_reported():
+    from ursonet_b200 import lib
+    shape = lib.conv_shape(1, 16, 16, 48, 64, 3, 1, "same")         # 48 input channels: not a multiple of 64
+    x = torch.zeros(1, 16, 16, 48, dtype=torch.bfloat16, device=DEV)
+    y = torch.zeros(1, 16, 16, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(3, 3, 48, 64, device=DEV)
+    with pytest.raises(lib.UrsoError):
+        lib.Conv2dFwd(shape, x, w, None, None, y)
+    assert b"multiple of 64" in lib.load().urso_last_error()

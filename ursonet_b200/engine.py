@@ -143,7 +143,7 @@ class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
-                 parity=None, n_slices=None):
+                 parity=None):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -152,24 +152,17 @@ class Engine:
         if self.parity and training:
             raise NotImplementedError("PARITY_MODE (split-bf16 operands) is forward-only")
         self.graph: Graph = build_graph(cfg)
-        # Batch slices: the conv stack of every slice is an independent chain of launches issued on its own CUDA stream
-        # (lane), so the tail wave of one persistent kernel overlaps the head of another, and the small per-layer
-        # kernels (weight staging, parameter gradients: the "aux" lane) hide behind the convolutions.
-        # Lanes: 0 .. n_slices-1 = the slices' conv chains; optionally one more lane per slice for its weight-gradient
-        # launches (wgrad of a layer and the dgrad chain below it are independent); the last lane = "aux".
-        # URSO_LANES=0 puts everything on one stream.
-        if n_slices is None:
-            n_slices = int(os.environ.get("URSO_SLICES", "1"))
-        self.n_slices = 1 if self.parity else max(1, min(int(n_slices), self.B))
-        self.slices = [(self.B * i // self.n_slices, self.B * (i + 1) // self.n_slices) for i in range(self.n_slices)]
+        # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
+        # chain); the weight-gradient launches run on their own lane(s) (wgrad of a layer only needs the du its dgrad
+        # predecessor produced, so it overlaps the dgrad chain below it and fills its tail waves); the small per-layer
+        # kernels (BN fold, weight staging, parameter gradients) run on the last, "aux" lane.  URSO_LANES=0 puts
+        # everything on one stream.  (Batch slices -- independent half-batch chains -- were measured slower in round 1:
+        # smaller kernels lose more to wave quantisation than the overlap returns; removed.)
         multi = (not self.parity) and int(os.environ.get("URSO_LANES", "1")) != 0
-        # URSO_WLANE = number of wgrad lanes per slice (0: wgrad stays in the slice's chain).  With 2, consecutive wgrad
-        # launches (independent of each other) alternate lanes, so the atomic-reduction tail of one overlaps the next.
+        # URSO_WLANE = number of wgrad lanes (0: wgrad stays in the main chain)
         self.wgrad_lanes = int(os.environ.get("URSO_WLANE", "1")) if (multi and training) else 0
-        self.aux_lane = (self.n_slices * (1 + self.wgrad_lanes)) if multi else 0
+        self.aux_lane = (1 + self.wgrad_lanes) if multi else 0
         self._wgrad_rr = 0
-        if not multi:
-            self.n_slices, self.slices = 1, [(0, self.B)]
         self._lane_streams = None
         self.sparse_bwd = training and int(os.environ.get("URSO_SPARSE_BWD", "1")) != 0
         self.sparse = set()      # buffers whose gradient lives on the even-even pixels only
@@ -247,16 +240,6 @@ class Engine:
             fn()
 
     # ------------------------------------------------------------------ plan helpers
-    @staticmethod
-    def _use_halo(k, stride, oh, ow, kc, n):
-        """Halo mode of Engine F (one TMA box per channel chunk shared by all 3x3 taps): needs an 8 x 16 pixel patch that
-        tiles the map without waste.  kc = reduction channels per tap, n = output channels."""
-        import os
-        mode = int(os.environ.get("URSO_HALO", "0"))
-        if not mode or k != 3 or stride != 1 or oh % 16 or ow % 8 or kc % 64:
-            return False
-        return n <= 64 if mode == 1 else True
-
     def _idx(self, values):
         t = torch.tensor(list(values), dtype=torch.int32, device=self.device)
         self._keep.append(t)
@@ -278,13 +261,22 @@ class Engine:
         self._last[op.lane] = op
         return op
 
+    def _conv_shape(self, c: ConvSpec):
+        """urso_conv2d_shape of a graph conv (the stem is the ksize-7 operator over the staged tensor E)."""
+        if c.stem:
+            return lib.conv_shape(self.B, self.H, self.W, 3, c.cout, 7, 2, 3)
+        h, w, _ = self.graph.shapes[c.src]
+        return lib.conv_shape(self.B, h, w, c.cin, c.cout, c.k, c.stride, c.padding)
+
     def _build_forward(self):
+        """Forward launch list.  Every convolution is ONE C-ABI operator (urso_conv2d_fwd_*): the library plans the
+        K-segments / parity views / tiles and owns the weight-operand layout; Python only wires tensors."""
         g, B = self.graph, self.B
         S = lib.stream_ptr
         self.ops_stage, self.ops_fwd, self.ops_loss = [], [], []
         self._late_binds = []
         self._last = {}
-        self.Bf: Dict[str, torch.Tensor] = {}
+        self.fwd_ops: Dict[str, lib.Conv2dFwd] = {}
         aux = self.aux_lane
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
@@ -292,64 +284,36 @@ class Engine:
             self._add(self.ops_stage, OpRec(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
                 "urso_bn_fold", lib.ptr(bn[0]), lib.ptr(bn[1]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
                 sc.data_ptr(), sh.data_ptr(), c.cout, S()), "stage", c.name, lane=aux))
-            if c.stem:
-                segs, idx = P.stem_segments(), P.stem_weight_index(3)
-            else:
-                h, w_, _ = g.shapes[c.src]
-                geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w_)
-                segs, idx = P.fwd_segments(geom)
-            K = len(idx)
-            bmat = self._new((c.cout, K))
-            self.Bf[c.name] = bmat
-            idx_d = self._idx(idx)
-            staged = self._add(self.ops_stage, OpRec(lambda w=w, sc=sc, bmat=bmat, idx_d=idx_d, K=K, c=c: lib.call(
-                "urso_stage_weight_rows", w.data_ptr(), sc.data_ptr(), bmat.data_ptr(), idx_d.data_ptr(), K, c.cout,
-                c.cout, K, 0, S()), "stage", c.name, lane=aux))
-            oh, ow = g.shapes[c.dst][0], g.shapes[c.dst][1]
+            shape = self._conv_shape(c)
+            oh, ow = lib.out_hw(shape)
+            assert (oh, ow) == tuple(g.shapes[c.dst][:2]), (c.name, oh, ow, g.shapes[c.dst])
+            x = self.E if c.stem else self.act[c.src]
+            out = self.act[c.dst]
+            addend = self.act[c.addend] if c.addend else None
+            op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu)
+            self.fwd_ops[c.name] = op
+            staged = self._add(self.ops_stage, OpRec(op.stage, "stage", c.name, lane=aux))
             if c.stem:
                 ph, pw, _ = g.shapes[c.dst]
                 self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
-            for si, (b0, b1) in enumerate(self.slices):
-                nb_ = b1 - b0
-                out = self.act[c.dst][b0:b1]
-                addend = self.act[c.addend][b0:b1] if c.addend else None
-                if c.stem:
-                    tw, th = P.pick_patch(oh, ow, 128)
-                    plan = lib.ConvGemm([self.E[b0:b1]], bmat, segs, out, ow, oh, nb_, tw, th, shift=sh, relu=c.relu)
-                elif c.k == 1 and c.stride == 1:
-                    M = nb_ * oh * ow
-                    x = self.act[c.src][b0:b1].view(1, 1, M, c.cin)
-                    plan = lib.ConvGemm([x], bmat, segs, out.view(1, 1, M, c.cout), M, 1, 1, 128, 1, shift=sh,
-                                        addend=addend.view(1, 1, M, c.cout) if addend is not None else None, relu=c.relu)
-                else:
-                    tw, th = P.pick_patch(oh, ow, 128)
-                    halo = self._use_halo(c.k, c.stride, oh, ow, c.cin, c.cout)
-                    if halo:
-                        tw, th = 8, 16
-                    plan = lib.ConvGemm(P.input_views(self.act[c.src][b0:b1], c.stride), bmat, segs, out, ow, oh, nb_, tw,
-                                        th, shift=sh, addend=addend, relu=c.relu, halo=halo)
-                self._keep.append(plan)
-                fl = 2.0 * nb_ * oh * ow * c.cout * c.k * c.k * c.cin
-                nb = 2.0 * nb_ * (g.shapes[c.src][0] * g.shapes[c.src][1] * c.cin if not c.stem else self.E[0].numel()) \
-                    + (4.0 if c.out_fp32 else 2.0) * nb_ * oh * ow * c.cout * (2 if c.addend else 1) + 2.0 * bmat.numel()
-                self._add(self.ops_fwd, OpRec(plan.launch, "conv_fwd", c.name, fl, nb, lane=si, after=[staged]))
-                if c.stem:
-                    src, dst = self.act[c.dst][b0:b1], self.act["pool1"][b0:b1]
-                    amax = self.argmax[b0:b1] if self.argmax is not None else None
-                    self._add(self.ops_fwd, OpRec(lambda src=src, dst=dst, amax=amax, ph=ph, pw=pw, nb_=nb_: lib.call(
-                        "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(amax), nb_, ph, pw, 64, S()),
-                        "pool_fwd", "pool1", 0.0, 2.0 * nb_ * ph * pw * 64 * 1.25, lane=si))
+            fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
+            # algorithmic bytes: a strided 1x1 conv only touches the pixels it samples
+            in_elems = self.E[0].numel() if c.stem else \
+                g.shapes[c.src][0] * g.shapes[c.src][1] * c.cin // (c.stride * c.stride if c.k == 1 else 1)
+            nb = 2.0 * B * in_elems + (4.0 if c.out_fp32 else 2.0) * B * oh * ow * c.cout * (2 if c.addend else 1) \
+                + 2.0 * c.cout * c.k * c.k * c.cin
+            self._add(self.ops_fwd, OpRec(op.launch, "conv_fwd", c.name, fl, nb, after=[staged]))
+            if c.stem:
+                src, dst, amax = self.act[c.dst], self.act["pool1"], self.argmax
+                self._add(self.ops_fwd, OpRec(lambda src=src, dst=dst, amax=amax, ph=ph, pw=pw: lib.call(
+                    "urso_maxpool_fwd", src.data_ptr(), dst.data_ptr(), lib.ptr(amax), B, ph, pw, 64, S()),
+                    "pool_fwd", "pool1", 0.0, 2.0 * B * ph * pw * 64 * 1.25))
         self._build_heads_forward()
-
-    def _join_deps(self):
-        """Ops a lane-0 op must wait for so that every slice lane has finished what it was given so far."""
-        return [self._last.get(ln) for ln in range(1, self.n_slices)]
 
     def _build_heads_forward(self):
         g, B = self.graph, self.B
         S = lib.stream_ptr
         # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332); whole batch, lane 0
-        join = self._join_deps()
         for d in g.dense:
             w, b = self.params.view(d.name + "/kernel"), self.params.view(d.name + "/bias")
 
@@ -362,9 +326,7 @@ class Engine:
                 y = self.head[d.name]
                 lib.call("urso_dense_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), self.B, d.cin, d.cout, S())
                 lib.call("urso_dense_bias_act", y.data_ptr(), b.data_ptr(), self.B, d.cout, d.act, S())
-            self._add(self.ops_fwd, OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2,
-                                          after=join))
-            join = []
+            self._add(self.ops_fwd, OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
         if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
             self._add(self.ops_fwd, OpRec(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
                                                            self.ori_q.data_ptr(), None, None, self.B, 1.0, S()),
@@ -509,7 +471,7 @@ class Engine:
         # process buffers in reverse production order
         order = [c.dst for c in g.convs]
         order.insert(1, "pool1")
-        self.Bd = {}
+        self.dgrad_ops = {}
         self._bwd_root = None
         self._bwd_split = None
         for X in reversed(order):
@@ -521,17 +483,15 @@ class Engine:
                     "urso_colsum_bf16", self.dact["bottleneck_layer"].data_ptr(), self._zero_view(key).data_ptr(),
                     B * h6 * w6, P.ceil64(bw), S()), "misc", "colsum_bottleneck"))
                 self.colsum[X] = key
-                self._bwd_started = set()
             elif X == g.pool_src:     # stem output: gradient arrives through the max-pool
                 h, w, c = g.shapes[X]
                 self.dact[X] = self._new((B, h, w, c))
                 key = colsum_for(X)
-                for si, (b0, b1) in enumerate(self.slices):
-                    am, dp, dx = self.argmax[b0:b1], self.dact["pool1"][b0:b1], self.dact[X][b0:b1]
-                    self._add(self.ops_bwd, OpRec(lambda am=am, dp=dp, dx=dx, h=h, w=w, c=c, key=key, n=b1 - b0: lib.call(
-                        "urso_maxpool_bwd", None, am.data_ptr(), dp.data_ptr(), dx.data_ptr(),
-                        self._zero_view(key).data_ptr(), n, h, w, c, S()),
-                        "pool_bwd", X, 0.0, 2.0 * (b1 - b0) * h * w * c * 1.4, 1, lane=si, after=self._bwd_deps(si)))
+                am, dp, dx = self.argmax, self.dact["pool1"], self.dact[X]
+                self._add(self.ops_bwd, OpRec(lambda am=am, dp=dp, dx=dx, h=h, w=w, c=c, key=key: lib.call(
+                    "urso_maxpool_bwd", None, am.data_ptr(), dp.data_ptr(), dx.data_ptr(),
+                    self._zero_view(key).data_ptr(), B, h, w, c, S()),
+                    "pool_bwd", X, 0.0, 2.0 * B * h * w * c * 1.4, 1))
                 self.colsum[X] = key
             else:
                 convs = cons_conv.get(X, [])
@@ -557,186 +517,103 @@ class Engine:
             for op in self.ops_bwd[self._bwd_split[0]:]:
                 op.segment = 1
 
-    @staticmethod
-    def _bwd_geom(c, h, w, sparse_dst):
-        """Geometry of conv c for its gradient launches; with a sparse (even-even only) output gradient it acts as the
-        same filter at twice the stride on the decimated output grid."""
-        gm = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w)
-        return P.decimated_geom(gm) if sparse_dst else gm
-
-    def _bwd_deps(self, lane):
-        """Cross-lane dependency of the FIRST backward op of a slice lane: the whole-batch head backward (lane 0).
-        Later ops of the lane are ordered behind it by the stream."""
-        if lane in self._bwd_started:
-            return []
-        self._bwd_started.add(lane)
-        return [self._bwd_root]
-
     def _build_dgrad_group(self, X, convs, adds, colsum_for, need_cs):
-        """du_X = mask_X( sum_convs dgrad(du_conv.dst, W_conv) + sum_adds du_add.dst ), one Engine-F launch per
-        output phase (and batch slice) with the convolutions' K ranges concatenated (fused gradient fan-in)."""
+        """du_X = mask_X( sum_convs dgrad(du_conv.dst, W_conv) + sum_adds du_add.dst ): ONE C-ABI operator
+        (urso_conv2d_dgrad_*; one Engine-F launch per output phase with the consumers' K ranges concatenated)."""
         g, B = self.graph, self.B
-        S = lib.stream_ptr
         h, w, cin = g.shapes[X]
         assert len(adds) <= 1 and convs, (X, len(adds), len(convs))
         # Structural sparsity: a buffer consumed only by 1x1/stride-2 convolutions (the Keras-v1 block puts the stride on
         # the first 1x1, net.py:138,152) has a gradient that is non-zero on the even-even pixels only, and so has
-        # everything it feeds through 1x1 convolutions.  For such a consumer the gradient launches treat the conv as a
-        # stride-2 conv on the decimated gradient grid: 4x less work for a 1x1 (and X is sparse again), 9 -> 2.25 taps
-        # on average for a 3x3.  The never-written odd phases stay zero from allocation (torch.zeros), so any launch
-        # that reads such a buffer densely (e.g. as the gradient fan-in addend) is still exact.
+        # everything it feeds through 1x1 convolutions.  For such a consumer the gradient operators run the conv as a
+        # stride-2 conv on the decimated gradient grid (dy_sparse): 4x less work for a 1x1 (and X is sparse again),
+        # 9 -> 2.25 taps on average for a 3x3.  The never-written odd phases stay zero from allocation (torch.zeros), so
+        # any launch that reads such a buffer densely (e.g. as the gradient fan-in addend) is still exact.
         sparse_in = self.sparse_bwd and all(c.dst in self.sparse and c.stride == 1 for c in convs)
         stride = convs[0].stride * (2 if sparse_in else 1)
         assert all(c.stride == convs[0].stride for c in convs)
         assert not (adds and convs[0].stride != 1)
-        self.dact[X] = self._new((B, h, w, cin))
+        dX = self.dact[X] = self._new((B, h, w, cin))
         key = colsum_for(X) if need_cs else None
         self.colsum[X] = key
         # pool1 = max of post-ReLU values: masking its gradient by (pool1 > 0) IS the stem's ReLU mask (a window's max
         # is 0 only when all its inputs are 0), so the max-pool backward does not have to read the stem output
-        mask_all = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
-        geoms = [self._bwd_geom(c, h, w, sparse_in) for c in convs]
-        phases = [P.dgrad_phases(gm) for gm in geoms]
-        need_zero = False
-        flat_ok = stride == 1 and all(c.k == 1 for c in convs)
-        staged = []      # (phase index, segs, bmat)
-        stage_op = None  # last weight-staging op of this group (aux lane, in order: waiting for it covers them all)
-        for pi in range(stride * stride):
-            segs, parts, ktot = [], [], 0
-            for ci, c in enumerate(convs):
-                _, _, sg, tap_map = phases[ci][pi]
-                if not sg:
-                    continue
-                cop = P.ceil64(c.cout)
-                segs += [(ci, dh, dw, ch) for (_m, dh, dw, ch) in sg]
-                parts.append((c, tap_map, ktot, cop))
-                ktot += len(tap_map) * cop
-            if not segs:
-                need_zero = True
-                continue
-            bmat = self._new((cin, ktot))
-            self.Bd[(X, pi)] = bmat
-            for c, tap_map, koff, cop in parts:
-                wk = self.params.view(c.name + "/kernel")
-                sc = self.scale[c.name]
-                tap_d = self._idx(tap_map)
-                dst = bmat[:, koff:]
-                stage_op = self._add(self.ops_stage, OpRec(
-                    lambda wk=wk, sc=sc, dst=dst, tap_d=tap_d, n=len(tap_map), c=c, cop=cop, ktot=ktot:
-                    lib.call("urso_stage_weight_cols", wk.data_ptr(), sc.data_ptr(), dst.data_ptr(), tap_d.data_ptr(), n,
-                             c.cin, c.cout, cop, c.cin, ktot, S()), "stage", c.name, lane=self.aux_lane))
-            staged.append((pi, segs, bmat))
-        for si, (b0, b1) in enumerate(self.slices):
-            nb_ = b1 - b0
-            dX = self.dact[X][b0:b1]
-            mask = mask_all[b0:b1] if mask_all is not None else None
-            addend = self.dact[adds[0].dst][b0:b1] if adds else None
-            if need_zero and not self.sparse_bwd:
-                self._add(self.ops_bwd, OpRec(lambda dX=dX: dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(), lane=si,
-                                              after=self._bwd_deps(si)))
-            for pi, segs, bmat in staged:
-                oph, opw = phases[0][pi][0], phases[0][pi][1]
-                a_views = [self.dact[c.dst][b0:b1] for c in convs]
-                if sparse_in:
-                    a_views = [v[:, ::2, ::2, :] for v in a_views]
-                tgt = dX[:, oph::stride, opw::stride, :]
-                m_v = mask[:, oph::stride, opw::stride, :] if mask is not None else None
-                if flat_ok:
-                    M = nb_ * h * w
-                    L = dict(a=[v.view(1, 1, M, v.shape[3]) for v in a_views], b=bmat, segs=segs,
-                             out=dX.view(1, 1, M, cin), OW=M, OH=1, NB=1, TW=128, TH=1,
-                             addend=addend.view(1, 1, M, cin) if addend is not None else None,
-                             mask=mask.view(1, 1, M, cin) if mask is not None else None, cs=key)
-                else:
-                    th_, tw_ = tgt.shape[1], tgt.shape[2]
-                    tw, th = P.pick_patch(th_, tw_, 128)
-                    halo = len(convs) == 1 and self._use_halo(convs[0].k, stride, th_, tw_, convs[0].cout, cin)
-                    if halo:
-                        tw, th = 8, 16
-                    L = dict(a=a_views, b=bmat, segs=segs, out=tgt, OW=tw_, OH=th_, NB=nb_, TW=tw, TH=th,
-                             addend=addend, mask=m_v, cs=key, halo=halo)
+        mask = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
+        addend = self.dact[adds[0].dst] if adds else None
+        shapes = [self._conv_shape(c) for c in convs]
+        dys = [self.dact[c.dst] for c in convs]
+        ws = [self.params.view(c.name + "/kernel") for c in convs]
+        scs = [self.scale[c.name] for c in convs]
+        box = {}
+        # a 1x1 consumer at (effective) stride 2 only reaches the even-even phase of dX
+        only_phase0 = stride == 2 and all(c.k == 1 for c in convs)
+        fl = touched = a_elems = 0.0
+        for c, sh_ in zip(convs, shapes):
+            oh, ow = lib.out_hw(sh_)
+            if sparse_in:
+                oh, ow = (oh + 1) // 2, (ow + 1) // 2
+            fl += 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin      # executed work (decimated grid when sparse)
+            a_elems += B * oh * ow * P.ceil64(c.cout)
+        touched = dX.numel() / (4 if only_phase0 else 1)
+        nbytes = 2.0 * (a_elems + touched * (1 + (mask is not None) + (addend is not None))
+                        + sum(c.cout * c.k * c.k * c.cin for c in convs))
+        stage_op = self._add(self.ops_stage, OpRec(lambda: box["p"].stage(), "stage", "d:" + X, lane=self.aux_lane))
+        if stride == 2 and not self.sparse_bwd:      # phases no filter tap reaches must read as zero
+            self._add(self.ops_bwd, OpRec(lambda: box["p"].untouched and dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(),
+                                          after=self._bwd_deps()))
+        op = self._add(self.ops_bwd, OpRec(lambda: box["p"].launch(), "conv_dgrad", X, fl, nbytes,
+                                           after=self._bwd_deps() + [stage_op]))
 
-                def make(L=L):
-                    plan_box = {}
-
-                    def bind():
-                        cs = self._zero_view(L["cs"]) if L["cs"] else None
-                        plan_box["p"] = lib.ConvGemm(L["a"], L["b"], L["segs"], L["out"], L["OW"], L["OH"], L["NB"],
-                                                     L["TW"], L["TH"], addend=L["addend"], mask=L["mask"], colsum=cs,
-                                                     halo=L.get("halo", False))
-                    self._late_binds.append(bind)
-                    return lambda: plan_box["p"].launch()
-                fl = sum(2.0 * nb_ * gm.oh * gm.ow * cv.cout * cv.k * cv.k * cv.cin for gm, cv in zip(geoms, convs)) \
-                    / len(staged)      # executed work (decimated grid when the consumer gradient is sparse)
-                nbytes = 2.0 * (sum(v.numel() for v in L["a"]) + L["out"].numel() * (2 + (1 if addend is not None else 0))
-                                + bmat.numel())
-                self._add(self.ops_bwd, OpRec(make(), "conv_dgrad", X, fl, nbytes, lane=si,
-                                              after=self._bwd_deps(si) + [stage_op]))
-        if self.sparse_bwd and not adds and stride == 2 and [pi for pi, _, _ in staged] == [0] and h % 2 == 0 and w % 2 == 0:
+        def bind():
+            cs = self._zero_view(key) if key else None
+            box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs, dy_sparse=sparse_in)
+            op.launches = stage_op.launches = box["p"].n_launches
+            assert (box["p"].untouched == 0b1110) == only_phase0, (X, box["p"].untouched)
+        self._late_binds.append(bind)
+        self.dgrad_ops[X] = box
+        if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)
 
+    def _bwd_deps(self):
+        """Cross-lane dependencies of a main-lane backward op: none (lane 0 is ordered by its stream); kept as a hook."""
+        return []
+
     def _build_wgrad(self, c: ConvSpec):
+        """Raw weight gradient (urso_conv2d_wgrad_*) on the wgrad lane + urso_conv_param_grads on the aux lane."""
         g, B = self.graph, self.B
         S = lib.stream_ptr
-        sparse_du = False
-        if c.stem:
-            segs = [(m, dh, dw) for (m, dh, dw, _ch) in P.stem_segments()]
-            pc = 64
-            geom = None
-            oh, ow = g.shapes[c.dst][:2]
-            n_rows = 4 * 64
-            row_map = self._idx(P.stem_grad_row_map(3))
-        else:
-            h, w, _ = g.shapes[c.src]
-            sparse_du = self.sparse_bwd and c.dst in self.sparse and c.stride == 1
-            geom = self._bwd_geom(c, h, w, sparse_du)
-            segs = P.wgrad_segments(geom)
-            pc = c.cin
-            oh, ow = geom.oh, geom.ow
-            n_rows = c.k * c.k * c.cin
-            row_map = None
-        qc = c.cout
+        shape = self._conv_shape(c)
+        oh, ow = lib.out_hw(shape)
+        sparse_du = (not c.stem) and self.sparse_bwd and c.dst in self.sparse and c.stride == 1
+        if sparse_du:
+            oh, ow = (oh + 1) // 2, (ow + 1) // 2
+        n_rows = 4 * 64 if c.stem else c.k * c.k * c.cin
+        row_map = self._idx(lib.stem_grad_row_map()) if c.stem else None
         gkey = "G:" + c.name
         self._zero_specs.append((gkey, n_rows * c.cout))
         skey = "S:" + c.name
         if c.bn:
             self._zero_specs.append((skey, c.cout))
-        swap = (not c.stem) and c.k == 1 and c.stride == 1 and c.cin < 128 <= c.cout and not sparse_du
-        flat = (not c.stem) and c.k == 1 and c.stride == 1 and not sparse_du
-        wg_ops = []
-        for si, (b0, b1) in enumerate(self.slices):
-            nb_ = b1 - b0
-            du = self.dact[c.dst][b0:b1]
-            if sparse_du:
-                du = du[:, ::2, ::2, :]
-            p_views = [self.E[b0:b1]] if c.stem else P.input_views(self.act[c.src][b0:b1], geom.stride if geom else 1)
-            box = {}
+        x = self.E if c.stem else self.act[c.src]
+        du = self.dact[c.dst]
+        box = {}
 
-            def bind(box=box, du=du, p_views=p_views, nb_=nb_, b0=b0, b1=b1):
-                G = self._zero_view(gkey)
-                if flat:
-                    M = nb_ * oh * ow
-                    xv, dv = self.act[c.src][b0:b1].view(1, 1, M, c.cin), du.view(1, 1, M, du.shape[3])
-                    if swap:   # wide side on the 128-row MMA M dimension; transposed accumulation into HWIO
-                        box["p"] = lib.Wgrad([dv], xv, [(0, 0, 0)], qc, c.cin, M, 1, 1, 64, 1, G, c.cin * c.cout, 1, c.cout)
-                    else:
-                        box["p"] = lib.Wgrad([xv], dv, [(0, 0, 0)], c.cin, qc, M, 1, 1, 64, 1, G, c.cin * c.cout, c.cout, 1)
-                else:
-                    tw, th = P.pick_patch(oh, ow, 64)
-                    box["p"] = lib.Wgrad(p_views, du, segs, pc, qc, ow, oh, nb_, tw, th, G, pc * c.cout, c.cout, 1)
-            self._late_binds.append(bind)
-            fl = 2.0 * nb_ * oh * ow * c.cout * c.k * c.k * c.cin
-            nb = 2.0 * (sum(v.numel() for v in p_views) + du.numel()) + 4.0 * n_rows * c.cout
-            if self.wgrad_lanes:   # own lane: ordered behind the dgrad that produced du (the last op of the slice lane)
-                lane = self.n_slices * (1 + self._wgrad_rr % self.wgrad_lanes) + si
-                deps = [self._last.get(si), self._bwd_root]
-            else:
-                lane, deps = si, self._bwd_deps(si)
-            wg_ops.append(self._add(self.ops_bwd, OpRec(lambda box=box: box["p"].launch(), "conv_wgrad", c.name, fl, nb,
-                                                        lane=lane, after=deps)))
+        def bind():
+            box["p"] = lib.Conv2dWgrad(shape, x, du, self._zero_view(gkey), dy_sparse=sparse_du)
+        self._late_binds.append(bind)
+        fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
+        sub = 4 if ((c.k == 1 and c.stride == 2) or (sparse_du and c.k == 1)) else 1     # pixels a strided 1x1 samples
+        nb = 2.0 * (x.numel() / sub + du.numel() / (4 if sparse_du else 1)) + 4.0 * n_rows * c.cout
+        if self.wgrad_lanes:   # own lane: ordered behind the dgrad that produced du (the last op of the main lane)
+            lane = 1 + self._wgrad_rr % self.wgrad_lanes
+            deps = [self._last.get(0), self._bwd_root]
+        else:
+            lane, deps = 0, []
+        wg_op = self._add(self.ops_bwd, OpRec(lambda: box["p"].launch(), "conv_wgrad", c.name, fl, nb, lane=lane,
+                                              after=deps))
         self._wgrad_rr += 1
         # parameter gradients from the raw wgrad (BN scale folded back, d gamma / d beta / d bias in closed form):
-        # aux lane, after the wgrad (and with it the d-beta column sums) of EVERY slice
+        # aux lane, after the wgrad (and with it the d-beta column sums)
         w, bias, bn = self._conv_weight_ptrs(c)
         pv = self.params.view
         dW = pv(c.name + "/kernel", self.grads)
@@ -754,7 +631,7 @@ class Engine:
                      dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta),
                      self._zero_view(skey).data_ptr() if c.bn else None, R, c.cout, S())
         self._add(self.ops_bwd, OpRec(run, "param_grads", c.name, 0.0, 12.0 * R * c.cout, 2, lane=self.aux_lane,
-                                      after=wg_ops))
+                                      after=[wg_op]))
 
     def _build_update(self):
         S = lib.stream_ptr

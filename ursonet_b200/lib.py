@@ -42,6 +42,33 @@ class WgradDesc(C.Structure):
                 ("split_k", C.c_int32), ("block_q", C.c_int32)]
 
 
+MAX_FANIN = 4
+
+
+class Conv2dShape(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("K", C.c_int32),
+                ("ksize", C.c_int32), ("stride", C.c_int32), ("pad_t", C.c_int32), ("pad_l", C.c_int32),
+                ("pad_b", C.c_int32), ("pad_r", C.c_int32)]
+
+
+class Conv2dFwdDesc(C.Structure):
+    _fields_ = [("shape", Conv2dShape), ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p),
+                ("shift", C.c_void_p), ("addend", C.c_void_p), ("y", C.c_void_p), ("relu", C.c_int32),
+                ("out_fp32", C.c_int32), ("workspace", C.c_void_p)]
+
+
+class Conv2dDgradDesc(C.Structure):
+    _fields_ = [("n_convs", C.c_int32), ("shape", Conv2dShape * MAX_FANIN), ("dy", C.c_void_p * MAX_FANIN),
+                ("w", C.c_void_p * MAX_FANIN), ("scale", C.c_void_p * MAX_FANIN), ("dy_sparse", C.c_int32),
+                ("mask", C.c_void_p), ("addend", C.c_void_p), ("dx", C.c_void_p), ("colsum", C.c_void_p),
+                ("workspace", C.c_void_p)]
+
+
+class Conv2dWgradDesc(C.Structure):
+    _fields_ = [("shape", Conv2dShape), ("x", C.c_void_p), ("dy", C.c_void_p), ("dy_sparse", C.c_int32),
+                ("G", C.c_void_p)]
+
+
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes (all return int unless listed in _RESTYPES); kept in sync with include/urso_b200.h
@@ -57,6 +84,26 @@ SIGNATURES = {
     "urso_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(_vp)],
     "urso_wgrad_launch": [_vp, _vp],
     "urso_wgrad_destroy": [_vp],
+    "urso_sizeof_conv2d_fwd_desc": [],
+    "urso_sizeof_conv2d_dgrad_desc": [],
+    "urso_sizeof_conv2d_wgrad_desc": [],
+    "urso_same_pad": [_i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)],
+    "urso_conv2d_fwd_workspace_bytes": [C.POINTER(Conv2dShape)],
+    "urso_conv2d_fwd_create": [C.POINTER(Conv2dFwdDesc), C.POINTER(_vp)],
+    "urso_conv2d_fwd_stage_weights": [_vp, _vp],
+    "urso_conv2d_fwd_launch": [_vp, _vp],
+    "urso_conv2d_fwd_destroy": [_vp],
+    "urso_conv2d_dgrad_workspace_bytes": [C.POINTER(Conv2dDgradDesc)],
+    "urso_conv2d_dgrad_create": [C.POINTER(Conv2dDgradDesc), C.POINTER(_vp)],
+    "urso_conv2d_dgrad_stage_weights": [_vp, _vp],
+    "urso_conv2d_dgrad_launch": [_vp, _vp],
+    "urso_conv2d_dgrad_untouched_phases": [_vp],
+    "urso_conv2d_dgrad_num_launches": [_vp],
+    "urso_conv2d_dgrad_destroy": [_vp],
+    "urso_conv2d_wgrad_create": [C.POINTER(Conv2dWgradDesc), C.POINTER(_vp)],
+    "urso_conv2d_wgrad_launch": [_vp, _vp],
+    "urso_conv2d_wgrad_destroy": [_vp],
+    "urso_stem_grad_row_map": [C.POINTER(_i32)],
     "urso_stem_stage": [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_maxpool_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "urso_maxpool_bwd": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
@@ -84,7 +131,10 @@ SIGNATURES = {
     "urso_pad_cast_rows": [_vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
-_RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None}
+_RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
+             "urso_same_pad": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
+             "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
 _lib = None
 
@@ -108,6 +158,10 @@ def load():
         fn.restype = _RESTYPES.get(name, C.c_int)
     if lib.urso_sizeof_convgemm_desc() != C.sizeof(ConvGemmDesc) or lib.urso_sizeof_wgrad_desc() != C.sizeof(WgradDesc):
         raise UrsoError("ctypes struct layout does not match include/urso_b200.h (rebuild the library)")
+    if (lib.urso_sizeof_conv2d_fwd_desc() != C.sizeof(Conv2dFwdDesc)
+            or lib.urso_sizeof_conv2d_dgrad_desc() != C.sizeof(Conv2dDgradDesc)
+            or lib.urso_sizeof_conv2d_wgrad_desc() != C.sizeof(Conv2dWgradDesc)):
+        raise UrsoError("ctypes conv2d operator structs do not match include/urso_b200.h (rebuild the library)")
     _lib = lib
     return lib
 
@@ -218,3 +272,121 @@ class Wgrad:
         if getattr(self, "_h", None) and _lib is not None:
             _lib.urso_wgrad_destroy(self._h)
             self._h = None
+
+
+# ------------------------------------------------------------------------------------------------ Conv2D operators
+def same_pad(n, k, s):
+    """TF 'SAME' (before, after) padding of one dimension, computed by the library (urso_same_pad)."""
+    b, a = _i32(), _i32()
+    load().urso_same_pad(n, k, s, C.byref(b), C.byref(a))
+    return b.value, a.value
+
+
+def conv_shape(N, H, W, Cin, K, ksize, stride, padding):
+    """urso_conv2d_shape from a Keras-style padding spec: 'same' | 'valid' | int (explicit symmetric ZeroPadding2D)."""
+    if padding == "same":
+        (pt, pb), (pl, pr) = same_pad(H, ksize, stride), same_pad(W, ksize, stride)
+    elif padding == "valid":
+        pt = pb = pl = pr = 0
+    else:
+        pt = pb = pl = pr = int(padding)
+    return Conv2dShape(N, H, W, Cin, K, ksize, stride, pt, pl, pb, pr)
+
+
+def out_hw(s):
+    return (s.H + s.pad_t + s.pad_b - s.ksize) // s.stride + 1, (s.W + s.pad_l + s.pad_r - s.ksize) // s.stride + 1
+
+
+def _workspace(nbytes, device):
+    import torch
+    if nbytes < 0:
+        check(2, "workspace query")
+    return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class Conv2dFwd:
+    """urso_conv2d_fwd_t: y = relu?( conv(x, w * scale) + shift + addend ).  All planning happens in the library."""
+
+    def __init__(self, shape, x, w, scale, shift, y, addend=None, relu=False):
+        import torch
+        d = Conv2dFwdDesc()
+        d.shape = shape
+        self.ws = _workspace(load().urso_conv2d_fwd_workspace_bytes(C.byref(shape)), x.device)
+        d.x, d.w, d.scale, d.shift, d.addend, d.y = ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(addend), ptr(y)
+        d.relu, d.out_fp32, d.workspace = int(relu), int(y.dtype == torch.float32), self.ws.data_ptr()
+        assert x.is_contiguous() and y.is_contiguous() and (addend is None or addend.is_contiguous())
+        self._keep = (x, w, scale, shift, y, addend)
+        h = _vp()
+        check(load().urso_conv2d_fwd_create(C.byref(d), C.byref(h)), "urso_conv2d_fwd_create")
+        self._h = h
+
+    def stage(self):
+        check(load().urso_conv2d_fwd_stage_weights(self._h, stream_ptr()), "urso_conv2d_fwd_stage_weights")
+
+    def launch(self):
+        check(load().urso_conv2d_fwd_launch(self._h, stream_ptr()), "urso_conv2d_fwd_launch")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.urso_conv2d_fwd_destroy(self._h)
+            self._h = None
+
+
+class Conv2dDgrad:
+    """urso_conv2d_dgrad_t: dx = mask( sum_i dgrad_i(dy_i, w_i * scale_i) + addend ) with fused fan-in."""
+
+    def __init__(self, shapes, dys, ws, scales, dx, mask=None, addend=None, colsum=None, dy_sparse=False):
+        d = Conv2dDgradDesc()
+        d.n_convs = len(shapes)
+        for i, (s, dy, w, sc) in enumerate(zip(shapes, dys, ws, scales)):
+            assert dy.is_contiguous()
+            d.shape[i], d.dy[i], d.w[i], d.scale[i] = s, ptr(dy), ptr(w), ptr(sc)
+        d.dy_sparse = int(dy_sparse)
+        d.mask, d.addend, d.dx, d.colsum = ptr(mask), ptr(addend), ptr(dx), ptr(colsum)
+        assert dx.is_contiguous() and (mask is None or mask.is_contiguous()) and (addend is None or addend.is_contiguous())
+        self.ws = _workspace(load().urso_conv2d_dgrad_workspace_bytes(C.byref(d)), dx.device)
+        d.workspace = self.ws.data_ptr()
+        self._keep = (dys, ws, scales, dx, mask, addend, colsum)
+        h = _vp()
+        check(load().urso_conv2d_dgrad_create(C.byref(d), C.byref(h)), "urso_conv2d_dgrad_create")
+        self._h = h
+        self.n_launches = load().urso_conv2d_dgrad_num_launches(h)
+        self.untouched = load().urso_conv2d_dgrad_untouched_phases(h)
+
+    def stage(self):
+        check(load().urso_conv2d_dgrad_stage_weights(self._h, stream_ptr()), "urso_conv2d_dgrad_stage_weights")
+
+    def launch(self):
+        check(load().urso_conv2d_dgrad_launch(self._h, stream_ptr()), "urso_conv2d_dgrad_launch")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.urso_conv2d_dgrad_destroy(self._h)
+            self._h = None
+
+
+class Conv2dWgrad:
+    """urso_conv2d_wgrad_t: G[k*k*C, K] += x (*) dy  (raw fp32 weight gradient of the unscaled conv; caller zeroes G)."""
+
+    def __init__(self, shape, x, dy, G, dy_sparse=False):
+        d = Conv2dWgradDesc()
+        d.shape, d.x, d.dy, d.dy_sparse, d.G = shape, ptr(x), ptr(dy), int(dy_sparse), ptr(G)
+        assert x.is_contiguous() and dy.is_contiguous()
+        self._keep = (x, dy, G)
+        h = _vp()
+        check(load().urso_conv2d_wgrad_create(C.byref(d), C.byref(h)), "urso_conv2d_wgrad_create")
+        self._h = h
+
+    def launch(self):
+        check(load().urso_conv2d_wgrad_launch(self._h, stream_ptr()), "urso_conv2d_wgrad_launch")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.urso_conv2d_wgrad_destroy(self._h)
+            self._h = None
+
+
+def stem_grad_row_map():
+    m = (_i32 * 147)()
+    load().urso_stem_grad_row_map(m)
+    return list(m)
