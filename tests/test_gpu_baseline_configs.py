@@ -226,5 +226,6 @@ def test_first_graph_step_equals_eager_step():
             torch.cuda.synchronize()
             outs.append((eng.params.flat - w0).clone())
         d_eager, d_graph = outs
-        # a doubled update would give d_graph ~ 2 * d_eager (SGD: 1.9x with momentum)
-        assert (d_eager - d_graph).norm().item() <= 1e-3 * d_eager.norm().item(), opt
+        # a doubled update would give d_graph ~ 2 * d_eager (SGD: 1.9x with momentum), i.e. a relative difference ~ 1;
+        # atomic summation order + the chaotic random net give ~2e-3 (measured)
+        assert (d_eager - d_graph).norm().item() <= 5e-2 * d_eager.norm().item(), opt
