@@ -23,6 +23,9 @@ extern "C" {
 int urso_version(void);
 const char* urso_last_error(void);
 int urso_num_sms(void);
+/* Limit the persistent Engine-F grids planned from now on to n CTAs (0 = one per SM): leaves SMs free for kernels that
+ * must run concurrently (an overlapped NCCL all-reduce), and lets tests exercise deep per-CTA tile queues at small sizes. */
+void urso_set_max_ctas(int n);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);
@@ -75,13 +78,16 @@ typedef struct {
   int32_t block_n;    /* N tile: 0 = auto, else 32 / 64 / 128 / 256 */
   int32_t halo;       /* 1: halo reuse -- all segments are taps of ONE stride-1 view (n_a == 1, TW == 8, TH == 16): each
                          64-channel chunk of the input patch (+ its halo) is fetched once and every tap reads a
-                         row-shifted window of it from shared memory instead of re-fetching it from L2 */
+                         row-shifted window of it from shared memory instead of re-fetching it from L2; when the weight
+                         operand has one N tile and fits (<= 100 KB) it is kept resident in shared memory as well */
 } urso_convgemm_desc;
 
 typedef struct urso_convgemm urso_convgemm_t;
 int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t** out);
 int urso_convgemm_launch(urso_convgemm_t* h, void* stream);
 void urso_convgemm_destroy(urso_convgemm_t* h);
+/* plan introspection (tests / profiling): out9 = {block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid} */
+int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9);
 
 /* ---- Engine W: weight-gradient GEMM on tcgen05 (replaces Conv2DBackpropFilter of TF autodiff).
  *   G[t][p, q] (+)= sum_pixels  P_t[pixel + (dh_t,dw_t), p] * Q[pixel, q]        t = 0..n_seg-1
@@ -152,6 +158,7 @@ int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d_fwd_t** ou
 int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream);
 int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream);
 void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h);
+int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9); /* see urso_convgemm_plan_info */
 
 /* Input gradient with fused fan-in: dx = mask( sum_i dgrad_i(dy_i, w_i) + addend ), one launch per output phase
  * (stride^2 phases), the convolutions' reduction ranges concatenated.  All consumers share x's shape and stride.

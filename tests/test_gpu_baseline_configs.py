@@ -106,6 +106,19 @@ def test_cfg2_resnet50_640x960_ori16_train_layer_local():
     assert eng.sparse, "the structural-sparsity dgrad launches must be exercised at this shape"
 
 
+@pytest.mark.parametrize("backbone", ["resnet50", "resnet18"])
+def test_small_train_layer_local_with_deep_tile_queues(backbone):
+    """Same layer-local check at 128x192 with the persistent grids limited to 3 CTAs: every launch of the network runs with
+    many tiles per CTA (two pipelines, ring wrap-around, accumulator phase flips)."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_max_ctas(3)
+    try:
+        cfg = make_cfg(backbone, True)
+        run_train_parity(cfg, 2, seed=71)
+    finally:
+        lib.load().urso_set_max_ctas(0)
+
+
 def test_cfg4_resnet101_640x960_ori24_train_layer_local():
     """BASELINE configs[3] at B = 1: RN-101 (22 stage-4 identity blocks), ori_resolution 24 = 13 824 bins."""
     cfg = baseline_cfg("resnet101", True, 640, 960, 24)

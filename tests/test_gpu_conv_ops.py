@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(params=[0, 3], autouse=True, ids=["all_sms", "3_ctas"])
+def cta_limit(request):
+    """Every case also runs with the persistent grids limited to 3 CTAs (urso_set_max_ctas): each CTA then works through a
+    long queue of tiles, so the two operand pipelines, their ring wrap-arounds and the accumulator-stage phase flips are
+    exercised even at these small shapes."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_max_ctas(request.param)
+    yield
+    lib.load().urso_set_max_ctas(0)
+
+
 def bf16_exact(*shape, scale=1.0, seed=0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(torch.float64)
@@ -211,3 +222,67 @@ def test_operator_errors_are_reported():
     with pytest.raises(lib.UrsoError):
         lib.Conv2dFwd(shape, x, w, None, None, y)
     assert b"multiple of 64" in lib.load().urso_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ pipelines at depth
+# Shapes with MANY tiles per CTA (>= 8 on 148 SMs), so that both operand pipelines wrap their shared-memory rings and
+# reuse each of their two accumulator stages several times (barrier phase flips), in every planning mode:
+# halo + resident weights (N = 64), halo + streamed weights (N = 128, two channel chunks), stream mode with two K steps
+# per barrier round, one pipeline with BLOCK_N = 256.
+BIG_CASES = [  # k, stride, padding, cin, cout, N, h, w, expect (subset of plan_info)
+    (3, 1, "same", 64, 64, 4, 160, 240, dict(halo=1, bres=1, npipe=2)),
+    (3, 1, "same", 128, 128, 16, 80, 120, dict(halo=1, bres=0, npipe=2)),
+    (1, 1, "valid", 256, 64, 4, 160, 240, dict(halo=0, npipe=2)),
+    (1, 1, "valid", 512, 128, 8, 80, 120, dict(halo=0, npipe=2)),
+    (3, 1, "same", 256, 256, 8, 40, 60, dict(halo=0, npipe=1, block_n=256)),
+    (1, 2, "valid", 256, 128, 8, 160, 240, dict(halo=0, npipe=2)),
+]
+
+
+@pytest.mark.parametrize("k,stride,padding,cin,cout,N,h,w,expect", BIG_CASES)
+def test_conv2d_fwd_many_tiles_per_cta(k, stride, padding, cin, cout, N, h, w, expect):
+    from ursonet_b200 import lib
+    x = bf16_exact(N, h, w, cin, seed=61)
+    wk = bf16_exact(k, k, cin, cout, scale=0.05, seed=62)
+    scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+    shift = torch.randn(cout, dtype=torch.float64)
+    shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)
+    oh, ow = lib.out_hw(shape)
+    y = torch.full((N, oh, ow, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    op = lib.Conv2dFwd(shape, x.to(torch.bfloat16).to(DEV), wk.float().to(DEV), scale.float().to(DEV),
+                       shift.float().to(DEV), y, relu=True)
+    info = op.plan_info()
+    for key, val in expect.items():
+        assert info[key] == val, (key, info)
+    op.stage()
+    op.launch()
+    op.launch()          # a second launch must not depend on state left by the first
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = torch.relu(O.conv2d(x, staged(wk, scale.float().double()), None, stride, padding) + shift.float().double())
+    assert relerr(y.double().cpu(), ref) <= 6e-3, info
+
+
+def test_conv2d_dgrad_halo_resident_with_mask_many_tiles():
+    """The stage-2 3x3 input gradient of the bench workload (64 channels, 160x240): halo + resident weights + two
+    pipelines + the TMA-prefetched ReLU mask, 8 tiles per CTA."""
+    from ursonet_b200 import lib
+    N, h, w, c = 4, 160, 240, 64
+    shape = lib.conv_shape(N, h, w, c, c, 3, 1, "same")
+    wk = bf16_exact(3, 3, c, c, scale=0.05, seed=71)
+    scale = 0.5 + torch.rand(c, dtype=torch.float64)
+    dy = bf16_exact(N, h, w, c, seed=72)
+    mask = bf16_exact(N, h, w, c, seed=73)
+    xr = torch.zeros(N, h, w, c, dtype=torch.float64, requires_grad=True)
+    (gref,) = torch.autograd.grad(O.conv2d(xr, staged(wk, scale.float().double()), None, 1, "same"), xr, dy)
+    gref = gref * (mask > 0)
+    dx = torch.zeros(N, h, w, c, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(c, dtype=torch.float32, device=DEV)
+    op = lib.Conv2dDgrad([shape], [dy.to(torch.bfloat16).to(DEV)], [wk.float().to(DEV)], [scale.float().to(DEV)], dx,
+                         mask=mask.to(torch.bfloat16).to(DEV), colsum=cs)
+    op.stage()
+    op.launch()
+    torch.cuda.synchronize()
+    got = dx.double().cpu()
+    assert relerr(got, gref) <= 6e-3
+    assert torch.allclose(cs.double().cpu(), got.sum((0, 1, 2)), rtol=1e-3, atol=1e-2 * got.abs().max().item())

@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(params=[0, 3], autouse=True, ids=["all_sms", "3_ctas"])
+def cta_limit(request):
+    """Every case also runs with the persistent grids limited to 3 CTAs (urso_set_max_ctas): each CTA then works through a
+    long queue of tiles, so the two operand pipelines, their ring wrap-arounds and the accumulator-stage phase flips are
+    exercised even at these small shapes."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_max_ctas(request.param)
+    yield
+    lib.load().urso_set_max_ctas(0)
+
+
 def bf16_exact(*shape, scale=1.0, seed=0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(torch.float64)

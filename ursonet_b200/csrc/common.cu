@@ -26,6 +26,12 @@ int num_sms() {
   return n;
 }
 
+static int g_max_ctas = 0;
+int max_ctas() {
+  const int n = num_sms();
+  return (g_max_ctas > 0 && g_max_ctas < n) ? g_max_ctas : n;
+}
+
 encode_tiled_fn get_encode_tiled() {
   static encode_tiled_fn fn = nullptr;
   static std::once_flag once;
@@ -82,6 +88,7 @@ extern "C" {
 int urso_version(void) { return 100; }
 const char* urso_last_error(void) { return urso::g_err.c_str(); }
 int urso_num_sms(void) { return urso::num_sms(); }
+void urso_set_max_ctas(int n) { urso::g_max_ctas = n; }
 int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
 int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }
 }

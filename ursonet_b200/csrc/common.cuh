@@ -12,6 +12,7 @@ namespace urso {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+int max_ctas();   // num_sms() or the urso_set_max_ctas() limit: grid size of the persistent Engine-F kernels
 
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency, so the
 // library loads -- and its symbols can be checked -- on a machine without a driver).

@@ -2,34 +2,43 @@
 //
 //   D[pixel, n] = sum over K-segments (filter taps / concatenated inputs) of  A_seg[pixel + shift, c] * B[n, k]
 //
-//  * A tiles: 128 output pixels (a TH x TW patch of one image) x 64 channels, fetched by ONE 4-D TMA box per
-//    K-step straight from the NHWC activation tensor.  The tap shift is added to the box coordinates and TMA's
-//    out-of-bounds zero fill implements the convolution padding -- no im2col buffer ever exists.
+//  * A tiles: 128 output pixels (a TH x TW patch of one image) x 64 channels, fetched by 4-D TMA boxes straight from the
+//    NHWC activation tensor.  The tap shift is added to the box coordinates and TMA's out-of-bounds zero fill implements
+//    the convolution padding -- no im2col buffer ever exists.
 //  * B tiles: BLOCK_N x 64 slices of the staged (BN-folded, K-major) weight matrix, 2-D TMA.
 //  * both land in 128B-swizzled shared memory and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued by
-//    one thread; fp32 accumulators live in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
-//    tile i+1.
-//  * epilogue (4 warps, one TMEM lane quadrant = 32 pixel rows each), per 64-channel chunk:
+//    one thread per pipeline; fp32 accumulators live in TMEM, double buffered per pipeline so the epilogue of a tile
+//    overlaps the MMAs of the next.
+//
+//  Operand supply.  Two things bound the small-N (64 / 128 channel) layers in round 1 (profiles/r01_progress.md,
+//  profiles/r02_umma_rounds.txt): (a) the MMA-issuing warp spends ~316 cycles per barrier round (wait + fence + elect +
+//  commit) on top of its MMAs, and (b) the L2 -> SM path delivers ~67 B/clk per SM while a 3x3 tile of N = 64 asks for
+//  128 B/clk.  This kernel answers both:
+//    - TWO PIPELINES (npipe = 2, BLOCK_N <= 128): two producer warps and two MMA-issuing warps work on ALTERNATE tiles
+//      of the CTA, each pair with its own shared-memory ring and its own two accumulator stages (4 x BLOCK_N TMEM
+//      columns).  While one issuer sits in its barrier round the other one's MMAs keep the tensor pipe busy
+//      (microbenchmark: pipe utilisation 0.38 -> 1.00 at N = 64 with 8 MMAs per round).
+//    - HALO MODE (3x3-style taps on one stride-1 view, 8 x 16 pixel patch): ONE TMA box per 64-channel chunk holds the
+//      patch plus its halo; every tap's A operand is a row-shifted window of it (UMMA descriptors swizzle on absolute
+//      smem address bits, so a start shifted by whole 128-byte rows reads what TMA wrote) -- 6.4x less A traffic.
+//    - RESIDENT B (halo mode, one N tile, weight operand <= 100 KB): the whole weight matrix is loaded once per CTA; a
+//      tile then costs one barrier wait and two commits for all of its (up to 36) MMAs.
+//    - kpack (stream mode): two K steps per barrier round.
+//
+//  * epilogue (8 warps = 4 TMEM lane quadrants x 2 alternating chunk sets), per 64-channel chunk:
 //      tcgen05.ld -> +shift -> +addend -> ReLU -> mask -> bf16
 //    ALL global traffic of the epilogue is TMA as well: every warp prefetches its own 32-row slab of the addend /
 //    mask tensors chunks ahead into a private smem ring (so HBM latency never sits on the critical path) and writes
-//    its output slab with a TMA store from a double-buffered smem slab (full 128-byte lines, automatic clipping of
+//    its output slab with a TMA store from a private smem slab (full 128-byte lines, automatic clipping of
 //    partial tiles, strided views for stride-2 dgrad).  No cross-warp synchronisation in the epilogue.
 //    A legacy register epilogue (direct vector stores) remains for fp32 outputs / BLOCK_N = 32 (bottleneck conv).
 //  * optional fused per-channel sums of the stored output (d beta): read back from the bf16 output slab
 //    (conflict free), accumulated per CTA in shared memory, flushed with one atomic per channel per CTA.
 //
-// Roles (384 threads): warps 0 and 3 = TMA producers (even / odd K steps), warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-11 = epilogue
-// (4 TMEM lane quadrants x 2 column halves).
+// Roles (384 threads): warps 0 and 3 = TMA producers, warps 1 and 2 = MMA issuers (warp 2 also allocates TMEM),
+// warps 4-11 = epilogue.  With one pipeline the two producers take alternate barrier rounds and warp 2 only allocates.
 #include "common.cuh"
 #include "ptx.cuh"
-
-// Bottleneck-isolation knobs (URSO_DBG_NO_TMA / URSO_DBG_NO_MMA, scripts/bench_isolate.py) are compiled in only with
-// `make DEBUG_KNOBS=1`: they put a branch into the producer and MMA-issue loops.
-#ifndef URSO_DEBUG_KNOBS
-#define URSO_DEBUG_KNOBS 0
-#endif
 
 namespace urso {
 
@@ -60,17 +69,26 @@ __host__ inline FastDiv make_fastdiv(uint32_t d) {
 __device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
 
 struct ConvGemmParams {
-  CUtensorMap a_maps[URSO_MAX_AMAPS];
-  CUtensorMap b_map;
+  CUtensorMap a_maps[URSO_MAX_AMAPS];       // stream mode: box {64, TW, TH, 1} per view
+  CUtensorMap a_halo_map;                   // halo mode: box {64, halo_w, halo_h, 1} of view 0
+  CUtensorMap b_map;                        // box {64, BLOCK_N}
   CUtensorMap out_map, add_map, mask_map;   // epilogue slabs: box {64, bw, bh, 1}
   SegDev seg[URSO_MAX_SEGS];
-  int n_seg;
+  int n_seg, ksteps;
   int OW, OH, NB;
   int TW, TH, tw_shift;
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   FastDiv fd_ntn, fd_tw, fd_th;
   int ncols;
-  int stages;        // mainloop ring depth (runtime: depends on how much smem the epilogue needs)
+  int npipe;         // 1 or 2 producer -> MMA pipelines working on alternate tiles
+  int stages;        // per pipeline: stream mode = ring of (A, B) stages; halo mode = ring of B tiles (unless resident)
+  int kpack;         // stream mode: K steps (of 64) per stage / barrier round
+  int halo, halo_w, halo_dw_min, halo_dh_min, halo_bytes;
+  int a_stages, a_stage_bytes;   // halo mode, per pipeline
+  int bres;          // halo mode: the whole weight operand is resident in shared memory
+  int pipe_bytes;    // shared memory of one pipeline (its A ring followed by its B ring)
+  int b_ring_off;    // offset of a pipeline's B ring from its base
+  int bres_off, ctrl_off;
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
   int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
@@ -81,35 +99,20 @@ struct ConvGemmParams {
   int out_fp32, relu;
   const float* shift;
   float* colsum;
-  int dbg_row_shift, dbg_base_offset;   // descriptor experiments (scripts/exp_desc_shift.py)
-  int dbg_no_tma, dbg_no_mma;            // bottleneck isolation (URSO_DBG_NO_TMA / URSO_DBG_NO_MMA): results are garbage
-  // halo mode (3x3-style taps on one stride-1 view, TW == 8): ONE TMA box per channel chunk holds the whole
-  // (TH+dh range) x (TW+dw range) pixel halo; every tap's A operand is a row-shifted window of it (UMMA descriptors
-  // swizzle on absolute smem address bits, so a start shifted by whole 128-byte rows reads what TMA wrote).
-  CUtensorMap a_halo_map;
-  int halo, halo_w, halo_dw_min, halo_dh_min, halo_bytes;
-  int a_stages, a_stage_bytes, a_ring_bytes;
-  // cluster mode: CTA pairs work on two adjacent M tiles of the same N tile; each CTA fetches HALF of the weight tile
-  // and multicasts it to both (halves the L2 -> SM traffic of B, which bounds the large-N tiles)
-  CUtensorMap b_half_map;
-  int cluster, total_pairs;
-  int cta2;   // CTA pairs with tcgen05.mma.cta_group::2 (BLOCK_N = 256 only; see the kernel)
-  int kpack;  // K steps (of 64) per pipeline stage / barrier round: 2 halves the per-K-step issue overhead of the MMA warp
-              // (wait + fence + elect + commit ~ 190 cycles, scripts/umma_rate.cu), which bounds the N <= 128 launches
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 8;                       // per pipeline
 constexpr int kCtrlBytes = 1024;                    // barriers + tmem slot
 constexpr int kMaxColsumCols = 2048;
-constexpr int kColsumAccBytes = kMaxColsumCols * 4;
 constexpr int kSlabBytes = 32 * 128;                // 32 pixel rows x 64 bf16 channels
 constexpr int kMaxEiDepth = 3;                      // per-warp prefetch ring depth (chunks ahead), runtime <= this
 constexpr int kTrStride = 36;                       // legacy colsum transpose scratch (floats per row)
 constexpr int kLegacyScratchBytes = 4 * 32 * kTrStride * 4;
 constexpr int kSmemBudget = 227 * 1024;             // the dynamic smem base is 1 KB aligned by declaration: no slack
+constexpr int kMaxBresBytes = 100 * 1024;
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
@@ -122,17 +125,6 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, i
   img = (int)im;
   h0 = thi * p.TH;
   w0 = twi * p.TW;
-}
-
-// Work items: tiles (one CTA each) or, in cluster mode, tile PAIRS (m_tile = 2*pair + cluster rank, same n_tile).
-__device__ __forceinline__ int work_first(const ConvGemmParams& p) { return p.cluster ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
-__device__ __forceinline__ int work_step(const ConvGemmParams& p) { return p.cluster ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
-__device__ __forceinline__ int work_end(const ConvGemmParams& p) { return p.cluster ? p.total_pairs : p.total_tiles; }
-__device__ __forceinline__ int work_tile(const ConvGemmParams& p, int wk) {
-  if (!p.cluster) return wk;
-  const int ntn = p.n_tiles_n;
-  const int q = (int)fdiv((uint32_t)wk, p.fd_ntn);
-  return (2 * q + (int)(blockIdx.x & 1)) * ntn + (wk - q * ntn);   // may lie beyond the last tile: an all-OOB dummy
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -152,55 +144,48 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
 // Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
 template <int BLOCK_N>
 struct ChunkIter {
-  int wk, tile, j, nch, n_tile, img, h0, w0;
+  int wk, j, nch, n_tile, img, h0, w0;
   bool valid;
   __device__ __forceinline__ void load(const ConvGemmParams& p) {
-    valid = wk < work_end(p);
+    valid = wk < p.total_tiles;
     if (valid) {
-      tile = work_tile(p, wk);
-      decode_tile(p, tile, n_tile, img, h0, w0);
+      decode_tile(p, wk, n_tile, img, h0, w0);
       const int rem = p.ncols - n_tile * BLOCK_N;
       nch = (rem < BLOCK_N ? rem : BLOCK_N) >> 6;
     }
   }
   __device__ __forceinline__ void init(const ConvGemmParams& p) {
-    wk = work_first(p);
+    wk = (int)blockIdx.x;
     j = 0;
     load(p);
   }
   __device__ __forceinline__ void next(const ConvGemmParams& p) {
     if (++j >= nch) {
       j = 0;
-      wk += work_step(p);
+      wk += (int)gridDim.x;
       load(p);
     }
   }
 };
 
-// CTA2 = true: CTA pairs (cluster of 2) issue ONE tcgen05.mma.cta_group::2 per K = 16 slice over two adjacent M tiles of the
-// same N tile (M = 256): each CTA stages its own A tile and HALF of the weight tile, so the per-SM operand ingest of a
-// 128x256 tile drops from 48 to 32 KB per K step.  The leader CTA (cluster rank 0) owns the full / tempty barriers and
-// issues the MMAs; TMA loads of both CTAs signal the leader's full barrier; commits arrive on both CTAs' barriers.
-template <int BLOCK_N, bool CTA2>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  constexpr int kBTileBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;
-  constexpr int kTmemCols = 2 * BLOCK_N;
-  const uint32_t pair_rank = CTA2 ? cluster_ctarank() : 0u;
+  constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   // 1024-byte aligned by declaration (SWIZZLE_128B atoms): no integer round trip on the base pointer, so the compiler
   // keeps the shared address space and emits LDS/STS/ATOMS with 32-bit addresses instead of generic accesses
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int kStages = p.stages;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + p.a_ring_bytes;
-  uint8_t* ctrl = sB + kStages * p.kpack * kBTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* ei_bar = tempty_bar + 2;                       // [8 warps][kMaxEiDepth]
-  uint64_t* afull_bar = ei_bar + 8 * kMaxEiDepth;          // halo mode: A ring barriers
-  uint64_t* aempty_bar = afull_bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
+  const int npipe = p.npipe;
+  const int pshift = npipe - 1;          // npipe is 1 or 2: (it & pshift) = pipeline of tile `it`, it >> pshift = its index there
+  uint8_t* ctrl = smem + p.ctrl_off;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);            // [2][kMaxStages]
+  uint64_t* empty_bar = full_bar + 2 * kMaxStages;                   // [2][kMaxStages]
+  uint64_t* afull_bar = empty_bar + 2 * kMaxStages;                  // [2][4]   halo mode: A ring
+  uint64_t* aempty_bar = afull_bar + 8;                              // [2][4]
+  uint64_t* tfull_bar = aempty_bar + 8;                              // [4] accumulator stages (2 per pipeline)
+  uint64_t* tempty_bar = tfull_bar + 4;                              // [4]
+  uint64_t* bres_bar = tempty_bar + 4;                               // [1] resident weight operand loaded
+  uint64_t* ei_bar = bres_bar + 1;                                   // [8 warps][kMaxEiDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 8 * kMaxEiDepth);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
   float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes);   // legacy epilogue only
 
@@ -218,105 +203,122 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], CTA2 ? 2 : 1);         // CTA2: one expect_tx arrival per CTA of the pair (leader's barrier)
-      mbar_init(&empty_bar[i], (p.cluster && !CTA2) ? 2 : 1);   // multicast mode: both CTAs' MMAs must have consumed it
+    for (int i = 0; i < 2 * kMaxStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], CTA2 ? 16 : (p.epi_tma ? 8 : 4));   // CTA2: the epilogue warps of BOTH CTAs (leader's barrier)
-    }
-    for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
+    }
+    mbar_init(bres_bar, 1);
+    for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled layouts assume it
-  if (warp == 2) {
-    if constexpr (CTA2) tmem_alloc_2cta(tmem_slot, kTmemCols);
-    else tmem_alloc(tmem_slot, kTmemCols);
-  }
+  const uint32_t tmem_cols = (uint32_t)(2 * npipe * BLOCK_N);        // 64 .. 512: a power of two
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   if (p.colsum != nullptr) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
   }
   tc_fence_before();
-  if (p.cluster) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to it
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Producer and MMA issuer: ALL lanes of the warp run the (warp-uniform) control flow and barrier waits; one elected
+  // Producers and MMA issuers: ALL lanes of the warp run the (warp-uniform) control flow and barrier waits; one elected
   // lane issues the TMA / tcgen05 instructions.  Keeping the loop state warp-uniform lets the compiler hold it in
   // uniform registers -- a loop that lives inside `if (lane == 0)` costs ~130 SASS instructions per K step in R2UR /
   // ELECT shuffling and made the single issuing thread the bottleneck of every small-N tile.
   if (warp == 0 || warp == 3) {
-    // ------------------------------------------------------------------ TMA producers (two warps: even / odd K steps;
-    // a single issuing thread cannot arm a barrier and issue two TMA loads per 128-cycle K step of a small-N tile)
-    const int par = warp == 0 ? 0 : 1;
-    int g = 0;   // global K-step counter of this CTA
+    // ------------------------------------------------------------------ TMA producers
+    const int pw = warp == 0 ? 0 : 1;                 // producer index
+    const int pipe = npipe == 2 ? pw : 0;             // two pipelines: one producer each; one pipeline: alternate rounds
+    uint8_t* pbase = smem + pipe * p.pipe_bytes;
+    uint8_t* sA = pbase;
+    uint8_t* sB = pbase + p.b_ring_off;
+    uint64_t* fullb = full_bar + pipe * kMaxStages;
+    uint64_t* emptyb = empty_bar + pipe * kMaxStages;
+    const int kStages = p.stages;
     if (p.halo) {
-      int stage = 0, a_stage = 0;
-      uint32_t phase = 0, a_phase = 0;
+      uint64_t* afullb = afull_bar + pipe * 4;
+      uint64_t* aemptyb = aempty_bar + pipe * 4;
       const int c_chunks = p.seg[0].c_chunks;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
+      if (p.bres && pw == 0) {          // the whole weight operand, once (n_tiles_n == 1)
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bres_bar, p.ksteps * kBTileBytes);
+          for (int ks = 0; ks < p.ksteps; ++ks)
+            tma_load_2d(smem + p.bres_off + ks * kBTileBytes, &p.b_map, bres_bar, ks * kBlockK, 0);
+        }
+        __syncwarp();
+      }
+      int stage = 0, a_stage = 0, g = 0;
+      uint32_t phase = 0, a_phase = 0;
+      const bool a_mine = npipe == 2 || pw == 0;
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
-        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
+        decode_tile(p, wk, n_tile, img, h0, w0);
         for (int c = 0; c < c_chunks; ++c) {
-          if (par == 0) mbar_wait(&aempty_bar[a_stage], a_phase ^ 1);
-          if (par == 0 && elect_one()) {
-            mbar_arrive_expect_tx(&afull_bar[a_stage], p.halo_bytes);
-            tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afull_bar[a_stage], c * kBlockK,
-                        w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+          if (a_mine) {
+            mbar_wait(&aemptyb[a_stage], a_phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&afullb[a_stage], p.halo_bytes);
+              tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afullb[a_stage], c * kBlockK,
+                          w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++a_stage == p.a_stages) {
             a_stage = 0;
             a_phase ^= 1;
           }
-          for (int s = 0; s < p.n_seg; ++s, ++g) {
-            if ((g & 1) == par) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&full_bar[stage], kBTileBytes);
-                tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], (s * c_chunks + c) * kBlockK,
-                            n_tile * BLOCK_N);
+          if (!p.bres) {
+            for (int s = 0; s < p.n_seg; ++s, ++g) {
+              if (npipe == 2 || (g & 1) == pw) {
+                mbar_wait(&emptyb[stage], phase ^ 1);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&fullb[stage], kBTileBytes);
+                  tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &fullb[stage], (s * c_chunks + c) * kBlockK,
+                              n_tile * BLOCK_N);
+                }
+                __syncwarp();
               }
-              __syncwarp();
-            }
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
         }
       }
-    } else if (p.kpack >= 2) {
-      // kpack (2 or 4) K steps per stage: the owning producer warp (stage groups alternate between the two) arms the barrier once
-      // with the bytes of both K steps (one at the odd end of a tile) and issues their four tile loads
+    } else {
+      // stream mode: a stage holds kpack K steps (A tile + B tile each); the owning producer arms the barrier once
+      // with the bytes of the whole round and issues its tile loads
       int stage = 0, gg = 0;
       uint32_t phase = 0;
       const int kp = p.kpack;
-      int ksteps = 0;
-      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
+      const int ksteps = p.ksteps;
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
-        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
+        decode_tile(p, wk, n_tile, img, h0, w0);
         int kcol = 0, ks = 0, slot = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
-            if ((gg & 1) == par) {
-              if (slot == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (npipe == 2 || (gg & 1) == pw) {
+              if (slot == 0) mbar_wait(&emptyb[stage], phase ^ 1);
               if (elect_one()) {
                 if (slot == 0) {
                   const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
-                  mbar_arrive_expect_tx(&full_bar[stage], n_grp * (kATileBytes + kBTileBytes));
+                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes));
                 }
-                tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK,
+                tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK,
                             w0 + sg.dw, h0 + sg.dh, img);
-                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
+                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N);
               }
               __syncwarp();
             }
@@ -332,102 +334,78 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
-    } else {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t crank = p.cluster ? (blockIdx.x & 1) : 0;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p)) {
-        int n_tile, img, h0, w0;
-        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
-        int kcol = 0;
-        for (int s = 0; s < p.n_seg; ++s) {
-          const SegDev sg = p.seg[s];
-          for (int c = 0; c < sg.c_chunks; ++c, ++g) {
-            if ((g & 1) == par) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              if constexpr (CTA2) {
-                if (elect_one()) {
-                  // both CTAs signal the LEADER's full barrier (shared::cluster address of rank 0)
-                  const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-#if URSO_DEBUG_KNOBS
-                  if (p.dbg_no_tma && g >= kStages) {
-                    mbar_arrive_cluster(fb);      // isolation: keep the handshake, skip the loads
-                  } else
-#endif
-                  {
-                  mbar_arrive_expect_tx_cluster(fb, kATileBytes + kBTileBytes);
-                  tma_load_4d_2cta(sA + stage * kATileBytes, &p.a_maps[sg.map_id], fb, c * kBlockK, w0 + sg.dw, h0 + sg.dh,
-                                   img);
-                  tma_load_2d_2cta(sB + stage * kBTileBytes, &p.b_half_map, fb, kcol,
-                                   n_tile * BLOCK_N + (int)pair_rank * (BLOCK_N / 2));
-                  }
-                }
-              } else
-#if URSO_DEBUG_KNOBS
-              if (p.dbg_no_tma && g >= kStages) {
-                if (elect_one()) mbar_arrive(&full_bar[stage]);
-              } else
-#endif
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&full_bar[stage], kATileBytes + kBTileBytes);
-                tma_load_4d(sA + stage * kATileBytes, &p.a_maps[sg.map_id], &full_bar[stage], c * kBlockK, w0 + sg.dw,
-                            h0 + sg.dh, img);
-                if (p.cluster)   // my half of the weight tile, delivered to both CTAs of the pair
-                  tma_load_2d_mcast(sB + stage * kBTileBytes + crank * (kBTileBytes / 2), &p.b_half_map, &full_bar[stage],
-                                    kcol, n_tile * BLOCK_N + crank * (BLOCK_N / 2), (uint16_t)3);
-                else
-                  tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &full_bar[stage], kcol, n_tile * BLOCK_N);
-              }
-              __syncwarp();
-            }
-            kcol += kBlockK;
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || (warp == 2 && npipe == 2)) {
+    // ------------------------------------------------------------------ MMA issuers (one per pipeline)
+    const int pipe = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
     // descriptor = constant high word | (smem address >> 4); advancing K by 16 elements (32 B) adds 2 to the low word
     constexpr uint64_t kDescHiB = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t a_base = smem_u32(smem + pipe * p.pipe_bytes);
+    const uint32_t b_base = a_base + p.b_ring_off;
+    uint64_t* fullb = full_bar + pipe * kMaxStages;
+    uint64_t* emptyb = empty_bar + pipe * kMaxStages;
+    uint64_t* tfullb = tfull_bar + pipe * 2;
+    uint64_t* temptyb = tempty_bar + pipe * 2;
+    const int kStages = p.stages;
     if (p.halo) {
+      uint64_t* afullb = afull_bar + pipe * 4;
+      uint64_t* aemptyb = aempty_bar + pipe * 4;
       int stage = 0, a_stage = 0;
       uint32_t phase = 0, a_phase = 0;
       const int c_chunks = p.seg[0].c_chunks;
       // next 8-pixel group = next patch row = halo_w smem rows further
       const uint64_t desc_hi_a = (uint64_t((p.halo_w * 128) >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
-      int it = 0;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+      const uint32_t bres_base = smem_u32(smem + p.bres_off);
+      if (p.bres) {
+        mbar_wait(bres_bar, 0);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      }
+      int li = 0;
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x, ++li) {
+        const int as = li & 1;
+        mbar_wait(&temptyb[as], ((li >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (pipe * 2 + as) * BLOCK_N;
         for (int c = 0; c < c_chunks; ++c) {
-          mbar_wait(&afull_bar[a_stage], a_phase);
+          mbar_wait(&afullb[a_stage], a_phase);
+          tc_fence_after();
           const uint32_t a_tile = a_base + a_stage * p.a_stage_bytes;
-          for (int s = 0; s < p.n_seg; ++s) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
+          if (p.bres) {
+            // one barrier round for all taps of this channel chunk
             if (elect_one()) {
-              const SegDev sg = p.seg[s];
-              const uint32_t a_addr = a_tile + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
-              const uint64_t ad = desc_hi_a | (a_addr >> 4);
-              const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
-              umma_bf16(d_tmem, ad, bd, idesc, (c | s) != 0);
+              for (int s = 0; s < p.n_seg; ++s) {
+                const SegDev sg = p.seg[s];
+                const uint32_t a_addr = a_tile + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
+                const uint64_t ad = desc_hi_a | (a_addr >> 4);
+                const uint64_t bd = kDescHiB | ((bres_base + (s * c_chunks + c) * kBTileBytes) >> 4);
+                umma_bf16(d_tmem, ad, bd, idesc, (c | s) != 0);
 #pragma unroll
-              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
-              umma_commit(&empty_bar[stage]);
-              if (s == p.n_seg - 1) umma_commit(&aempty_bar[a_stage]);   // halo tile free once all taps retire
+                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              }
+              umma_commit(&aemptyb[a_stage]);
             }
             __syncwarp();
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
+          } else {
+            for (int s = 0; s < p.n_seg; ++s) {
+              mbar_wait(&fullb[stage], phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const SegDev sg = p.seg[s];
+                const uint32_t a_addr = a_tile + ((sg.dh - p.halo_dh_min) * p.halo_w + (sg.dw - p.halo_dw_min)) * 128;
+                const uint64_t ad = desc_hi_a | (a_addr >> 4);
+                const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
+                umma_bf16(d_tmem, ad, bd, idesc, (c | s) != 0);
+#pragma unroll
+                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                umma_commit(&emptyb[stage]);
+                if (s == p.n_seg - 1) umma_commit(&aemptyb[a_stage]);   // halo tile free once all taps retire
+              }
+              __syncwarp();
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
             }
           }
           if (++a_stage == p.a_stages) {
@@ -435,24 +413,23 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             a_phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull_bar[as]);
+        if (elect_one()) umma_commit(&tfullb[as]);
         __syncwarp();
       }
-    } else if (p.kpack >= 2) {
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       const int kp = p.kpack;
-      int ksteps = 0;
-      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
-      int it = 0;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+      const int ksteps = p.ksteps;
+      int li = 0;
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x, ++li) {
+        const int as = li & 1;
+        mbar_wait(&temptyb[as], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + (pipe * 2 + as) * BLOCK_N;
         for (int ks = 0; ks < ksteps; ks += kp) {
           const int n = ksteps - ks < kp ? ksteps - ks : kp;
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&fullb[stage], phase);
           tc_fence_after();
           if (elect_one()) {
             for (int j = 0; j < n; ++j) {
@@ -462,7 +439,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
             }
-            umma_commit(&empty_bar[stage]);   // one commit per kpack K steps
+            umma_commit(&emptyb[stage]);   // one commit per barrier round
           }
           __syncwarp();
           if (++stage == kStages) {
@@ -470,61 +447,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&tfull_bar[as]);
-        __syncwarp();
-      }
-    } else if (!CTA2 || pair_rank == 0) {     // CTA pairs: the leader issues for both CTAs
-      int stage = 0;
-      uint32_t phase = 0;
-      int ksteps = 0;
-      for (int s = 0; s < p.n_seg; ++s) ksteps += p.seg[s].c_chunks;
-      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kBlockM, BLOCK_N, 0, 0);   // M = 256 across the pair
-      int it = 0;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = kDescHiB | ((a_base + stage * kATileBytes + p.dbg_row_shift * 128) >> 4);
-            const uint64_t bd = kDescHiB | ((b_base + stage * kBTileBytes) >> 4);
-            if constexpr (CTA2) {
-#if URSO_DEBUG_KNOBS
-              if (!p.dbg_no_mma)
-#endif
-              {
-                umma_bf16_2cta(d_tmem, ad, bd, idesc2, ks != 0);
-#pragma unroll
-                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, 1u);
-              }
-              umma_commit_2cta(&empty_bar[stage]);      // the slot is free in BOTH CTAs once these MMAs retire
-            } else {
-#if URSO_DEBUG_KNOBS
-              if (!p.dbg_no_mma)
-#endif
-              {
-                umma_bf16(d_tmem, ad, bd, idesc, ks != 0);
-#pragma unroll
-                for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
-              }
-              // smem slot reusable once these MMAs retire (cluster: tell the peer too -- it multicasts into my stage)
-              if (p.cluster) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
-              else umma_commit(&empty_bar[stage]);
-            }
-          }
-          __syncwarp();
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        if (elect_one()) {                              // accumulator complete -> epilogue (of both CTAs of a pair)
-          if constexpr (CTA2) umma_commit_2cta(&tfull_bar[as]);
-          else umma_commit(&tfull_bar[as]);
-        }
+        if (elect_one()) umma_commit(&tfullb[as]);      // accumulator complete -> epilogue
         __syncwarp();
       }
     }
@@ -577,9 +500,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       uint32_t in_phase = 0;
       int it = 0;            // tiles of this CTA visited
       // every tile of the CTA is visited by BOTH warp sets (each must release the accumulator stage exactly once)
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+      for (int wk = blockIdx.x; wk < p.total_tiles; wk += gridDim.x, ++it) {
+        const int li = it >> pshift;                         // index of the tile within its pipeline
+        const int as = ((it & pshift) << 1) | (li & 1);      // accumulator stage: 2 per pipeline
+        const uint32_t aphase = (li >> 1) & 1;
         mbar_wait_relaxed(&tfull_bar[as], aphase);
         tc_fence_after();
         while (cur.valid && cur.wk == wk) {
@@ -695,20 +619,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         // all of this warp's TMEM reads of the tile are complete: release the accumulator stage (8 arrivals)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's barrier
-          else mbar_arrive(&tempty_bar[as]);
-        }
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
       if (lane == 0) tma_store_wait_all();
     } else {
       // ---------------- legacy register epilogue (fp32 output / BLOCK_N == 32)
       int it = 0;
-      for (int wk = work_first(p); wk < work_end(p); wk += work_step(p), ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+      for (int wk = blockIdx.x; wk < p.total_tiles; wk += gridDim.x, ++it) {
+        const int li = it >> pshift;
+        const int as = ((it & pshift) << 1) | (li & 1);
+        const uint32_t aphase = (li >> 1) & 1;
         int n_tile, img, h0, w0;
-        decode_tile(p, work_tile(p, wk), n_tile, img, h0, w0);
+        decode_tile(p, wk, n_tile, img, h0, w0);
         const int h = h0 + rh, w = w0 + rw;
         const bool valid = (h < p.OH) && (w < p.OW) && (img < p.NB);
         const long long o_off = (long long)img * p.out.sn + (long long)h * p.out.sh + (long long)w * p.out.sw;
@@ -814,12 +736,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   }
 
   tc_fence_before();
-  if (p.cluster) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
-  else __syncthreads();
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, kTmemCols);
-    else tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -833,31 +753,15 @@ struct urso_convgemm {
   int smem_bytes;
 };
 
-template <int BLOCK_N, bool CTA2 = false>
+template <int BLOCK_N>
 static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
-  if (h->params.cluster) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(h->grid);
-    cfg.blockDim = dim3(384);
-    cfg.dynamicSmemBytes = h->smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::conv_gemm_kernel<BLOCK_N, CTA2>, h->params));
-  } else {
-    urso::conv_gemm_kernel<BLOCK_N, CTA2><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
-  }
+  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -873,6 +777,70 @@ static int make_pix_map(CUtensorMap* out, const urso_pix& px, int C, int W, int 
   return urso::make_view_map(out, v, bw, bh);
 }
 
+// Shared-memory plan of the operand pipelines.  Returns false when the requested mode does not fit.
+namespace {
+struct PipePlan {
+  int npipe, stages, kpack, a_stages, bres;
+  int pipe_bytes, b_ring_off, bres_bytes;
+};
+
+bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, long long tiles_per_cta, PipePlan* pl) {
+  const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2;
+  // preference order: two pipelines (hides the issue-side cost of a barrier round, the bound of the N <= 128 launches),
+  // two K steps per round where the ring still gets >= 2 stages per pipeline
+  const bool dual_ok = bn <= 128 && tiles_per_cta >= 2;
+  const int cand[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+  for (int i = 0; i < 4; ++i) {
+    const int np = cand[i][0], kp = cand[i][1];
+    if (np == 2 && !dual_ok) continue;
+    if (kp == 2 && (ksteps < 4 || bn > 128)) continue;
+    if (kp == 2 && np == 2 && bn == 128) continue;     // N = 128: 4 MMAs per round already run at the full rate with 2 issuers
+    if (kp == 2 && np == 1 && epi_inputs) continue;    // measured in round 1: loses where the epilogue rings squeeze the ring
+    int stages = avail / (np * kp * step_bytes);
+    if (stages > urso::kMaxStages) stages = urso::kMaxStages;
+    const int need = (np == 2 || kp == 2) ? 2 : 2;
+    if (stages < need) continue;
+    if (np == 2 && kp == 1 && stages < 3 && avail / step_bytes >= 3) continue;   // prefer one deeper ring over two shallow ones
+    pl->npipe = np; pl->kpack = kp; pl->stages = stages; pl->a_stages = 0; pl->bres = 0; pl->bres_bytes = 0;
+    pl->b_ring_off = stages * kp * urso::kATileBytes;
+    pl->pipe_bytes = stages * kp * step_bytes;
+    return true;
+  }
+  return false;
+}
+
+bool plan_halo(int avail, int bn, int ksteps, int n_tiles_n, int a_stage_bytes, long long tiles_per_cta, PipePlan* pl) {
+  const int bt = bn * urso::kBlockK * 2;
+  const bool dual_ok = bn <= 128 && tiles_per_cta >= 2;
+  for (int np = dual_ok ? 2 : 1; np >= 1; --np) {
+    // resident weight operand: one N tile and it fits next to >= 2 halo stages per pipeline
+    if (n_tiles_n == 1 && ksteps * bt <= urso::kMaxBresBytes) {
+      int a_st = (avail - ksteps * bt) / (np * a_stage_bytes);
+      if (a_st > 3) a_st = 3;
+      if (a_st >= 2) {
+        pl->npipe = np; pl->kpack = 1; pl->stages = 1; pl->a_stages = a_st; pl->bres = 1; pl->bres_bytes = ksteps * bt;
+        pl->b_ring_off = a_st * a_stage_bytes;
+        pl->pipe_bytes = a_st * a_stage_bytes;
+        return true;
+      }
+    }
+    // streamed weight tiles: 2 halo stages + >= 3 B tiles per pipeline
+    const int per_pipe = avail / np;
+    int b_st = (per_pipe - 2 * a_stage_bytes) / bt;
+    if (b_st > urso::kMaxStages) b_st = urso::kMaxStages;
+    if (b_st >= 3) {
+      int a_st = (per_pipe - b_st * bt) / a_stage_bytes;
+      if (a_st > 3) a_st = 3;
+      pl->npipe = np; pl->kpack = 1; pl->stages = b_st; pl->a_stages = a_st; pl->bres = 0; pl->bres_bytes = 0;
+      pl->b_ring_off = a_st * a_stage_bytes;
+      pl->pipe_bytes = a_st * a_stage_bytes + b_st * bt;
+      return true;
+    }
+  }
+  return false;
+}
+}  // namespace
+
 extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t** out) {
   using namespace urso;
   URSO_REQUIRE(d != nullptr && out != nullptr, "null argument");
@@ -887,7 +855,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   auto* h = new urso_convgemm();
   ConvGemmParams& p = h->params;
   memset(&p, 0, sizeof(p));
-  int ktot = 0;
+  int ktot = 0, ksteps = 0;
   for (int s = 0; s < d->n_seg; ++s) {
     const urso_seg& sg = d->seg[s];
     if (sg.map_id < 0 || sg.map_id >= d->n_a || sg.c_chunks < 1 || sg.c_chunks * 64 > ((d->a[sg.map_id].C + 63) / 64) * 64) {
@@ -897,12 +865,14 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     }
     p.seg[s] = SegDev{(int16_t)sg.map_id, (int16_t)sg.dh, (int16_t)sg.dw, (int16_t)sg.c_chunks};
     ktot += sg.c_chunks * 64;
+    ksteps += sg.c_chunks;
   }
   if (ktot != d->b_k) {
     set_error("segments cover K=%d but b_k=%d", ktot, d->b_k);
     delete h;
     return 2;
   }
+  p.ksteps = ksteps;
   for (int i = 0; i < URSO_MAX_AMAPS; ++i) {
     const urso_view4& v = d->a[i < d->n_a ? i : 0];
     if (int rc = make_view_map(&p.a_maps[i], v, d->TW, d->TH)) {
@@ -911,77 +881,61 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     }
   }
   int bn = d->block_n;
-  if (bn == 0 && d->b_rows >= 256) {
-    if (const char* e = getenv("URSO_BN_MAX")) bn = atoi(e);   // experiments: cap the N tile
-  }
   if (bn == 0) bn = d->b_rows >= 256 && d->b_rows % 256 == 0 ? 256 : (d->b_rows >= 128 ? 128 : (d->b_rows >= 64 ? 64 : 32));
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
     set_error("block_n=%d unsupported", bn);
     delete h;
     return 2;
   }
-  // epilogue flavour and shared-memory plan
+  // epilogue flavour and its shared memory
   const int kColAcc = d->colsum != nullptr ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
   p.colacc_bytes = kColAcc;
   p.has_add = d->addend.ptr != nullptr;
   p.has_mask = d->mask.ptr != nullptr;
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
+  const int n_in = p.has_add + p.has_mask;
   int epi_bytes;
   if (p.epi_tma) {
-    // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight)
-    // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to mainloop stages.  Short-K
-    // launches are epilogue / store bound: deeper rings keep more TMA traffic in flight.
-    const int n_in = p.has_add + p.has_mask;
-    int ksteps_total = 0;
-    for (int s2 = 0; s2 < d->n_seg; ++s2) ksteps_total += d->seg[s2].c_chunks;
-    const bool heavy = ksteps_total >= 4;
-    // A depth-1 input ring exposes the full TMA latency of every chunk, a depth-2 ring costs mainloop stages.  Launches
-    // with a short K loop (<= 6 K steps: the MMAs of a tile take less time than its epilogue) are epilogue bound and get
-    // the deeper ring; long-K launches keep their stages.  Measured per layer: gpurun_out s15 (profiles/r01_progress.md).
-    const bool epi_bound = ksteps_total <= 6;
-    int min_stages = 3;
+    // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight).
+    // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to the operand pipelines.  Launches
+    // with a short K loop (<= 6 K steps: the MMAs of a tile take less time than its epilogue) are epilogue / store bound:
+    // a depth-1 input ring would expose the full TMA latency of every chunk (measured per layer in round 1).
+    const bool heavy = ksteps >= 4;
+    const bool epi_bound = ksteps <= 6;
     p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
     p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
-    if (n_in > 0 && epi_bound) {
-      p.ei_depth = 2;
-      min_stages = 2;
+    if (n_in > 0 && epi_bound) p.ei_depth = 2;
+    epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
+    const int bn_min = bn == 256 ? 128 : bn;   // the narrowest tile this launch may fall back to must still get 2 stages
+    if (p.ei_depth == 2 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
+      p.ei_depth = 1;
+      epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
     }
-    int ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
-    epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
-    {   // the narrowest tile this launch may fall back to must still get 2 mainloop stages
-      const int bn_min = bn == 256 ? 128 : bn;
-      if (p.ei_depth == 2 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
-        p.ei_depth = 1;
-        ei_bytes = 8 * p.ei_depth * n_in * kSlabBytes;
-        epi_bytes = ei_bytes + 8 * p.eo_depth * kSlabBytes;
-      }
-    }
+    const int min_stages = (n_in > 0 && epi_bound) ? 2 : 3;
     if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
   } else {
     epi_bytes = kLegacyScratchBytes;
   }
   h->block_n = bn;
-  // CTA pairs (cta_group::2): each CTA stages half of the weight tile.  Opt-in (URSO_CTA2=1) while it is being evaluated.
-  p.cta2 = 0;
-  if (const char* e = getenv("URSO_CTA2")) p.cta2 = (atoi(e) && bn == 256 && !d->halo && p.epi_tma) ? 1 : 0;
-  const int b_rows_cta = p.cta2 ? bn / 2 : bn;      // rows of B resident per CTA
-  p.kpack = 1;
-  {
-    int kst = 0;
-    for (int s2 = 0; s2 < d->n_seg; ++s2) kst += d->seg[s2].c_chunks;
-    // measured per layer (gpurun_out kp_*, profiles/r01_progress.md): a win for launches WITHOUT epilogue inputs and a
-    // long enough K loop (stem -9 %, stage-2 3x3 -10 %, bottleneck conv -26 %), a loss where the epilogue rings already
-    // squeeze the stage count (dgrad with mask / addend).  URSO_KPACK=0 disables, =2 forces it for every N <= 128 launch.
-    const bool no_epi_inputs = d->addend.ptr == nullptr && d->mask.ptr == nullptr;
-    // (4 K steps per round, URSO_KPACK=4, measured worse for the 9-K-step 3x3 layers: rounds of 4,4,1 on a 2-deep ring)
-    int want = (no_epi_inputs && kst >= 4) ? 2 : 1;
-    if (const char* e = getenv("URSO_KPACK")) want = atoi(e);
-    if ((want == 2 || want == 4) && bn <= 128 && !d->halo && !p.cta2 && kst >= 2 && getenv("URSO_CLUSTER") == nullptr)
-      p.kpack = want;
+  p.n_tiles_n = (d->b_rows + bn - 1) / bn;
+  p.tiles_w = (d->OW + d->TW - 1) / d->TW;
+  p.tiles_h = (d->OH + d->TH - 1) / d->TH;
+  const long long total = (long long)p.tiles_w * p.tiles_h * d->NB * p.n_tiles_n;
+  if (total <= 0 || total > 0x7fffffffLL) {
+    set_error("bad tile count %lld", total);
+    delete h;
+    return 2;
   }
-  int stages;
+  p.total_tiles = (int)total;
+  int sms = max_ctas();
+  if (sms <= 0) sms = 148;
+  h->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const long long tiles_per_cta = (total + h->grid - 1) / h->grid;
+  const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes - 1024;   // 1 KB: alignment of the epilogue rings
+  PipePlan pl;
+  bool planned = false;
   if (d->halo) {
-    // validate + plan the halo ring: one box per channel chunk, B tiles in their own ring
+    // validate the halo geometry: one stride-1 view, 8 x 16 patch, equal chunk counts, small tap offsets
     int dw_min = 1 << 20, dw_max = -(1 << 20), dh_min = 1 << 20, dh_max = -(1 << 20);
     bool ok = d->n_a == 1 && d->TW == 8 && d->TH == 16;
     for (int s2 = 0; s2 < d->n_seg && ok; ++s2) {
@@ -996,53 +950,45 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       delete h;
       return 2;
     }
-    p.halo = 1;
-    p.halo_w = 8 + dw_max - dw_min;
-    const int halo_h = 16 + dh_max - dh_min;
-    p.halo_dw_min = dw_min;
-    p.halo_dh_min = dh_min;
-    p.halo_bytes = p.halo_w * halo_h * 128;
-    p.a_stage_bytes = (p.halo_bytes + 1023) / 1024 * 1024;
-    p.a_stages = 3;
-    p.a_ring_bytes = p.a_stages * p.a_stage_bytes;
-    if (int rc = make_view_map(&p.a_halo_map, d->a[0], p.halo_w, halo_h)) {
-      delete h;
-      return rc;
-    }
-    const int btile = bn * kBlockK * 2;
-    stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes - p.a_ring_bytes) / btile;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 3) {
-      set_error("halo mode: not enough shared memory for the B ring (BLOCK_N=%d)", bn);
-      delete h;
-      return 2;
-    }
-  } else {
-    int stage_bytes = p.kpack * (kATileBytes + b_rows_cta * kBlockK * 2);
-    stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
-    while (stages < 2 && p.kpack > 1) {   // not enough room for two packed stages: fewer K steps per stage
-      p.kpack /= 2;
-      stage_bytes = p.kpack * (kATileBytes + b_rows_cta * kBlockK * 2);
-      stages = (kSmemBudget - kCtrlBytes - kColAcc - epi_bytes) / stage_bytes;
-    }
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) {
-      set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
-      delete h;
-      return 2;
-    }
-    p.a_ring_bytes = stages * p.kpack * kATileBytes;
+    const int halo_w = 8 + dw_max - dw_min, halo_h = 16 + dh_max - dh_min;
+    const int a_stage_bytes = (halo_w * halo_h * 128 + 1023) / 1024 * 1024;
+    if (plan_halo(avail, bn, ksteps, p.n_tiles_n, a_stage_bytes, tiles_per_cta, &pl)) {
+      planned = true;
+      p.halo = 1;
+      p.halo_w = halo_w;
+      p.halo_dw_min = dw_min;
+      p.halo_dh_min = dh_min;
+      p.halo_bytes = halo_w * halo_h * 128;
+      p.a_stage_bytes = a_stage_bytes;
+      if (int rc = make_view_map(&p.a_halo_map, d->a[0], halo_w, halo_h)) {
+        delete h;
+        return rc;
+      }
+    }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
   }
-  p.stages = stages;
-  const int fixed = p.a_ring_bytes + stages * p.kpack * (d->halo ? bn : b_rows_cta) * kBlockK * 2 + kCtrlBytes + kColAcc;
+  if (!planned && !plan_stream(avail, bn, ksteps, n_in > 0, tiles_per_cta, &pl)) {
+    set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
+    delete h;
+    return 2;
+  }
+  p.npipe = pl.npipe;
+  p.stages = pl.stages;
+  p.kpack = pl.kpack;
+  p.a_stages = pl.a_stages;
+  p.bres = pl.bres;
+  p.pipe_bytes = pl.pipe_bytes;
+  p.b_ring_off = pl.b_ring_off;
+  p.bres_off = pl.npipe * pl.pipe_bytes;
+  p.ctrl_off = p.bres_off + pl.bres_bytes;
+  const int fixed = p.ctrl_off + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
-    p.eo_off = p.ei_off + 8 * p.ei_depth * (p.has_add + p.has_mask) * kSlabBytes;
+    p.eo_off = p.ei_off + 8 * p.ei_depth * n_in * kSlabBytes;
     h->smem_bytes = p.eo_off + 8 * p.eo_depth * kSlabBytes;
   } else {
     h->smem_bytes = fixed + kLegacyScratchBytes;
   }
-  if (h->smem_bytes > 227 * 1024) {
+  if (h->smem_bytes > kSmemBudget) {
     set_error("internal: shared memory plan %d bytes exceeds 227 KB", h->smem_bytes);
     delete h;
     return 2;
@@ -1066,35 +1012,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.TW = d->TW; p.TH = d->TH;
   p.tw_shift = 0;
   while ((1 << p.tw_shift) < d->TW) ++p.tw_shift;
-  p.tiles_w = (d->OW + d->TW - 1) / d->TW;
-  p.tiles_h = (d->OH + d->TH - 1) / d->TH;
-  p.n_tiles_n = (d->b_rows + bn - 1) / bn;
   p.fd_ntn = make_fastdiv((uint32_t)p.n_tiles_n);
   p.fd_tw = make_fastdiv((uint32_t)p.tiles_w);
   p.fd_th = make_fastdiv((uint32_t)p.tiles_h);
-  long long total = (long long)p.tiles_w * p.tiles_h * d->NB * p.n_tiles_n;
-  if (total <= 0 || total > 0x7fffffffLL) {
-    set_error("bad tile count %lld", total);
-    delete h;
-    return 2;
-  }
-  p.total_tiles = (int)total;
-  {
-    // cluster pairs (experimental, URSO_CLUSTER=1): measured slower on every layer -- a 2-CTA multicast does not reduce
-    // L2 -> SM traffic (the L2 already de-duplicates near-simultaneous unicast requests), see profiles/r01_progress.md
-    int want = 0;
-    if (const char* e = getenv("URSO_CLUSTER")) want = atoi(e) && !p.halo && total >= 64;
-    if (p.cta2) want = 1;
-    if (want) {
-      const long long mt = (long long)p.tiles_w * p.tiles_h * d->NB;
-      p.cluster = 1;
-      p.total_pairs = (int)(((mt + 1) / 2) * p.n_tiles_n);
-      if (int rc = make_mat_map(&p.b_half_map, d->b, d->b_rows, d->b_k, bn / 2)) {
-        delete h;
-        return rc;
-      }
-    }
-  }
   p.ncols = d->b_rows;
   p.out = PixDev{d->out.ptr, d->out.sn, d->out.sh, d->out.sw};
   p.addend = PixDev{d->addend.ptr, d->addend.sn, d->addend.sh, d->addend.sw};
@@ -1103,17 +1023,6 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.relu = d->relu;
   p.shift = d->shift;
   p.colsum = d->colsum;
-  if (const char* e = getenv("URSO_DBG_NO_TMA")) p.dbg_no_tma = atoi(e);
-  if (const char* e = getenv("URSO_DBG_NO_MMA")) p.dbg_no_mma = atoi(e);
-  if (const char* e = getenv("URSO_DBG_ROW_SHIFT")) p.dbg_row_shift = atoi(e);
-  if (const char* e = getenv("URSO_DBG_BASE_OFFSET")) p.dbg_base_offset = atoi(e);
-  int sms = num_sms();
-  if (sms <= 0) sms = 148;
-  h->grid = p.total_tiles < sms ? p.total_tiles : sms;
-  if (p.cluster) {
-    const int nclusters = p.total_pairs < sms / 2 ? p.total_pairs : sms / 2;
-    h->grid = 2 * nclusters;
-  }
   *out = h;
   return 0;
 }
@@ -1125,10 +1034,19 @@ extern "C" int urso_convgemm_launch(urso_convgemm_t* h, void* stream) {
     case 32: return launch_conv_gemm<32>(h, s);
     case 64: return launch_conv_gemm<64>(h, s);
     case 128: return launch_conv_gemm<128>(h, s);
-    case 256: return h->params.cta2 ? launch_conv_gemm<256, true>(h, s) : launch_conv_gemm<256>(h, s);
+    case 256: return launch_conv_gemm<256>(h, s);
   }
   urso::set_error("unsupported BLOCK_N %d", h->block_n);
   return 2;
 }
 
 extern "C" void urso_convgemm_destroy(urso_convgemm_t* h) { delete h; }
+
+/* plan introspection (tests / profiling): writes {block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid} */
+extern "C" int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9) {
+  URSO_REQUIRE(h != nullptr && out9 != nullptr, "null argument");
+  const urso::ConvGemmParams& p = h->params;
+  const int32_t v[9] = {h->block_n, p.npipe, p.stages, p.kpack, p.halo, p.bres, p.a_stages, h->smem_bytes, h->grid};
+  for (int i = 0; i < 9; ++i) out9[i] = v[i];
+  return 0;
+}

@@ -62,6 +62,16 @@ void pick_patch(int oh, int ow, int npix, int* tw_out, int* th_out) {
   }
 }
 
+// Halo mode of Engine F (one TMA box per channel chunk feeds every filter tap from shared memory) wants an 8 x 16 pixel
+// patch; take it when that patch covers the map with at most 7 % more pixels than the best patch would.
+bool halo_patch_ok(int oh, int ow) {
+  int tw, th;
+  pick_patch(oh, ow, 128, &tw, &th);
+  const long long best = (long long)((ow + tw - 1) / tw) * tw * ((oh + th - 1) / th) * th;
+  const long long halo = (long long)((ow + 7) / 8) * 8 * ((oh + 15) / 16) * 16;
+  return halo * 100 <= best * 107;
+}
+
 struct Tap {
   int tap, map, dh, dw;
 };
@@ -191,6 +201,9 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
     idx = stem_weight_index(3);
     cd.OW = g.ow; cd.OH = g.oh; cd.NB = s.N;
     pick_patch(g.oh, g.ow, 128, &cd.TW, &cd.TH);
+    if (halo_patch_ok(g.oh, g.ow)) {    // the 4 row taps read one (16+3) x 8 box
+      cd.TW = 8; cd.TH = 16; cd.halo = 1;
+    }
     cd.out = dense_pix(d->y, g.oh, g.ow, s.K);
   } else {
     URSO_REQUIRE(s.C % 64 == 0, "input channels %d must be a multiple of 64", s.C);
@@ -223,6 +236,9 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
       }
       cd.OW = g.ow; cd.OH = g.oh; cd.NB = s.N;
       pick_patch(g.oh, g.ow, 128, &cd.TW, &cd.TH);
+      if (s.stride == 1 && s.ksize == 3 && halo_patch_ok(g.oh, g.ow)) {
+        cd.TW = 8; cd.TH = 16; cd.halo = 1;
+      }
       cd.out = dense_pix(d->y, g.oh, g.ow, yc);
       cd.addend = d->addend ? dense_pix(d->addend, g.oh, g.ow, yc) : kNoPix;
     }
@@ -255,6 +271,10 @@ extern "C" int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream)
 extern "C" int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_launch(h->plan, stream);
+}
+extern "C" int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9) {
+  URSO_REQUIRE(h != nullptr, "null handle");
+  return urso_convgemm_plan_info(h->plan, out9);
 }
 extern "C" void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h) {
   if (h == nullptr) return;
@@ -417,6 +437,9 @@ extern "C" int urso_conv2d_dgrad_create(const urso_conv2d_dgrad_desc* d, urso_co
       const int th_ = (H - ph.oph + stride - 1) / stride, tw_ = (W - ph.opw + stride - 1) / stride;
       cd.OW = tw_; cd.OH = th_; cd.NB = N;
       pick_patch(th_, tw_, 128, &cd.TW, &cd.TH);
+      if (stride == 1 && d->n_convs == 1 && d->shape[0].ksize == 3 && halo_patch_ok(th_, tw_)) {
+        cd.TW = 8; cd.TH = 16; cd.halo = 1;
+      }
       cd.out = strided_pix(d->dx, H, W, cin, ph.oph, ph.opw, stride, 2);
       cd.mask = d->mask ? strided_pix(d->mask, H, W, cin, ph.oph, ph.opw, stride, 2) : kNoPix;
       cd.addend = d->addend ? strided_pix(d->addend, H, W, cin, 0, 0, 1, 2) : kNoPix;

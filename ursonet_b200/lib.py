@@ -76,11 +76,13 @@ SIGNATURES = {
     "urso_version": [],
     "urso_last_error": [],
     "urso_num_sms": [],
+    "urso_set_max_ctas": [_i32],
     "urso_sizeof_convgemm_desc": [],
     "urso_sizeof_wgrad_desc": [],
     "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
     "urso_convgemm_launch": [_vp, _vp],
     "urso_convgemm_destroy": [_vp],
+    "urso_convgemm_plan_info": [_vp, C.POINTER(_i32)],
     "urso_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(_vp)],
     "urso_wgrad_launch": [_vp, _vp],
     "urso_wgrad_destroy": [_vp],
@@ -93,6 +95,7 @@ SIGNATURES = {
     "urso_conv2d_fwd_stage_weights": [_vp, _vp],
     "urso_conv2d_fwd_launch": [_vp, _vp],
     "urso_conv2d_fwd_destroy": [_vp],
+    "urso_conv2d_fwd_plan_info": [_vp, C.POINTER(_i32)],
     "urso_conv2d_dgrad_workspace_bytes": [C.POINTER(Conv2dDgradDesc)],
     "urso_conv2d_dgrad_create": [C.POINTER(Conv2dDgradDesc), C.POINTER(_vp)],
     "urso_conv2d_dgrad_stage_weights": [_vp, _vp],
@@ -132,7 +135,7 @@ SIGNATURES = {
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
-             "urso_same_pad": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
              "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
              "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
@@ -236,6 +239,12 @@ class ConvGemm:
     def launch(self):
         check(load().urso_convgemm_launch(self._h, stream_ptr()), "urso_convgemm_launch")
 
+    def plan_info(self):
+        """dict(block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid) of the planned launch."""
+        v = (_i32 * 9)()
+        check(load().urso_convgemm_plan_info(self._h, v), "urso_convgemm_plan_info")
+        return dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem_bytes", "grid"), v))
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.urso_convgemm_destroy(self._h)
@@ -322,6 +331,12 @@ class Conv2dFwd:
 
     def stage(self):
         check(load().urso_conv2d_fwd_stage_weights(self._h, stream_ptr()), "urso_conv2d_fwd_stage_weights")
+
+    def plan_info(self):
+        """Planned Engine-F launch: dict(block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid)."""
+        v = (_i32 * 9)()
+        check(load().urso_conv2d_fwd_plan_info(self._h, v), "urso_conv2d_fwd_plan_info")
+        return dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem_bytes", "grid"), v))
 
     def launch(self):
         check(load().urso_conv2d_fwd_launch(self._h, stream_ptr()), "urso_conv2d_fwd_launch")
