@@ -261,7 +261,7 @@ def main():
     agg = {}
     for r in prof:
         a = agg.setdefault(r["kind"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
-        a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
+        a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += r.get("launches", 1)
     if args.profile_json:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_json)), exist_ok=True)
         json.dump({"per_launch": prof, "by_kind": agg}, open(args.profile_json, "w"), indent=1)

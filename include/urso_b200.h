@@ -26,6 +26,9 @@ int urso_num_sms(void);
 /* Limit the persistent Engine-F grids planned from now on to n CTAs (0 = one per SM): leaves SMs free for kernels that
  * must run concurrently (an overlapped NCCL all-reduce), and lets tests exercise deep per-CTA tile queues at small sizes. */
 void urso_set_max_ctas(int n);
+/* Dry run (tests of the host-side planners on a machine without a GPU): while on, *_create calls plan tiles, shared
+ * memory and pipelines for a 148-SM device but encode no tensor maps and touch no device memory; launches fail. */
+void urso_set_dry_run(int on);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);
@@ -276,6 +279,10 @@ int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const fl
  * chunk_coef[i] applies to elements [256 i, 256 i + 256): reg gradient 2*wd/size(w) (0 for gamma/beta);
  * chunk_lr[i] is 1 for trainable chunks, 0 for frozen ones (their gradient is zeroed and excluded from the norm).
  * hyper_dev (device fp32[8]): [0]=lr (Adam: lr_t), [1]=momentum|beta1, [2]=beta2, [3]=eps, [4]=clipnorm.        */
+/* Gradient accumulation over micro-batches (BASELINE configs[4]: global batch 256 on fewer than 8 GPUs):
+ * acc = beta * acc + grad (beta = 0 on the first micro-batch); when out != NULL the result alpha * acc is written to out
+ * (the last micro-batch: out = the gradient arena, alpha = 1 / number of micro-batches) and acc is left untouched. */
+int urso_grad_accumulate(float* acc, const float* grad, float* out, float beta, float alpha, int64_t n, void* stream);
 int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef, const float* chunk_lr,
                        float grad_scale, float* sumsq_out, int64_t n, void* stream);
 int urso_sgd_step(float* param, float* vel, const float* grad, const float* chunk_lr, const float* sumsq,

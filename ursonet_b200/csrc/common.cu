@@ -6,6 +6,7 @@
 namespace urso {
 
 static thread_local std::string g_err;
+static int g_dry_run = 0;    // urso_set_dry_run: plan only (no tensor-map encoding, no device access)
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -18,6 +19,7 @@ void set_error(const char* fmt, ...) {
 
 int num_sms() {
   static int n = 0;
+  if (g_dry_run) return 148;      // planning without a device: assume a B200
   if (n == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -27,6 +29,7 @@ int num_sms() {
 }
 
 static int g_max_ctas = 0;
+bool dry_run() { return g_dry_run != 0; }
 int max_ctas() {
   const int n = num_sms();
   return (g_max_ctas > 0 && g_max_ctas < n) ? g_max_ctas : n;
@@ -46,6 +49,7 @@ encode_tiled_fn get_encode_tiled() {
 }
 
 int make_view_map(CUtensorMap* out, const urso_view4& v, int box_w, int box_h) {
+  if (dry_run()) return 0;
   encode_tiled_fn enc = get_encode_tiled();
   URSO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   URSO_REQUIRE(v.base != nullptr && (reinterpret_cast<uintptr_t>(v.base) & 15) == 0, "view base must be 16B aligned");
@@ -66,6 +70,7 @@ int make_view_map(CUtensorMap* out, const urso_view4& v, int box_w, int box_h) {
 }
 
 int make_mat_map(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int box_rows) {
+  if (dry_run()) return 0;
   encode_tiled_fn enc = get_encode_tiled();
   URSO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   URSO_REQUIRE(base != nullptr && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "matrix base must be 16B aligned");
@@ -89,6 +94,7 @@ int urso_version(void) { return 100; }
 const char* urso_last_error(void) { return urso::g_err.c_str(); }
 int urso_num_sms(void) { return urso::num_sms(); }
 void urso_set_max_ctas(int n) { urso::g_max_ctas = n; }
+void urso_set_dry_run(int on) { urso::g_dry_run = on; }
 int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
 int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }
 }

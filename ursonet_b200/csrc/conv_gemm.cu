@@ -931,12 +931,13 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   if (sms <= 0) sms = 148;
   h->grid = p.total_tiles < sms ? p.total_tiles : sms;
   const long long tiles_per_cta = (total + h->grid - 1) / h->grid;
-  const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes - 1024;   // 1 KB: alignment of the epilogue rings
   PipePlan pl;
   bool planned = false;
+  int halo_w = 0, halo_h = 0, dw_min = 0, dh_min = 0;
   if (d->halo) {
     // validate the halo geometry: one stride-1 view, 8 x 16 patch, equal chunk counts, small tap offsets
-    int dw_min = 1 << 20, dw_max = -(1 << 20), dh_min = 1 << 20, dh_max = -(1 << 20);
+    int dw_max = -(1 << 20), dh_max = -(1 << 20);
+    dw_min = dh_min = 1 << 20;
     bool ok = d->n_a == 1 && d->TW == 8 && d->TH == 16;
     for (int s2 = 0; s2 < d->n_seg && ok; ++s2) {
       ok = d->seg[s2].map_id == 0 && d->seg[s2].c_chunks == d->seg[0].c_chunks;
@@ -950,26 +951,43 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       delete h;
       return 2;
     }
-    const int halo_w = 8 + dw_max - dw_min, halo_h = 16 + dh_max - dh_min;
-    const int a_stage_bytes = (halo_w * halo_h * 128 + 1023) / 1024 * 1024;
-    if (plan_halo(avail, bn, ksteps, p.n_tiles_n, a_stage_bytes, tiles_per_cta, &pl)) {
-      planned = true;
-      p.halo = 1;
-      p.halo_w = halo_w;
-      p.halo_dw_min = dw_min;
-      p.halo_dh_min = dh_min;
-      p.halo_bytes = halo_w * halo_h * 128;
-      p.a_stage_bytes = a_stage_bytes;
-      if (int rc = make_view_map(&p.a_halo_map, d->a[0], halo_w, halo_h)) {
-        delete h;
-        return rc;
-      }
-    }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
+    halo_w = 8 + dw_max - dw_min;
+    halo_h = 16 + dh_max - dh_min;
   }
-  if (!planned && !plan_stream(avail, bn, ksteps, n_in > 0, tiles_per_cta, &pl)) {
+  // Plan the operand pipelines in what the epilogue leaves; if nothing fits, shrink the epilogue rings to depth 1 and retry.
+  // (All regions are multiples of 1 KB, so the epilogue rings need no alignment slack.)
+  for (int attempt = 0; attempt < 2 && !planned; ++attempt) {
+    if (attempt == 1) {
+      if (!p.epi_tma || (p.ei_depth == 1 && p.eo_depth == 1)) break;
+      p.ei_depth = p.eo_depth = 1;
+      epi_bytes = 8 * n_in * kSlabBytes + 8 * kSlabBytes;
+    }
+    const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes;
+    if (d->halo) {
+      const int a_stage_bytes = (halo_w * halo_h * 128 + 1023) / 1024 * 1024;
+      if (plan_halo(avail, bn, ksteps, p.n_tiles_n, a_stage_bytes, tiles_per_cta, &pl)) {
+        planned = true;
+        p.halo = 1;
+        p.halo_w = halo_w;
+        p.halo_dw_min = dw_min;
+        p.halo_dh_min = dh_min;
+        p.halo_bytes = halo_w * halo_h * 128;
+        p.a_stage_bytes = a_stage_bytes;
+        continue;
+      }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
+    }
+    planned = plan_stream(avail, bn, ksteps, n_in > 0, tiles_per_cta, &pl);
+  }
+  if (!planned) {
     set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
     delete h;
     return 2;
+  }
+  if (p.halo) {
+    if (int rc = make_view_map(&p.a_halo_map, d->a[0], halo_w, halo_h)) {
+      delete h;
+      return rc;
+    }
   }
   p.npipe = pl.npipe;
   p.stages = pl.stages;
@@ -1029,6 +1047,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
 
 extern "C" int urso_convgemm_launch(urso_convgemm_t* h, void* stream) {
   URSO_REQUIRE(h != nullptr, "null handle");
+  URSO_REQUIRE(!urso::dry_run(), "dry run: nothing can be launched");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (h->block_n) {
     case 32: return launch_conv_gemm<32>(h, s);

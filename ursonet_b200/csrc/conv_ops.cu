@@ -141,6 +141,7 @@ std::vector<int32_t> stem_weight_index(int cin) {
 }
 
 int upload_i32(void* dst, const std::vector<int32_t>& v) {
+  if (urso::dry_run()) return 0;
   URSO_CUDA_OK(cudaMemcpy(dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   return 0;
 }

@@ -309,6 +309,19 @@ __global__ void split_f32_kernel(const float* __restrict__ y, const float* __res
   }
 }
 
+// Gradient accumulation over micro-batches: acc = beta * acc + grad; out = alpha * acc (if out).  16-byte vectors.
+__global__ void grad_accumulate_kernel(float* acc, const float* grad, float* out,   // out may alias grad
+                                       float beta, float alpha, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta != 0.f) a = reinterpret_cast<const float4*>(acc)[i];
+    a.x = beta * a.x + g.x; a.y = beta * a.y + g.y; a.z = beta * a.z + g.z; a.w = beta * a.w + g.w;
+    if (out != nullptr) reinterpret_cast<float4*>(out)[i] = make_float4(alpha * a.x, alpha * a.y, alpha * a.z, alpha * a.w);
+    else reinterpret_cast<float4*>(acc)[i] = a;
+  }
+}
+
 static inline int grid_for_p(long long n, int block, int max_blocks) {
   long long g = (n + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -376,6 +389,15 @@ int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const fl
   if (gamma != nullptr || dbias != nullptr)
     bn_param_finalize_kernel<<<(CO + 127) / 128, 128, 0, st>>>(s_scratch, colsum, scale, gamma, mean, var, bias, eps,
                                                               dbias, dgamma, dbeta, CO);
+  URSO_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int urso_grad_accumulate(float* acc, const float* grad, float* out, float beta, float alpha, int64_t n, void* stream) {
+  URSO_REQUIRE(acc && grad, "null pointer");
+  URSO_REQUIRE(n % 4 == 0, "n must be a multiple of 4 (the arenas are 256-element aligned)");
+  grad_accumulate_kernel<<<grid_for_p(n / 4, 256, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, grad, out, beta, alpha, n / 4);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -472,6 +472,7 @@ class Engine:
         order = [c.dst for c in g.convs]
         order.insert(1, "pool1")
         self.dgrad_ops = {}
+        self.dgrad_meta = []     # == graph.backward_groups(self.graph)[0] (checked by the tests)
         self._bwd_root = None
         self._bwd_split = None
         for X in reversed(order):
@@ -571,6 +572,8 @@ class Engine:
             assert (box["p"].untouched == 0b1110) == only_phase0, (X, box["p"].untouched)
         self._late_binds.append(bind)
         self.dgrad_ops[X] = box
+        self.dgrad_meta.append(dict(X=X, convs=convs, add=adds[0].dst if adds else None, mask=mask is not None,
+                                    colsum=key is not None, sparse_in=sparse_in, stride=stride, only_phase0=only_phase0))
         if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)
 
@@ -856,6 +859,33 @@ class Engine:
         self.gt_ori.copy_(self._st[2], non_blocking=True)
         self._ev_free.record(main)
 
+    grad_acc = None
+
+    def accumulate(self, micro, n_micro, use_graph=True):
+        """Forward + losses + backward of micro-batch `micro` (0-based) of `n_micro` on the current input / label buffers.
+        Gradients of the micro-batches are averaged: after the last one `self.grads` holds the mean (what one step on
+        the concatenated batch gives for the per-sample-mean losses; rel_loss is normalised per micro-batch, like per
+        shard under data parallelism).  Global batch 256 on one GPU = 8 micro-batches of 32 (BASELINE configs[4])."""
+        assert self.training and 0 <= micro < n_micro
+        self._replay("train", self._phase_train, use_graph)
+        if n_micro > 1:
+            if self.grad_acc is None:
+                self.grad_acc = torch.zeros_like(self.grads)
+            last = micro == n_micro - 1
+            lib.call("urso_grad_accumulate", self.grad_acc.data_ptr(), self.grads.data_ptr(),
+                     self.grads.data_ptr() if last else None, 0.0 if micro == 0 else 1.0, 1.0 / n_micro,
+                     self.grads.numel(), lib.stream_ptr())
+
+    def apply_update(self, lr, allreduce=None, use_graph=True, allreduce_async=None):
+        """All-reduce of the flat gradient arena (if any) + regulariser + global-norm clip + optimizer step."""
+        self.set_hyper(lr)
+        if allreduce_async is not None:
+            allreduce_async(self.grads).wait()
+        elif allreduce is not None:
+            allreduce(self.grads)
+        self._replay("update", self._phase_update, use_graph)
+        self.opt_t += 1
+
     def train_step(self, lr, allreduce=None, use_graph=True, allreduce_async=None):
         """One optimisation step on the current input/label buffers: fwd + loss + bwd (graph A), all-reduce of the flat
         gradient arena, regulariser + clip + update (graph B).  `allreduce(t)` reduces in place on the current stream;
@@ -863,8 +893,8 @@ class Engine:
         schedule: backward is replayed in two graphs and the all-reduce of the arena tail (>= 90 % of the parameters,
         whose gradients are complete first) runs on NCCL's stream while the rest of backward executes."""
         assert self.training
-        self.set_hyper(lr)
         if allreduce_async is not None and self._bwd_split is not None:
+            self.set_hyper(lr)
             off = self._bwd_split[1]
             if use_graph and "train_a" not in self._graphs:
                 self._phase_train()    # eager warm-up of EVERY kernel; part B alone is not idempotent (it accumulates
@@ -875,14 +905,11 @@ class Engine:
             w2 = allreduce_async(self.grads[:off])
             w1.wait()
             w2.wait()
+            self._replay("update", self._phase_update, use_graph)
+            self.opt_t += 1
         else:
-            self._replay("train", self._phase_train, use_graph)
-            if allreduce_async is not None:
-                allreduce_async(self.grads).wait()
-            elif allreduce is not None:
-                allreduce(self.grads)
-        self._replay("update", self._phase_update, use_graph)
-        self.opt_t += 1
+            self.accumulate(0, 1, use_graph)
+            self.apply_update(lr, allreduce, use_graph, allreduce_async)
 
     def count_launches(self, train=True):
         """Kernels of liburso_b200.so launched per train step (or per forward): bench.py's gpu_launches."""
@@ -920,5 +947,5 @@ class Engine:
             if not isinstance(op, OpRec):
                 continue
             ms = min(a.elapsed_time(b) for a, b in recs[i])
-            out.append(dict(kind=op.kind, name=op.name, ms=ms, flops=op.flops, bytes=op.bytes))
+            out.append(dict(kind=op.kind, name=op.name, ms=ms, flops=op.flops, bytes=op.bytes, launches=op.launches))
         return out

@@ -176,3 +176,40 @@ def weight_entries(g: Graph):
         out.append((d.name + "/kernel", (d.cin, d.cout), True, True))
         out.append((d.name + "/bias", (d.cout,), True, True))
     return out
+
+
+def backward_groups(g: Graph, sparse_bwd: bool = True):
+    """The input-gradient launches of the backward plan as data (what Engine._build_backward builds, without a device):
+    one group per activation buffer X, in processing (reverse production) order:
+      dict(X, convs=[ConvSpec consumers], add=name of the buffer whose gradient arrives through an identity shortcut,
+           mask=bool (X is a ReLU output, or pool1), colsum=bool (the producer of X needs d beta / d bias),
+           sparse_in=bool (all consumers' output gradients live on even-even pixels only), stride=effective stride,
+           only_phase0=bool).  Also returns the set of buffers whose own gradient is sparse."""
+    producers = {c.dst: c for c in g.convs}
+    cons_conv, cons_add = {}, {}
+    for c in g.convs:
+        cons_conv.setdefault(c.src, []).append(c)
+        if c.addend:
+            cons_add.setdefault(c.addend, []).append(c)
+    order = [c.dst for c in g.convs]
+    order.insert(1, "pool1")
+    sparse, groups = set(), []
+    for X in reversed(order):
+        if X == "bottleneck_layer" or X == g.pool_src:
+            continue
+        convs, adds = cons_conv.get(X, []), cons_add.get(X, [])
+        if not convs and len(adds) == 1 and X not in g.relu_buffers:
+            continue           # linear shortcut branch: aliases its consumer's gradient
+        prod = producers.get(X)
+        need_cs = prod is not None and bool(prod.bias or prod.bn or prod.addend in
+                                            [c.dst for c in g.convs if not c.relu and (c.bias or c.bn)])
+        sparse_in = sparse_bwd and all(c.dst in sparse and c.stride == 1 for c in convs)
+        stride = convs[0].stride * (2 if sparse_in else 1)
+        only_phase0 = stride == 2 and all(c.k == 1 for c in convs)
+        h, w, _ = g.shapes[X]
+        groups.append(dict(X=X, convs=convs, add=adds[0].dst if adds else None,
+                           mask=(X in g.relu_buffers or X == "pool1"), colsum=need_cs, sparse_in=sparse_in,
+                           stride=stride, only_phase0=only_phase0))
+        if sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
+            sparse.add(X)
+    return groups, sparse

@@ -77,6 +77,7 @@ SIGNATURES = {
     "urso_last_error": [],
     "urso_num_sms": [],
     "urso_set_max_ctas": [_i32],
+    "urso_set_dry_run": [_i32],
     "urso_sizeof_convgemm_desc": [],
     "urso_sizeof_wgrad_desc": [],
     "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
@@ -120,6 +121,7 @@ SIGNATURES = {
     "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp],
     "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
     "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 5 + [_i32, _i32, _vp],
+    "urso_grad_accumulate": [_vp, _vp, _vp, _f32, _f32, _i64, _vp],
     "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "urso_amsgrad_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
@@ -135,7 +137,7 @@ SIGNATURES = {
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
-             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
              "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
              "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
