@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--height", type=int, default=600)
     ap.add_argument("--ori_resolution", type=int, default=16)
     ap.add_argument("--regress_ori", action="store_true", help="quaternion regression head (BASELINE configs[2])")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch (BASELINE configs[4]: 256): each rank takes global/N images per step as "
+                         "micro-batches of --batch with gradient accumulation; reported as strong scaling")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -183,6 +186,13 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_micro = 1
+    if args.global_batch:
+        per_rank = args.global_batch // world
+        assert per_rank * world == args.global_batch and per_rank % min(args.batch, per_rank) == 0, "global batch must split evenly"
+        args.batch = min(args.batch, per_rank)
+        n_micro = per_rank // args.batch
+        workload += f", global batch {args.global_batch} = {world} ranks x {n_micro} micro-batches x {args.batch}"
     eng = Engine(cfg, args.batch, training=True, world_size=world, seed=0)
     img, loc, ori = synth_batch(cfg, args.batch, seed=rank)
     h_img, h_loc, h_ori = img.pin_memory(), loc.pin_memory(), ori.pin_memory()
@@ -203,8 +213,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def train_step():
+        if n_micro == 1:
+            eng.train_step(lr, allreduce, use_graph, ar_async)
+        else:       # gradient accumulation: n_micro x (fwd + bwd), then ONE all-reduce + update
+            for m in range(n_micro):
+                eng.accumulate(m, n_micro, use_graph)
+            eng.apply_update(lr, allreduce, use_graph, ar_async)
+
     for _ in range(max(args.warmup, 3)):
-        eng.train_step(lr, allreduce, use_graph, ar_async)
+        train_step()
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     barrier()
@@ -213,7 +231,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        eng.train_step(lr, allreduce, use_graph, ar_async)
+        train_step()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -221,7 +239,8 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     t_ms = t_ms.item()
-    value = world * args.batch * args.steps / (t_ms / 1e3)
+    imgs_per_step = world * args.batch * n_micro
+    value = imgs_per_step * args.steps / (t_ms / 1e3)
     # ---------------- timed region 2: end to end through the public step API with host buffers
     losses_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
@@ -231,10 +250,16 @@ def main():
     e2.record()
     eng.upload_async(h_img, h_loc, h_ori)               # first batch; every later upload overlaps the previous step
     for i in range(args.steps):
-        eng.swap_in()                                   # uploaded batch -> the buffers the graphs read (waits for the H2D)
-        if i + 1 < args.steps:
-            eng.upload_async(h_img, h_loc, h_ori)       # next step's H2D (59 MB from pinned memory) on the copy stream
-        eng.train_step(lr, allreduce, use_graph, ar_async)
+        for m in range(n_micro):
+            eng.swap_in()                               # uploaded batch -> the buffers the graphs read (waits for the H2D)
+            if i + 1 < args.steps or m + 1 < n_micro:
+                eng.upload_async(h_img, h_loc, h_ori)   # next (micro-)batch's H2D (59 MB from pinned memory) on the copy stream
+            if n_micro == 1:
+                eng.train_step(lr, allreduce, use_graph, ar_async)
+            else:
+                eng.accumulate(m, n_micro, use_graph)
+        if n_micro > 1:
+            eng.apply_update(lr, allreduce, use_graph, ar_async)
         losses_host[i & 1].copy_(eng.losses, non_blocking=True)      # D2H of this step's losses (pinned, async)
         loss_ev[i & 1].record()
         if i > 0:                                       # the host reads EVERY step's losses, one step behind the GPU,
@@ -247,8 +272,8 @@ def main():
     t2 = torch.tensor([e2.elapsed_time(e3)], device="cuda")
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.batch * args.steps / (t2.item() / 1e3)
-    h2d = h_img.numel() + 4 * h_loc.numel() + 4 * h_ori.numel()
+    e2e_value = imgs_per_step * args.steps / (t2.item() / 1e3)
+    h2d = n_micro * (h_img.numel() + 4 * h_loc.numel() + 4 * h_ori.numel())
     loss_vals = loss_log[-1]
     assert len(loss_log) == args.steps
 
@@ -288,15 +313,17 @@ def main():
                 "step_frac_of_tensor_peak": value / world * TRAIN_GFLOP_PER_IMG / 1e3 / peak_tf
                 if args.backbone == "resnet50" and args.width == 960 else None}
     out = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True,
+           "scaling": "strong" if args.global_batch else "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": workload, "parallelism": f"dp{world}", "global_batch": world * args.batch,
+           "config": {"workload": workload, "parallelism": f"dp{world}", "global_batch": imgs_per_step,
+                      "micro_batches_per_step": n_micro,
                       "l2": "per-step working set (bf16 activations + gradients, >8 GB at batch 32) >> 126 MB L2: no flush needed",
                       "cuda_graphs": use_graph, "weights": "Keras-default random init (--weights none)"},
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                    "ms_per_step": t2.item() / args.steps},
-           "gpu_launches": eng.count_launches(True) * args.steps,
+           "gpu_launches": ((eng.count_launches(True) - 2) * n_micro + 2 + (n_micro if n_micro > 1 else 0)) * args.steps,
            "roofline": roofline, "losses_last_step": loss_vals}
     if not args.no_cpu_baseline and world == 1:
         rate, ms, done, B, cores = cpu_reference_step_rate(cfg, 2, 0, budget_s=20.0)

@@ -96,3 +96,22 @@ def test_missing_extension_fails_loudly(monkeypatch):
     monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/liburso_b200.so")
     with pytest.raises(lib.UrsoError, match="no CPU / eager fallback"):
         lib.load()
+
+
+def test_f16_flag_runs_on_the_16_bit_engine(workdir):
+    """--f16 (net.py:590-593) is served by the bf16-storage engine with the reference's fp16 Adam epsilon."""
+    model = run_cli(workdir, "train", "--weights", "none", "--batch_size", "1", "--epochs", "1", "--steps_per_epoch", "1",
+                    "--f16")
+    assert model.config.F16 and model.epoch == 1
+    assert torch.isfinite(model.engine.params.flat).all()
+
+
+def test_ctypes_example_of_integration_md_runs():
+    """examples/conv2d_ctypes.py: a stand-alone ctypes binding of one Conv2D operator (no ursonet_b200 import)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "conv2d_ctypes.py")], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max rel err" in r.stdout

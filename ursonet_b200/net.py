@@ -65,8 +65,12 @@ class UrsoNet:
     def build(self, mode, config):
         assert mode in ["training", "inference"]
         if getattr(config, "F16", False):
-            raise NotImplementedError("--f16 (pure fp16 variables) is not built; the engine computes in bf16 with fp32 "
-                                      "accumulation and fp32 master weights")
+            # Reference: K.set_floatx('float16') + epsilon 1e-4 (net.py:590-593): pure fp16 variables and maths, no loss
+            # scaling, no master copy.  This build serves the flag with its one 16-bit engine: bf16 storage / MMA operands
+            # (same bytes and tensor-core rate as fp16, fp32 exponent range so no loss scaling is needed), fp32
+            # accumulation and fp32 master weights; the fp16 Adam epsilon (1e-4) is honoured (Engine.set_hyper).
+            # DESIGN.md section 8 records the decision.
+            log("--f16: 16-bit storage is bf16 in this build (fp32 accumulate + fp32 master weights), Adam eps = 1e-4")
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.world = world
         per_gpu = int(config.BATCH_SIZE) // max(1, int(getattr(config, "GPU_COUNT", 1)))
