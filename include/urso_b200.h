@@ -79,6 +79,13 @@ typedef struct {
   int32_t relu;
   float* colsum;      /* [b_rows] fp32 or NULL: atomically accumulates per-channel sums of the stored output */
   int32_t block_n;    /* N tile: 0 = auto, else 32 / 64 / 128 / 256 */
+  /* Bit-packed ReLU masks (1 bit per element instead of re-reading the bf16 activation in backward: 16x fewer bytes).
+   * One 32-bit word per pixel and 32-channel group g: channel 32g + 2i + j  <->  bit (15 - i) + 16 j  (i = 0..15, j = 0,1).
+   * ptr + strides in BYTES addressing the word group of pixel (n,h,w) of the OUTPUT grid: ptr + n*sn + h*sh + w*sw.
+   * relu_bits (fprop, TMA epilogue only): written with (stored output != 0).  mask_bits (dgrad): output forced to 0
+   * where the bit is clear; use it INSTEAD of `mask`. */
+  urso_pix relu_bits;
+  urso_pix mask_bits;
   int32_t halo;       /* 1: halo reuse -- all segments are taps of ONE stride-1 view (n_a == 1, TW == 8, TH == 16): each
                          64-channel chunk of the input patch (+ its halo) is fetched once and every tap reads a
                          row-shifted window of it from shared memory instead of re-fetching it from L2; when the weight
@@ -153,6 +160,8 @@ typedef struct {
   int32_t relu;
   int32_t out_fp32;
   void* workspace;
+  void* relu_bits;     /* uint32 [N,OH,OW,K/32] or NULL: bit-packed (y != 0), the ReLU mask backward needs (see
+                          urso_convgemm_desc.relu_bits for the bit order); K % 64 == 0, bf16 output */
 } urso_conv2d_fwd_desc;
 
 typedef struct urso_conv2d_fwd urso_conv2d_fwd_t;
@@ -166,6 +175,7 @@ int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9); /* see
 /* Input gradient with fused fan-in: dx = mask( sum_i dgrad_i(dy_i, w_i) + addend ), one launch per output phase
  * (stride^2 phases), the convolutions' reduction ranges concatenated.  All consumers share x's shape and stride.
  *   mask    bf16 [N,H,W,C]: the forward activation x (ReLU backward: dx = 0 where x <= 0) or NULL
+ *   mask_bits: the same mask, bit-packed (preferred)
  *   addend  bf16 [N,H,W,C]: gradient arriving through an identity shortcut, or NULL
  *   colsum  fp32 [C]: += per-channel sums of dx (d beta / d bias of the layer that produced x), or NULL
  *   dy_sparse: every dy_i is non-zero on its even-even pixels only (it sits behind a 1x1/stride-2 convolution, the
@@ -185,6 +195,8 @@ typedef struct {
   void* dx;
   float* colsum;
   void* workspace;
+  const void* mask_bits; /* uint32 [N,H,W,C/32] or NULL: the ReLU mask of x as written by urso_conv2d_fwd's relu_bits;
+                            replaces `mask` (16x fewer bytes, no shared-memory ring in the epilogue) */
 } urso_conv2d_dgrad_desc;
 
 typedef struct urso_conv2d_dgrad urso_conv2d_dgrad_t;
@@ -194,6 +206,7 @@ int urso_conv2d_dgrad_stage_weights(urso_conv2d_dgrad_t* h, void* stream);
 int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream);
 int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h);
 int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h);
+int urso_conv2d_dgrad_plan_info(const urso_conv2d_dgrad_t* h, int32_t launch, int32_t* out9); /* see urso_convgemm_plan_info */
 void urso_conv2d_dgrad_destroy(urso_conv2d_dgrad_t* h);
 
 /* Raw weight gradient G[k*k*C, K] (fp32, HWIO order, accumulated with atomics: the caller zeroes it) of the UNSCALED

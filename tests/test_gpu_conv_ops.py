@@ -286,3 +286,97 @@ def test_conv2d_dgrad_halo_resident_with_mask_many_tiles():
     got = dx.double().cpu()
     assert relerr(got, gref) <= 6e-3
     assert torch.allclose(cs.double().cpu(), got.sum((0, 1, 2)), rtol=1e-3, atol=1e-2 * got.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ bit-packed ReLU masks
+def unpack_bits(bits, C):
+    """int32 [N,H,W,C/32] -> bool [N,H,W,C] following the documented order (include/urso_b200.h, urso_convgemm_desc):
+    channel 32g + 2i + j  <->  bit (15 - i) + 16 j of word g."""
+    b = bits.cpu().to(torch.int64) & 0xFFFFFFFF
+    out = torch.zeros(*bits.shape[:3], C, dtype=torch.bool)
+    for g in range(C // 32):
+        for i in range(16):
+            for j in range(2):
+                out[..., 32 * g + 2 * i + j] = ((b[..., g] >> ((15 - i) + 16 * j)) & 1).bool()
+    return out
+
+
+@pytest.mark.parametrize("k,stride,padding,cin,cout,N,h,w", [
+    (1, 1, "valid", 64, 256, 2, 16, 24),        # flat pixels, 4 chunks per tile
+    (3, 1, "same", 64, 64, 2, 32, 24),          # halo patch
+    (3, 1, "same", 128, 128, 2, 20, 30),        # partial tiles
+    (1, 2, "valid", 128, 64, 2, 16, 24),
+    (3, 1, "same", 64, 64, 4, 160, 240),        # two pipelines, many tiles per CTA
+])
+def test_relu_bits_written_by_fwd_and_consumed_by_dgrad(k, stride, padding, cin, cout, N, h, w):
+    from ursonet_b200 import lib
+    x = bf16_exact(N, h, w, cin, seed=81)
+    wk = bf16_exact(k, k, cin, cout, scale=0.05, seed=82)
+    scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+    shift = torch.randn(cout, dtype=torch.float64) * 0.3
+    shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)
+    oh, ow = lib.out_hw(shape)
+    y = torch.full((N, oh, ow, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    bits = torch.full((N, oh, ow, cout // 32), -1, dtype=torch.int32, device=DEV)
+    op = lib.Conv2dFwd(shape, x.to(torch.bfloat16).to(DEV), wk.float().to(DEV), scale.float().to(DEV),
+                       shift.float().to(DEV), y, relu=True, relu_bits=bits)
+    op.stage()
+    op.launch()
+    torch.cuda.synchronize()
+    # the bits are exactly (stored output > 0)
+    assert torch.equal(unpack_bits(bits, cout), (y.float().cpu() > 0))
+    frac = (y.float() > 0).float().mean().item()
+    assert 0.2 < frac < 0.8          # a meaningful mask
+    # dgrad of a 3x3 consumer of y with the bit mask == dgrad with the bf16 activation as the mask (bit-exact)
+    c2 = 64
+    shape2 = lib.conv_shape(N, oh, ow, cout, c2, 3, 1, "same")
+    w2 = bf16_exact(3, 3, cout, c2, scale=0.05, seed=83).float().to(DEV)
+    s2 = (0.5 + torch.rand(c2)).to(DEV)
+    dy = bf16_exact(N, oh, ow, c2, seed=84).to(torch.bfloat16).to(DEV)
+    outs = []
+    for use_bits in (False, True):
+        dx = torch.zeros(N, oh, ow, cout, dtype=torch.bfloat16, device=DEV)
+        cs = torch.zeros(cout, dtype=torch.float32, device=DEV)
+        dop = lib.Conv2dDgrad([shape2], [dy], [w2], [s2], dx, mask=None if use_bits else y,
+                              mask_bits=bits if use_bits else None, colsum=cs)
+        dop.stage()
+        dop.launch()
+        torch.cuda.synchronize()
+        outs.append((dx.clone(), cs.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-3)
+    assert (outs[1][0].float().abs().sum() > 0)
+
+
+def test_mask_bits_on_a_strided_dgrad_phase_grid():
+    """Stride-2 consumers write dx one parity phase at a time: the bit mask is then addressed through the phase-strided
+    pixel grid (conv block: 1x1/s2 '2a' + 1x1/s2 shortcut on a 256-channel block output)."""
+    from ursonet_b200 import lib
+    N, h, w, cin = 2, 16, 24, 256
+    xact = bf16_exact(N, h, w, cin, seed=91)
+    mask_ref = xact > 0
+    # build the bits from the documented order on the host
+    words = torch.zeros(N, h, w, cin // 32, dtype=torch.int64)
+    for g in range(cin // 32):
+        for i in range(16):
+            for j in range(2):
+                words[..., g] |= mask_ref[..., 32 * g + 2 * i + j].to(torch.int64) << ((15 - i) + 16 * j)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).to(DEV)
+    shapes, dys, ws, scs = [], [], [], []
+    for i, cout in enumerate((128, 512)):
+        sh = lib.conv_shape(N, h, w, cin, cout, 1, 2, "valid")
+        oh, ow = lib.out_hw(sh)
+        shapes.append(sh)
+        dys.append(bf16_exact(N, oh, ow, cout, seed=92 + i).to(torch.bfloat16).to(DEV))
+        ws.append(bf16_exact(1, 1, cin, cout, scale=0.05, seed=94 + i).float().to(DEV))
+        scs.append((0.5 + torch.rand(cout)).to(DEV))
+    outs = []
+    for use_bits in (False, True):
+        dx = torch.zeros(N, h, w, cin, dtype=torch.bfloat16, device=DEV)
+        dop = lib.Conv2dDgrad(shapes, dys, ws, scs, dx, mask=None if use_bits else xact.to(torch.bfloat16).to(DEV),
+                              mask_bits=words if use_bits else None)
+        dop.stage()
+        dop.launch()
+        torch.cuda.synchronize()
+        outs.append(dx.clone())
+    assert torch.equal(outs[0], outs[1]) and outs[0].float().abs().sum() > 0

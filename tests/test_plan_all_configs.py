@@ -48,6 +48,7 @@ def plan_network(l, cfg, B):
         d.x, d.w, d.scale, d.shift, d.y, d.workspace = FAKE, FAKE, FAKE, FAKE, FAKE, FAKE
         d.addend = FAKE if c.addend else None
         d.relu, d.out_fp32 = int(c.relu), int(c.out_fp32)
+        d.relu_bits = FAKE if (c.relu and c.dst in g.relu_buffers and c.dst != g.pool_src) else None    # as the engine does
         h = C.c_void_p()
         rc = l.urso_conv2d_fwd_create(C.byref(d), C.byref(h))
         assert rc == 0, (c.name, l.urso_last_error())
@@ -70,7 +71,9 @@ def plan_network(l, cfg, B):
         for i, c in enumerate(grp["convs"]):
             d.shape[i], d.dy[i], d.w[i], d.scale[i] = shape_of(g, c, B, H, W), FAKE, FAKE, FAKE
         d.dy_sparse = int(grp["sparse_in"])
-        d.mask = FAKE if grp["mask"] else None
+        bits = grp["mask"] and grp["X"] != "pool1"          # the engine: bit-packed masks except for pool1
+        d.mask = FAKE if (grp["mask"] and not bits) else None
+        d.mask_bits = FAKE if bits else None
         d.addend = FAKE if grp["add"] else None
         d.dx, d.colsum, d.workspace = FAKE, (FAKE if grp["colsum"] else None), FAKE
         assert l.urso_conv2d_dgrad_workspace_bytes(C.byref(d)) > 0, (grp["X"], l.urso_last_error())
@@ -79,6 +82,9 @@ def plan_network(l, cfg, B):
         assert rc == 0, (grp["X"], l.urso_last_error())
         assert (l.urso_conv2d_dgrad_untouched_phases(h) == 0b1110) == grp["only_phase0"], grp["X"]
         n_dgrad += l.urso_conv2d_dgrad_num_launches(h)
+        v = (C.c_int32 * 9)()
+        l.urso_conv2d_dgrad_plan_info(h, 0, v)
+        infos["d:" + grp["X"]] = dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem", "grid"), v))
         l.urso_conv2d_dgrad_destroy(h)
     return g, infos, n_dgrad, sparse
 
@@ -98,7 +104,7 @@ CONFIGS = [   # BASELINE.json configs[0..4] + the other backbones at the bench s
 def test_every_launch_of_the_network_plans(dry, backbone, h, w, B, classify, bins):
     cfg = make_cfg(backbone, h, w, classify, bins)
     g, infos, n_dgrad, sparse = plan_network(dry, cfg, B)
-    assert len(infos) == len(g.convs) and n_dgrad >= len(g.convs) // 2
+    assert sum(1 for k in infos if not k.startswith("d:")) == len(g.convs) and n_dgrad >= len(g.convs) // 2
 
 
 def test_bench_workload_gets_the_intended_modes(dry):
@@ -109,6 +115,12 @@ def test_bench_workload_gets_the_intended_modes(dry):
     _, infos, _, sparse = plan_network(dry, cfg, 32)
     for name in ("conv1", "res2a_branch2b", "res2b_branch2b", "res2c_branch2b"):
         assert infos[name]["halo"] == 1 and infos[name]["bres"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
+    # the 3x3 input gradients plan like their forward twins now that the ReLU mask is bit-packed (no smem ring for it)
+    # (the last block of a stage has a sparse output gradient: its 3x3 dgrad runs as 4 decimated phase launches instead)
+    for name in ("d:res2a_branch2a", "d:res2b_branch2a"):
+        assert infos[name]["halo"] == 1 and infos[name]["bres"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
+    for name in ("d:res3a_branch2a", "d:res3c_branch2a"):
+        assert infos[name]["halo"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
     for name in ("res3a_branch2b", "res3d_branch2b"):
         assert infos[name]["halo"] == 1 and infos[name]["bres"] == 0 and infos[name]["npipe"] == 2, (name, infos[name])
     for name, i in infos.items():

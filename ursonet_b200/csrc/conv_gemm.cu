@@ -96,6 +96,7 @@ struct ConvGemmParams {
   int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
   int colacc_bytes;    // per-CTA column-sum accumulator (0 when the launch has no colsum: the space goes to stages)
   PixDev out, addend, mask;
+  PixDev bits_out, mask_bits;   // bit-packed ReLU masks (1 bit per element, 32-channel words): strides in BYTES
   int out_fp32, relu;
   const float* shift;
   float* colsum;
@@ -495,6 +496,22 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       if (n_in > 0 && lane == 0) {
         for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
       }
+      // bit-packed ReLU mask of the dgrad epilogue: 64 bits per pixel row and chunk, read straight from global memory into
+      // two registers one chunk AHEAD (the load has a whole chunk of epilogue work to arrive) -- no shared-memory ring
+      const bool has_mbits = p.mask_bits.ptr != nullptr;
+      auto load_mask_bits = [&](const ChunkIter<BLOCK_N>& ci) -> uint2 {
+        uint2 r = make_uint2(0u, 0u);
+        if (ci.valid && (ci.h0 + rh < p.OH) && (ci.w0 + rw < p.OW) && (ci.img < p.NB)) {
+          const char* a = static_cast<const char*>(p.mask_bits.ptr) + (long long)ci.img * p.mask_bits.sn +
+                          (long long)(ci.h0 + rh) * p.mask_bits.sh + (long long)(ci.w0 + rw) * p.mask_bits.sw +
+                          ((ci.n_tile * BLOCK_N + ci.j * 64) >> 3);
+          r = __ldg(reinterpret_cast<const uint2*>(a));
+        }
+        return r;
+      };
+      ChunkIter<BLOCK_N> nxt = cur;
+      uint2 mb_next = make_uint2(0u, 0u);
+      if (has_mbits) mb_next = load_mask_bits(cur);
       int n_done = 0;        // my chunks consumed so far
       int in_slot = 0, out_slot = 0;   // ring positions (kept incrementally: no runtime modulo on the critical path)
       uint32_t in_phase = 0;
@@ -512,8 +529,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           const uint8_t* in_slab = ei + in_slot * slot_bytes;
           uint8_t* out_slab = eo + out_slot * kSlabBytes;
           // rows outside the image are clipped by the TMA store; they only have to be zeroed for the column sums
-          const bool valid = p.colsum == nullptr ||
-                             ((cur.h0 + rh < p.OH) && (cur.w0 + rw < p.OW) && (cur.img < p.NB));
+          const bool in_img = (cur.h0 + rh < p.OH) && (cur.w0 + rw < p.OW) && (cur.img < p.NB);
+          const bool valid = p.colsum == nullptr || in_img;
+          uint2 mb = make_uint2(0u, 0u);
+          if (has_mbits) {   // this chunk's mask words were loaded one chunk ago; start the load for my next chunk
+            mb = mb_next;
+            nxt.next(p);
+            if (nxt.valid) nxt.next(p);
+            mb_next = load_mask_bits(nxt);
+          }
           if (n_done >= kEoDepth) {   // the TMA store that last used this output slab must have drained it
             if (lane == 0) {
               if (kEoDepth >= 3) tma_store_wait_read<2>();
@@ -523,6 +547,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             __syncwarp();
           }
           if (n_in > 0) mbar_wait(&my_bar[in_slot], in_phase);
+          uint2 obits = make_uint2(0u, 0u);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint32_t acc[32];
@@ -565,6 +590,21 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             }
+            if (p.bits_out.ptr != nullptr) {
+              // ReLU mask of the stored output, 1 bit per element: word i (channels 2i, 2i+1 of this 32-channel half)
+              // contributes bit 15-i (channel 2i) and bit 31-i (channel 2i+1)
+              const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+              uint32_t bw = 0u;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                bw = bw * 2u + (__hne2_mask(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]), z2) & 0x00010001u);
+              if (hf == 0) obits.x = bw; else obits.y = bw;
+            }
+            if (has_mbits) {
+              const uint32_t b = hf == 0 ? mb.x : mb.y;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] &= ((b >> (15 - i)) & 0x00010001u) * 0xFFFFu;
+            }
             if (p.has_mask) {
               const uint8_t* ms = in_slab + p.has_add * kSlabBytes;
               const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -585,6 +625,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(out_slab + uoff[hf * 4 + i]) =
                   make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+          if (p.bits_out.ptr != nullptr && in_img) {
+            char* a = static_cast<char*>(p.bits_out.ptr) + (long long)cur.img * p.bits_out.sn +
+                      (long long)(cur.h0 + rh) * p.bits_out.sh + (long long)(cur.w0 + rw) * p.bits_out.sw + (col0 >> 3);
+            *reinterpret_cast<uint2*>(a) = obits;
           }
           fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();          // all lanes have finished reading the input slot and writing the output slab
@@ -893,6 +938,16 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.has_add = d->addend.ptr != nullptr;
   p.has_mask = d->mask.ptr != nullptr;
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
+  if ((d->relu_bits.ptr != nullptr || d->mask_bits.ptr != nullptr) && !p.epi_tma) {
+    set_error("bit-packed masks need the bf16 TMA epilogue (bf16 output, channels a multiple of 64)");
+    delete h;
+    return 2;
+  }
+  if (d->mask_bits.ptr != nullptr && d->mask.ptr != nullptr) {
+    set_error("mask and mask_bits are mutually exclusive");
+    delete h;
+    return 2;
+  }
   const int n_in = p.has_add + p.has_mask;
   int epi_bytes;
   if (p.epi_tma) {
@@ -1037,6 +1092,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.out = PixDev{d->out.ptr, d->out.sn, d->out.sh, d->out.sw};
   p.addend = PixDev{d->addend.ptr, d->addend.sn, d->addend.sh, d->addend.sw};
   p.mask = PixDev{d->mask.ptr, d->mask.sn, d->mask.sh, d->mask.sw};
+  p.bits_out = PixDev{d->relu_bits.ptr, d->relu_bits.sn, d->relu_bits.sh, d->relu_bits.sw};
+  p.mask_bits = PixDev{d->mask_bits.ptr, d->mask_bits.sn, d->mask_bits.sh, d->mask_bits.sw};
   p.out_fp32 = d->out_fp32;
   p.relu = d->relu;
   p.shift = d->shift;

@@ -124,6 +124,19 @@ urso_pix flat_pix(const void* base, int64_t m, int c) {
   return p;
 }
 const urso_pix kNoPix = {nullptr, 0, 0, 0};
+// bit-packed mask tensor [N,H,W,C/32] uint32 (C/8 bytes per pixel): BYTE strides of the (phase-strided / flattened) pixel grid
+urso_pix bits_strided_pix(const void* base, int h, int w, int c, int ph, int pw, int step) {
+  const int64_t pb = c / 8;
+  urso_pix p;
+  p.ptr = const_cast<char*>(static_cast<const char*>(base)) + ((int64_t)ph * w + pw) * pb;
+  p.sn = (int64_t)h * w * pb; p.sh = (int64_t)step * w * pb; p.sw = (int64_t)step * pb;
+  return p;
+}
+urso_pix bits_flat_pix(const void* base, int64_t m, int c) {
+  urso_pix p;
+  p.ptr = const_cast<void*>(base); p.sn = m * (c / 8); p.sh = m * (c / 8); p.sw = c / 8;
+  return p;
+}
 
 // K index -> row of the 7x7x3 HWIO kernel for the space-to-depth staged stem (urso_stem_stage layout):
 // k = r2*64 + s2*16 + ph*8 + pw*4 + c  <->  tap (r, s) = (2*r2 + ph, 2*s2 + pw), channel c;  -1 = zero padding.
@@ -206,6 +219,7 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
       cd.TW = 8; cd.TH = 16; cd.halo = 1;
     }
     cd.out = dense_pix(d->y, g.oh, g.ow, s.K);
+    if (d->relu_bits) cd.relu_bits = bits_strided_pix(d->relu_bits, g.oh, g.ow, s.K, 0, 0, 1);
   } else {
     URSO_REQUIRE(s.C % 64 == 0, "input channels %d must be a multiple of 64", s.C);
     const std::vector<Tap> taps = fwd_taps(g);
@@ -226,6 +240,7 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
       cd.OW = (int32_t)M; cd.OH = 1; cd.NB = 1; cd.TW = 128; cd.TH = 1;
       cd.out = flat_pix(d->y, M, yc);
       cd.addend = d->addend ? flat_pix(d->addend, M, yc) : kNoPix;
+      if (d->relu_bits) cd.relu_bits = bits_flat_pix(d->relu_bits, M, yc);
     } else {
       if (s.stride == 1) {
         cd.a[0] = dense_view(d->x, s.N, s.H, s.W, s.C);
@@ -242,6 +257,7 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
       }
       cd.out = dense_pix(d->y, g.oh, g.ow, yc);
       cd.addend = d->addend ? dense_pix(d->addend, g.oh, g.ow, yc) : kNoPix;
+      if (d->relu_bits) cd.relu_bits = bits_strided_pix(d->relu_bits, g.oh, g.ow, yc, 0, 0, 1);
     }
   }
   const int K = (int)idx.size();
@@ -423,6 +439,7 @@ extern "C" int urso_conv2d_dgrad_create(const urso_conv2d_dgrad_desc* d, urso_co
       cd.out = flat_pix(d->dx, M, cin);
       cd.addend = d->addend ? flat_pix(d->addend, M, cin) : kNoPix;
       cd.mask = d->mask ? flat_pix(d->mask, M, cin) : kNoPix;
+      if (d->mask_bits) cd.mask_bits = bits_flat_pix(d->mask_bits, M, cin);
     } else {
       for (int i = 0; i < d->n_convs; ++i) {
         const Geom& g = h->geoms[i];    // (decimated) output grid of consumer i
@@ -444,6 +461,7 @@ extern "C" int urso_conv2d_dgrad_create(const urso_conv2d_dgrad_desc* d, urso_co
       cd.out = strided_pix(d->dx, H, W, cin, ph.oph, ph.opw, stride, 2);
       cd.mask = d->mask ? strided_pix(d->mask, H, W, cin, ph.oph, ph.opw, stride, 2) : kNoPix;
       cd.addend = d->addend ? strided_pix(d->addend, H, W, cin, 0, 0, 1, 2) : kNoPix;
+      if (d->mask_bits) cd.mask_bits = bits_strided_pix(d->mask_bits, H, W, cin, ph.oph, ph.opw, stride);
     }
     if ((rc = urso_convgemm_create(&cd, &ph.plan))) break;
   }
@@ -472,6 +490,10 @@ extern "C" int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream) {
   for (const DgradPhase& ph : h->phases)
     if (int rc = urso_convgemm_launch(ph.plan, stream)) return rc;
   return 0;
+}
+extern "C" int urso_conv2d_dgrad_plan_info(const urso_conv2d_dgrad_t* h, int32_t launch, int32_t* out9) {
+  URSO_REQUIRE(h != nullptr && launch >= 0 && launch < (int)h->phases.size(), "bad handle / launch index");
+  return urso_convgemm_plan_info(h->phases[launch].plan, out9);
 }
 extern "C" int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h) { return h ? h->untouched : -1; }
 extern "C" int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h) { return h ? (int)h->phases.size() : -1; }

@@ -277,6 +277,8 @@ class Engine:
         self._late_binds = []
         self._last = {}
         self.fwd_ops: Dict[str, lib.Conv2dFwd] = {}
+        self.relu_bits: Dict[str, torch.Tensor] = {}
+        self.use_mask_bits = int(os.environ.get("URSO_MASK_BITS", "1")) != 0     # 0: bf16 activation as the mask (A/B runs)
         aux = self.aux_lane
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
@@ -290,7 +292,12 @@ class Engine:
             x = self.E if c.stem else self.act[c.src]
             out = self.act[c.dst]
             addend = self.act[c.addend] if c.addend else None
-            op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu)
+            # training: the ReLU mask backward needs is written bit-packed by the epilogue (1 bit per element; the
+            # gradient launches then read 1/16 of the bytes of the bf16 activation and need no smem ring for it)
+            bits = None
+            if self.training and self.use_mask_bits and c.relu and c.dst in g.relu_buffers and c.dst != g.pool_src:
+                bits = self.relu_bits[c.dst] = torch.zeros((B, oh, ow, c.cout // 32), dtype=torch.int32, device=self.device)
+            op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu, relu_bits=bits)
             self.fwd_ops[c.name] = op
             staged = self._add(self.ops_stage, OpRec(op.stage, "stage", c.name, lane=aux))
             if c.stem:
@@ -540,6 +547,9 @@ class Engine:
         # pool1 = max of post-ReLU values: masking its gradient by (pool1 > 0) IS the stem's ReLU mask (a window's max
         # is 0 only when all its inputs are 0), so the max-pool backward does not have to read the stem output
         mask = self.act[X] if (X in g.relu_buffers or X == "pool1") else None
+        mask_bits = self.relu_bits.get(X)
+        if mask_bits is not None:
+            mask = None
         addend = self.dact[adds[0].dst] if adds else None
         shapes = [self._conv_shape(c) for c in convs]
         dys = [self.dact[c.dst] for c in convs]
@@ -557,7 +567,7 @@ class Engine:
             a_elems += B * oh * ow * P.ceil64(c.cout)
         touched = dX.numel() / (4 if only_phase0 else 1)
         nbytes = 2.0 * (a_elems + touched * (1 + (mask is not None) + (addend is not None))
-                        + sum(c.cout * c.k * c.k * c.cin for c in convs))
+                        + sum(c.cout * c.k * c.k * c.cin for c in convs)) + (touched / 8 if mask_bits is not None else 0)
         stage_op = self._add(self.ops_stage, OpRec(lambda: box["p"].stage(), "stage", "d:" + X, lane=self.aux_lane))
         if stride == 2 and not self.sparse_bwd:      # phases no filter tap reaches must read as zero
             self._add(self.ops_bwd, OpRec(lambda: box["p"].untouched and dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(),
@@ -567,12 +577,14 @@ class Engine:
 
         def bind():
             cs = self._zero_view(key) if key else None
-            box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs, dy_sparse=sparse_in)
+            box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs, dy_sparse=sparse_in,
+                                       mask_bits=mask_bits)
             op.launches = stage_op.launches = box["p"].n_launches
             assert (box["p"].untouched == 0b1110) == only_phase0, (X, box["p"].untouched)
         self._late_binds.append(bind)
         self.dgrad_ops[X] = box
-        self.dgrad_meta.append(dict(X=X, convs=convs, add=adds[0].dst if adds else None, mask=mask is not None,
+        self.dgrad_meta.append(dict(X=X, convs=convs, add=adds[0].dst if adds else None,
+                                    mask=mask is not None or mask_bits is not None,
                                     colsum=key is not None, sparse_in=sparse_in, stride=stride, only_phase0=only_phase0))
         if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)

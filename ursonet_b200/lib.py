@@ -31,7 +31,8 @@ class ConvGemmDesc(C.Structure):
                 ("b_k", C.c_int32), ("seg", Seg * MAX_SEGS), ("n_seg", C.c_int32),
                 ("OW", C.c_int32), ("OH", C.c_int32), ("NB", C.c_int32), ("TW", C.c_int32), ("TH", C.c_int32),
                 ("out", Pix), ("out_fp32", C.c_int32), ("shift", C.c_void_p), ("addend", Pix), ("mask", Pix),
-                ("relu", C.c_int32), ("colsum", C.c_void_p), ("block_n", C.c_int32), ("halo", C.c_int32)]
+                ("relu", C.c_int32), ("colsum", C.c_void_p), ("block_n", C.c_int32), ("relu_bits", Pix),
+                ("mask_bits", Pix), ("halo", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -54,14 +55,14 @@ class Conv2dShape(C.Structure):
 class Conv2dFwdDesc(C.Structure):
     _fields_ = [("shape", Conv2dShape), ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("addend", C.c_void_p), ("y", C.c_void_p), ("relu", C.c_int32),
-                ("out_fp32", C.c_int32), ("workspace", C.c_void_p)]
+                ("out_fp32", C.c_int32), ("workspace", C.c_void_p), ("relu_bits", C.c_void_p)]
 
 
 class Conv2dDgradDesc(C.Structure):
     _fields_ = [("n_convs", C.c_int32), ("shape", Conv2dShape * MAX_FANIN), ("dy", C.c_void_p * MAX_FANIN),
                 ("w", C.c_void_p * MAX_FANIN), ("scale", C.c_void_p * MAX_FANIN), ("dy_sparse", C.c_int32),
                 ("mask", C.c_void_p), ("addend", C.c_void_p), ("dx", C.c_void_p), ("colsum", C.c_void_p),
-                ("workspace", C.c_void_p)]
+                ("workspace", C.c_void_p), ("mask_bits", C.c_void_p)]
 
 
 class Conv2dWgradDesc(C.Structure):
@@ -103,6 +104,7 @@ SIGNATURES = {
     "urso_conv2d_dgrad_launch": [_vp, _vp],
     "urso_conv2d_dgrad_untouched_phases": [_vp],
     "urso_conv2d_dgrad_num_launches": [_vp],
+    "urso_conv2d_dgrad_plan_info": [_vp, _i32, C.POINTER(_i32)],
     "urso_conv2d_dgrad_destroy": [_vp],
     "urso_conv2d_wgrad_create": [C.POINTER(Conv2dWgradDesc), C.POINTER(_vp)],
     "urso_conv2d_wgrad_launch": [_vp, _vp],
@@ -208,11 +210,20 @@ def pix(t):
     return Pix(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
 
 
+def bits_pix(t):
+    """urso_pix (BYTE strides) of a bit-packed mask tensor/view: int32 [N,H,W,C/32]."""
+    import torch
+    if t is None:
+        return Pix(None, 0, 0, 0)
+    assert t.dtype == torch.int32 and t.dim() == 4 and t.stride(3) == 1
+    return Pix(t.data_ptr(), 4 * t.stride(0), 4 * t.stride(1), 4 * t.stride(2))
+
+
 class ConvGemm:
     """Owning wrapper of a urso_convgemm_t plan (tensor maps are encoded once; launch is graph-capturable)."""
 
     def __init__(self, a_views, b, segs, out, OW, OH, NB, TW, TH, shift=None, addend=None, mask=None, relu=False,
-                 colsum=None, block_n=0, halo=False):
+                 colsum=None, block_n=0, halo=False, relu_bits=None, mask_bits=None):
         import torch
         d = ConvGemmDesc()
         assert 1 <= len(a_views) <= MAX_AMAPS and 1 <= len(segs) <= MAX_SEGS
@@ -233,7 +244,8 @@ class ConvGemm:
         d.colsum = ptr(colsum)
         d.block_n = block_n
         d.halo = int(halo)
-        self._keep = (a_views, b, out, shift, addend, mask, colsum)   # keep tensors alive
+        d.relu_bits, d.mask_bits = bits_pix(relu_bits), bits_pix(mask_bits)
+        self._keep = (a_views, b, out, shift, addend, mask, colsum, relu_bits, mask_bits)   # keep tensors alive
         h = _vp()
         check(load().urso_convgemm_create(C.byref(d), C.byref(h)), "urso_convgemm_create")
         self._h = h
@@ -318,15 +330,17 @@ def _workspace(nbytes, device):
 class Conv2dFwd:
     """urso_conv2d_fwd_t: y = relu?( conv(x, w * scale) + shift + addend ).  All planning happens in the library."""
 
-    def __init__(self, shape, x, w, scale, shift, y, addend=None, relu=False):
+    def __init__(self, shape, x, w, scale, shift, y, addend=None, relu=False, relu_bits=None):
         import torch
         d = Conv2dFwdDesc()
+        d.relu_bits = ptr(relu_bits)
+        assert relu_bits is None or (relu_bits.dtype == torch.int32 and relu_bits.is_contiguous())
         d.shape = shape
         self.ws = _workspace(load().urso_conv2d_fwd_workspace_bytes(C.byref(shape)), x.device)
         d.x, d.w, d.scale, d.shift, d.addend, d.y = ptr(x), ptr(w), ptr(scale), ptr(shift), ptr(addend), ptr(y)
         d.relu, d.out_fp32, d.workspace = int(relu), int(y.dtype == torch.float32), self.ws.data_ptr()
         assert x.is_contiguous() and y.is_contiguous() and (addend is None or addend.is_contiguous())
-        self._keep = (x, w, scale, shift, y, addend)
+        self._keep = (x, w, scale, shift, y, addend, relu_bits)
         h = _vp()
         check(load().urso_conv2d_fwd_create(C.byref(d), C.byref(h)), "urso_conv2d_fwd_create")
         self._h = h
@@ -352,8 +366,11 @@ class Conv2dFwd:
 class Conv2dDgrad:
     """urso_conv2d_dgrad_t: dx = mask( sum_i dgrad_i(dy_i, w_i * scale_i) + addend ) with fused fan-in."""
 
-    def __init__(self, shapes, dys, ws, scales, dx, mask=None, addend=None, colsum=None, dy_sparse=False):
+    def __init__(self, shapes, dys, ws, scales, dx, mask=None, addend=None, colsum=None, dy_sparse=False,
+                 mask_bits=None):
         d = Conv2dDgradDesc()
+        d.mask_bits = ptr(mask_bits)
+        assert mask_bits is None or (mask is None and mask_bits.is_contiguous())
         d.n_convs = len(shapes)
         for i, (s, dy, w, sc) in enumerate(zip(shapes, dys, ws, scales)):
             assert dy.is_contiguous()
@@ -363,7 +380,7 @@ class Conv2dDgrad:
         assert dx.is_contiguous() and (mask is None or mask.is_contiguous()) and (addend is None or addend.is_contiguous())
         self.ws = _workspace(load().urso_conv2d_dgrad_workspace_bytes(C.byref(d)), dx.device)
         d.workspace = self.ws.data_ptr()
-        self._keep = (dys, ws, scales, dx, mask, addend, colsum)
+        self._keep = (dys, ws, scales, dx, mask, addend, colsum, mask_bits)
         h = _vp()
         check(load().urso_conv2d_dgrad_create(C.byref(d), C.byref(h)), "urso_conv2d_dgrad_create")
         self._h = h
