@@ -25,7 +25,7 @@ class Conv2dShape(C.Structure):       # urso_conv2d_shape
 class Conv2dFwdDesc(C.Structure):     # urso_conv2d_fwd_desc
     _fields_ = [("shape", Conv2dShape), ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("addend", C.c_void_p), ("y", C.c_void_p), ("relu", C.c_int32),
-                ("out_fp32", C.c_int32), ("workspace", C.c_void_p)]
+                ("out_fp32", C.c_int32), ("workspace", C.c_void_p), ("relu_bits", C.c_void_p)]
 
 
 def main():
@@ -55,7 +55,8 @@ def main():
 
     y = torch.empty(N, OH, OW, K, dtype=torch.float32, device=dev)                  # the bottleneck output stays fp32
     ws = torch.empty(lib.urso_conv2d_fwd_workspace_bytes(C.byref(shape)), dtype=torch.uint8, device=dev)
-    d = Conv2dFwdDesc(shape, x.data_ptr(), w.data_ptr(), None, bias.data_ptr(), None, y.data_ptr(), 0, 1, ws.data_ptr())
+    d = Conv2dFwdDesc(shape, x.data_ptr(), w.data_ptr(), None, bias.data_ptr(), None, y.data_ptr(), 0, 1, ws.data_ptr(),
+                      None)
     h = C.c_void_p()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ok(lib.urso_conv2d_fwd_create(C.byref(d), C.byref(h)))      # plans segments / parity views / tiles, encodes tensor maps

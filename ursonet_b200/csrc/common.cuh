@@ -27,6 +27,11 @@ int make_view_map(CUtensorMap* out, const urso_view4& v, int box_w, int box_h);
 // bf16 row-major [rows, k] -> 2-D tensor map {k, rows}, box {64, box_rows}, SWIZZLE_128B.
 int make_mat_map(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int box_rows);
 
+// dense.cu: weight-streaming kernels of the Dense heads
+int dense_fwd2(const float* x, const float* w, float* y, int B, int K, int N, cudaStream_t s);
+int dense_dgrad2(const float* dy, const float* w, float* dx, int B, int K, int N, cudaStream_t s);
+int dense_wgrad2(const float* x, const float* dy, float* dw, int B, int K, int N, cudaStream_t s);
+
 #define URSO_CUDA_OK(expr)                                                                 \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \

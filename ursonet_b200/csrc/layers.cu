@@ -279,44 +279,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------ Dense heads (fp32)
-// y[b, n] += sum_{k in chunk} x[b,k] * w[k,n].  Block: 128 threads = 128 output columns, 32 batch rows in registers,
-// one K chunk of 64 per block (split-K over gridDim.y, combined with atomics; y pre-zeroed).
-constexpr int kDenseKC = 64;
-__global__ void __launch_bounds__(128) dense_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        float* __restrict__ y, int B, int K, int N) {
-  __shared__ float4 xs[kDenseKC][8];  // [k][b/4] : 32 batch rows
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  const int k0 = blockIdx.y * kDenseKC;
-  const int b0 = blockIdx.z * 32;
-  for (int i = threadIdx.x; i < kDenseKC * 32; i += 128) {
-    const int kk = i % kDenseKC, bb = i / kDenseKC;  // consecutive threads read consecutive k: coalesced
-    float v = 0.f;
-    if (k0 + kk < K && b0 + bb < B) v = x[(long long)(b0 + bb) * K + k0 + kk];
-    reinterpret_cast<float*>(&xs[kk][0])[bb] = v;
-  }
-  __syncthreads();
-  float acc[32];
-#pragma unroll
-  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-  if (n < N) {
-    const int kend = min(kDenseKC, K - k0);
-    for (int kk = 0; kk < kend; ++kk) {
-      const float wv = __ldg(w + (long long)(k0 + kk) * N + n);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 xv = xs[kk][q];
-        acc[4 * q + 0] += xv.x * wv;
-        acc[4 * q + 1] += xv.y * wv;
-        acc[4 * q + 2] += xv.z * wv;
-        acc[4 * q + 3] += xv.w * wv;
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < 32; ++b)
-      if (b0 + b < B) atomicAdd(y + (long long)(b0 + b) * N + n, acc[b]);
-  }
-}
-
+// The three GEMM-shaped kernels (fwd, dgrad, wgrad) live in dense.cu; the elementwise parts stay here.
 __global__ void dense_bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int B, int N, int act) {
   const long long total = (long long)B * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -341,86 +304,6 @@ __global__ void dense_mask_bias_grad_kernel(const float* __restrict__ y, float* 
     s += g;
   }
   if (db != nullptr) db[n] = s;
-}
-
-// dw[k, n] = sum_b x[b,k] dy[b,n].  Block = 128 columns x 8 k-rows; batch staged through shared memory in tiles of 32.
-__global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                          float* __restrict__ dw, int B, int K, int N) {
-  __shared__ float xs[32][8];
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  const int k0 = blockIdx.y * 8;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += 128) {
-      const int kk = i & 7, bb = i >> 3;
-      xs[bb][kk] = (b0 + bb < B && k0 + kk < K) ? x[(long long)(b0 + bb) * K + k0 + kk] : 0.f;
-    }
-    __syncthreads();
-    if (n < N) {
-      const int bend = min(32, B - b0);
-      for (int bb = 0; bb < bend; ++bb) {
-        const float g = __ldg(dy + (long long)(b0 + bb) * N + n);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += xs[bb][j] * g;
-      }
-    }
-  }
-  if (n < N) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (k0 + j < K) dw[(long long)(k0 + j) * N + n] = acc[j];
-  }
-}
-
-// dx[b, k] = sum_n dy[b,n] w[k,n].  Block = 8 warps = 8 k rows; dy is staged through shared memory in [32 b][128 n]
-// tiles shared by the 8 warps (8x fewer L2 reads than one warp per row reading dy on its own).
-// blockIdx.y splits the n range (n_per_split columns each, a multiple of 128) so that small-K layers still fill the chip
-// and no block walks more than a few serialised chunks; with more than one split the partial sums are added atomically
-// into a dx the host zeroed.
-__global__ void __launch_bounds__(256) dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                          float* __restrict__ dx, int B, int K, int N, int n_per_split) {
-  __shared__ float dys[32][128 + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * 8 + warp;
-  const float* wr = w + (long long)(k < K ? k : 0) * N;
-  const int n_begin = blockIdx.y * n_per_split;
-  const int n_end = min(N, n_begin + n_per_split);
-  const bool atomic = gridDim.y > 1;
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    float acc[32];
-#pragma unroll
-    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-    for (int n0 = n_begin; n0 < n_end; n0 += 128) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < 32 * 128; i += 256) {
-        const int bb = i >> 7, nn = i & 127;
-        dys[bb][nn] = (b0 + bb < B && n0 + nn < n_end) ? dy[(long long)(b0 + bb) * N + n0 + nn] : 0.f;
-      }
-      __syncthreads();
-      if (k < K) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int nn = t * 32 + lane;
-          const float wv = (n0 + nn < n_end) ? __ldg(wr + n0 + nn) : 0.f;
-#pragma unroll
-          for (int b = 0; b < 32; ++b) acc[b] += wv * dys[b][nn];
-        }
-      }
-    }
-    if (k < K) {
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const float sres = warp_sum(acc[b]);
-        if (lane == 0 && b0 + b < B) {
-          if (atomic) atomicAdd(&dx[(long long)(b0 + b) * K + k], sres);
-          else dx[(long long)(b0 + b) * K + k] = sres;
-        }
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------ losses
@@ -574,10 +457,7 @@ int urso_maxpool_bwd(const void* x, const void* argmax, const void* dy, void* dx
 
 int urso_dense_fwd(const float* x, const float* w, float* y, int32_t B, int32_t K, int32_t N, void* stream) {
   URSO_REQUIRE(x && w && y, "null pointer");
-  dim3 grid((N + 127) / 128, (K + kDenseKC - 1) / kDenseKC, (B + 31) / 32);
-  dense_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, w, y, B, K, N);
-  URSO_CUDA_OK(cudaGetLastError());
-  return 0;
+  return dense_fwd2(x, w, y, B, K, N, static_cast<cudaStream_t>(stream));      // dense.cu
 }
 
 int urso_dense_bias_act(float* y, const float* bias, int32_t B, int32_t N, int32_t act, void* stream) {
@@ -595,20 +475,10 @@ int urso_dense_bwd(const float* x, const float* w, const float* y, float* dy, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dense_mask_bias_grad_kernel<<<(N + 127) / 128, 128, 0, s>>>(y, dy, db, B, N, act);
   if (dw != nullptr) {
-    dim3 grid((N + 127) / 128, (K + 7) / 8);
-    dense_wgrad_kernel<<<grid, 128, 0, s>>>(x, dy, dw, B, K, N);
+    if (int rc = dense_wgrad2(x, dy, dw, B, K, N, s)) return rc;
   }
   if (dx != nullptr) {
-    const int kblocks = (K + 7) / 8, chunks = (N + 127) / 128;
-    int sms = num_sms();
-    if (sms <= 0) sms = 148;
-    int nsplit = (4 * sms + kblocks - 1) / kblocks;          // aim for >= 4 blocks per SM
-    if (nsplit > chunks) nsplit = chunks;
-    if (nsplit < 1) nsplit = 1;
-    const int n_per_split = ((chunks + nsplit - 1) / nsplit) * 128;
-    nsplit = (N + n_per_split - 1) / n_per_split;
-    if (nsplit > 1) URSO_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * K, s));
-    dense_dgrad_kernel<<<dim3(kblocks, nsplit), 256, 0, s>>>(dy, w, dx, B, K, N, n_per_split);
+    if (int rc = dense_dgrad2(dy, w, dx, B, K, N, s)) return rc;
   }
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
