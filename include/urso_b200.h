@@ -80,7 +80,8 @@ typedef struct {
   float* colsum;      /* [b_rows] fp32 or NULL: atomically accumulates per-channel sums of the stored output */
   int32_t block_n;    /* N tile: 0 = auto, else 32 / 64 / 128 / 256 */
   /* Bit-packed ReLU masks (1 bit per element instead of re-reading the bf16 activation in backward: 16x fewer bytes).
-   * One 32-bit word per pixel and 32-channel group g: channel 32g + 2i + j  <->  bit (15 - i) + 16 j  (i = 0..15, j = 0,1).
+   * One 32-bit word per pixel and 32-channel group g: channel 32g + c (c = 0..31)  <->  bit (7 - (c >> 2)) + 8 (c & 3)
+   * (the order the epilogues produce / consume with one byte-permute per channel pair).
    * ptr + strides in BYTES addressing the word group of pixel (n,h,w) of the OUTPUT grid: ptr + n*sn + h*sh + w*sw.
    * relu_bits (fprop, TMA epilogue only): written with (stored output != 0).  mask_bits (dgrad): output forced to 0
    * where the bit is clear; use it INSTEAD of `mask`. */

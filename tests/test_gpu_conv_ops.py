@@ -291,13 +291,12 @@ def test_conv2d_dgrad_halo_resident_with_mask_many_tiles():
 # ------------------------------------------------------------------------------------------------ bit-packed ReLU masks
 def unpack_bits(bits, C):
     """int32 [N,H,W,C/32] -> bool [N,H,W,C] following the documented order (include/urso_b200.h, urso_convgemm_desc):
-    channel 32g + 2i + j  <->  bit (15 - i) + 16 j of word g."""
+    channel 32g + c  <->  bit (7 - (c >> 2)) + 8 (c & 3) of word g."""
     b = bits.cpu().to(torch.int64) & 0xFFFFFFFF
     out = torch.zeros(*bits.shape[:3], C, dtype=torch.bool)
     for g in range(C // 32):
-        for i in range(16):
-            for j in range(2):
-                out[..., 32 * g + 2 * i + j] = ((b[..., g] >> ((15 - i) + 16 * j)) & 1).bool()
+        for c in range(32):
+            out[..., 32 * g + c] = ((b[..., g] >> ((7 - (c >> 2)) + 8 * (c & 3))) & 1).bool()
     return out
 
 
@@ -358,9 +357,8 @@ def test_mask_bits_on_a_strided_dgrad_phase_grid():
     # build the bits from the documented order on the host
     words = torch.zeros(N, h, w, cin // 32, dtype=torch.int64)
     for g in range(cin // 32):
-        for i in range(16):
-            for j in range(2):
-                words[..., g] |= mask_ref[..., 32 * g + 2 * i + j].to(torch.int64) << ((15 - i) + 16 * j)
+        for c in range(32):
+            words[..., g] |= mask_ref[..., 32 * g + c].to(torch.int64) << ((7 - (c >> 2)) + 8 * (c & 3))
     words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).to(DEV)
     shapes, dys, ws, scs = [], [], [], []
     for i, cout in enumerate((128, 512)):

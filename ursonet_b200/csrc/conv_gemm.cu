@@ -169,8 +169,12 @@ struct ChunkIter {
   }
 };
 
-template <int BLOCK_N>
+// FLAVOR specialises the TMA epilogue at compile time (the epilogue's instruction issue bounds every short-K launch, and
+// ~10 % of its instructions were uniform branches on launch flags): 0 = every option at run time; 1 = forward convs (no
+// mask / mask bits / column sums compiled in); 2 = gradient launches (no shift / ReLU / mask-bit output compiled in).
+template <int BLOCK_N, int FLAVOR>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  constexpr bool kFwdOps = FLAVOR != 2, kBwdOps = FLAVOR != 1;
   constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   // 1024-byte aligned by declaration (SWIZZLE_128B atoms): no integer round trip on the base pointer, so the compiler
   // keeps the shared address space and emits LDS/STS/ATOMS with 32-bit addresses instead of generic accesses
@@ -476,6 +480,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int uoff[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) uoff[u] = lane * 128 + ((u ^ (lane & 7)) << 4);
+      // column sums: byte offset of this lane's channel pair in row k (0..7) of an 8-row group of the swizzled slab
+      uint32_t csoff[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) csoff[k] = (uint32_t)(k * 128 + ((((lane >> 2) ^ k) << 4) + ((lane & 3) << 2)));
       ChunkIter<BLOCK_N> cur, pf;
       cur.init(p);
       if (half == 1 && cur.valid) cur.next(p);     // set 1 starts at the second chunk of the stream
@@ -498,7 +506,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       }
       // bit-packed ReLU mask of the dgrad epilogue: 64 bits per pixel row and chunk, read straight from global memory into
       // two registers one chunk AHEAD (the load has a whole chunk of epilogue work to arrive) -- no shared-memory ring
-      const bool has_mbits = p.mask_bits.ptr != nullptr;
+      const bool has_mbits = kBwdOps && p.mask_bits.ptr != nullptr;
       auto load_mask_bits = [&](const ChunkIter<BLOCK_N>& ci) -> uint2 {
         uint2 r = make_uint2(0u, 0u);
         if (ci.valid && (ci.h0 + rh < p.OH) && (ci.w0 + rw < p.OW) && (ci.img < p.NB)) {
@@ -530,7 +538,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           uint8_t* out_slab = eo + out_slot * kSlabBytes;
           // rows outside the image are clipped by the TMA store; they only have to be zeroed for the column sums
           const bool in_img = (cur.h0 + rh < p.OH) && (cur.w0 + rw < p.OW) && (cur.img < p.NB);
-          const bool valid = p.colsum == nullptr || in_img;
+          const bool valid = !(kBwdOps && p.colsum != nullptr) || in_img;
           uint2 mb = make_uint2(0u, 0u);
           if (has_mbits) {   // this chunk's mask words were loaded one chunk ago; start the load for my next chunk
             mb = mb_next;
@@ -556,7 +564,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-            if (p.shift != nullptr) {
+            if (kFwdOps && p.shift != nullptr) {
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0 + hf * 32);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -583,29 +591,37 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             }
             // pack to bf16 first; ReLU and the ReLU-backward mask are exact on the packed values
             uint32_t pk[16];
-            if (p.relu) {
+            if (kFwdOps && p.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(v[2 * i], v[2 * i + 1]);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             }
-            if (p.bits_out.ptr != nullptr) {
-              // ReLU mask of the stored output, 1 bit per element: word i (channels 2i, 2i+1 of this 32-channel half)
-              // contributes bit 15-i (channel 2i) and bit 31-i (channel 2i+1)
-              const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+            if (kFwdOps && p.bits_out.ptr != nullptr) {
+              // ReLU mask of the stored output, 1 bit per element: channel c (0..31) of this half  <->  bit
+              // (7 - (c >> 2)) + 8 (c & 3).  The stored values are >= 0, so "!= 0" is the carry of (half + 0x7FFF) into
+              // the half's top bit; PRMT gathers the four flag bytes of a word pair, 2.5 instructions per word.
               uint32_t bw = 0u;
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                bw = bw * 2u + (__hne2_mask(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]), z2) & 0x00010001u);
+              for (int sp = 7; sp >= 0; --sp) {
+                const uint32_t ya = pk[2 * sp] + 0x7FFF7FFFu, yb = pk[2 * sp + 1] + 0x7FFF7FFFu;
+                bw = (bw >> 1) | (prmt(ya, yb, 0x7531u) & 0x80808080u);
+              }
               if (hf == 0) obits.x = bw; else obits.y = bw;
             }
             if (has_mbits) {
+              // shift the four bits of word pair sp to the top of the four bytes; PRMT's sign-replication mode expands
+              // them to 0xFFFF / 0 half masks (2.5 instructions per word)
               const uint32_t b = hf == 0 ? mb.x : mb.y;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] &= ((b >> (15 - i)) & 0x00010001u) * 0xFFFFu;
+              for (int sp = 0; sp < 8; ++sp) {
+                const uint32_t t = b << sp;
+                pk[2 * sp] &= prmt(t, 0u, 0x9988u);
+                pk[2 * sp + 1] &= prmt(t, 0u, 0xBBAAu);
+              }
             }
-            if (p.has_mask) {
+            if (kBwdOps && p.has_mask) {
               const uint8_t* ms = in_slab + p.has_add * kSlabBytes;
               const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
@@ -626,7 +642,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               *reinterpret_cast<uint4*>(out_slab + uoff[hf * 4 + i]) =
                   make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
-          if (p.bits_out.ptr != nullptr && in_img) {
+          if (kFwdOps && p.bits_out.ptr != nullptr && in_img) {
             char* a = static_cast<char*>(p.bits_out.ptr) + (long long)cur.img * p.bits_out.sn +
                       (long long)(cur.h0 + rh) * p.bits_out.sh + (long long)(cur.w0 + rw) * p.bits_out.sw + (col0 >> 3);
             *reinterpret_cast<uint2*>(a) = obits;
@@ -638,19 +654,28 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             tma_store_commit();
             if (n_in > 0 && pf.valid) issue_prefetch();   // refill the input slot just consumed
           }
-          if (p.colsum != nullptr) {
+          if (kBwdOps && p.colsum != nullptr) {
             // lane l sums channel pair l of this chunk over the 32 rows of the bf16 output slab (conflict free:
             // at a fixed row the 32 lanes read the 32 distinct words of one 128-byte line)
-            float s0 = 0.f, s1 = 0.f;
-            const int c16 = lane >> 2, wsel = (lane & 3) << 2;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(out_slab + r * 128 + ((c16 ^ (r & 7)) << 4) + wsel);
-              s0 += bf16_lo(u);
-              s1 += bf16_hi(u);
+            // (row r = 8 g + k sits at g * 1024 + k * 128, its 16-byte unit c16 at (c16 ^ k) << 4: the eight per-k offsets
+            // are loop invariant, so the unrolled loop is LDS [reg + immediate] + 2 unpack + 2 FADD per row -- it used to
+            // spend 13 instructions per row, more than the rest of the epilogue)
+            float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+            const uint32_t slab_a = smem_u32(out_slab);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+              for (int k = 0; k < 8; k += 2) {
+                const uint32_t u = lds32(slab_a + csoff[k] + g * 1024);
+                const uint32_t v2 = lds32(slab_a + csoff[k + 1] + g * 1024);
+                s0 += bf16_lo(u);
+                s1 += bf16_hi(u);
+                t0 += bf16_lo(v2);
+                t1 += bf16_hi(v2);
+              }
             }
-            atomicAdd(&s_colacc[col0 + 2 * lane], s0);
-            atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1);
+            atomicAdd(&s_colacc[col0 + 2 * lane], s0 + t0);
+            atomicAdd(&s_colacc[col0 + 2 * lane + 1], s1 + t1);
           }
           ++n_done;
           if (++in_slot == kEiDepth) {
@@ -793,22 +818,31 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 // ====================================================================================== host side
 struct urso_convgemm {
   urso::ConvGemmParams params;
+  int flavor;      // epilogue specialisation of the kernel template (0 general, 1 forward, 2 gradient)
   int block_n;
   int grid;
   int smem_bytes;
 };
 
-template <int BLOCK_N>
-static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
+template <int BLOCK_N, int FLAVOR>
+static int launch_conv_gemm_f(const urso_convgemm* h, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    URSO_CUDA_OK(cudaFuncSetAttribute(urso::conv_gemm_kernel<BLOCK_N, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
+  urso::conv_gemm_kernel<BLOCK_N, FLAVOR><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
+}
+template <int BLOCK_N>
+static int launch_conv_gemm(const urso_convgemm* h, cudaStream_t stream) {
+  if constexpr (BLOCK_N >= 64) {
+    if (h->flavor == 1) return launch_conv_gemm_f<BLOCK_N, 1>(h, stream);
+    if (h->flavor == 2) return launch_conv_gemm_f<BLOCK_N, 2>(h, stream);
+  }
+  return launch_conv_gemm_f<BLOCK_N, 0>(h, stream);
 }
 
 static int make_pix_map(CUtensorMap* out, const urso_pix& px, int C, int W, int H, int N, int bw, int bh) {
@@ -1098,6 +1132,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.relu = d->relu;
   p.shift = d->shift;
   p.colsum = d->colsum;
+  const bool bwd_ops = d->mask.ptr != nullptr || d->mask_bits.ptr != nullptr || d->colsum != nullptr;
+  const bool fwd_ops = d->shift != nullptr || d->relu != 0 || d->relu_bits.ptr != nullptr;
+  h->flavor = !p.epi_tma ? 0 : (!bwd_ops ? 1 : (!fwd_ops ? 2 : 0));
   *out = h;
   return 0;
 }
