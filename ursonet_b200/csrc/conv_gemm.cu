@@ -35,8 +35,8 @@
 //  * optional fused per-channel sums of the stored output (d beta): read back from the bf16 output slab
 //    (conflict free), accumulated per CTA in shared memory, flushed with one atomic per channel per CTA.
 //
-// Roles (512 threads): warps 0 and 3 = TMA producers, warps 1 and 2 = MMA issuers (warp 2 also allocates TMEM),
-// warps 4-11 (or 4-15: three sets per TMEM lane quadrant for epilogue-bound launches) = epilogue.  With one pipeline the two producers take alternate barrier rounds and warp 2 only allocates.
+// Roles (384 threads): warps 0 and 3 = TMA producers, warps 1 and 2 = MMA issuers (warp 2 also allocates TMEM),
+// warps 4-11 = epilogue.  With one pipeline the two producers take alternate barrier rounds and warp 2 only allocates.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -91,8 +91,6 @@ struct ConvGemmParams {
   int bres_off, ctrl_off;
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
-  int epi_sets;      // TMA epilogue: warp sets per TMEM lane quadrant (2 or 3 -> 8 or 12 epilogue warps), each set takes
-                     // every epi_sets-th 64-channel chunk of the CTA's stream
   int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
   int eo_depth;      // per-warp output slabs (TMA stores in flight)
   int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
@@ -169,19 +167,13 @@ struct ChunkIter {
       load(p);
     }
   }
-  // my next chunk: every nsets-th one of the stream
-  __device__ __forceinline__ void step(const ConvGemmParams& p, int nsets) {
-    next(p);
-    for (int i = 1; i < nsets; ++i)
-      if (valid) next(p);
-  }
 };
 
 // FLAVOR specialises the TMA epilogue at compile time (the epilogue's instruction issue bounds every short-K launch, and
 // ~10 % of its instructions were uniform branches on launch flags): 0 = every option at run time; 1 = forward convs (no
 // mask / mask bits / column sums compiled in); 2 = gradient launches (no shift / ReLU / mask-bit output compiled in).
 template <int BLOCK_N, int FLAVOR>
-__global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr bool kFwdOps = FLAVOR != 2, kBwdOps = FLAVOR != 1;
   constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   // 1024-byte aligned by declaration (SWIZZLE_128B atoms): no integer round trip on the base pointer, so the compiler
@@ -197,8 +189,8 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* tfull_bar = aempty_bar + 8;                              // [4] accumulator stages (2 per pipeline)
   uint64_t* tempty_bar = tfull_bar + 4;                              // [4]
   uint64_t* bres_bar = tempty_bar + 4;                               // [1] resident weight operand loaded
-  uint64_t* ei_bar = bres_bar + 1;                                   // [12 warps][kMaxEiDepth]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 12 * kMaxEiDepth);
+  uint64_t* ei_bar = bres_bar + 1;                                   // [8 warps][kMaxEiDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 8 * kMaxEiDepth);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
   float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes);   // legacy epilogue only
 
@@ -226,10 +218,10 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], p.epi_tma ? 4 * p.epi_sets : 4);
+      mbar_init(&tempty_bar[i], p.epi_tma ? 8 : 4);
     }
     mbar_init(bres_bar, 1);
-    for (int i = 0; i < 12 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
+    for (int i = 0; i < 8 * kMaxEiDepth; ++i) mbar_init(&ei_bar[i], 1);
     fence_barrier_init();
   }
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled layouts assume it
@@ -464,13 +456,12 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && (p.epi_tma ? warp < 4 + 4 * p.epi_sets : warp < 8)) {
+  } else if (warp >= 4 && (p.epi_tma || warp < 8)) {
     // ------------------------------------------------------------------ epilogue
     // TMA flavour: 8 warps = 4 TMEM lane quadrants x 2 column halves (two warps share each 32-row x 64-channel
     // slab: more warps per scheduler hide the ALU latency of the elementwise work).  Legacy flavour: warps 4-7 only.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int set = (warp - 4) >> 2;      // warp set within the quadrant
-    const int nsets = p.epi_sets;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int rh = row >> p.tw_shift, rw = row & (p.TW - 1);
     if (p.epi_tma) {
@@ -481,7 +472,7 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
       const int n_in = p.has_add + p.has_mask;
       const int slot_bytes = n_in * kSlabBytes;
       const int kEiDepth = p.ei_depth, kEoDepth = p.eo_depth;
-      const int wslot = set * 4 + q;                                    // this warp's ring index
+      const int wslot = half * 4 + q;                                    // this warp's ring index
       uint8_t* ei = smem + p.ei_off + wslot * kEiDepth * slot_bytes;
       uint8_t* eo = smem + p.eo_off + wslot * kEoDepth * kSlabBytes;
       uint64_t* my_bar = ei_bar + wslot * kMaxEiDepth;
@@ -495,8 +486,7 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
       for (int k = 0; k < 8; ++k) csoff[k] = (uint32_t)(k * 128 + ((((lane >> 2) ^ k) << 4) + ((lane & 3) << 2)));
       ChunkIter<BLOCK_N> cur, pf;
       cur.init(p);
-      for (int i = 0; i < set; ++i)                // set s starts at chunk s of the stream
-        if (cur.valid) cur.next(p);
+      if (half == 1 && cur.valid) cur.next(p);     // set 1 starts at the second chunk of the stream
       pf = cur;
       int pf_slot = 0;                             // ring slot of the next prefetch
       auto issue_prefetch = [&]() {                // lane 0 only
@@ -508,7 +498,8 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
         if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         if (p.has_mask)
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
-        pf.step(p, nsets);                         // my chunks are every nsets-th one
+        pf.next(p);
+        if (pf.valid) pf.next(p);                  // my chunks are every other one
       };
       if (n_in > 0 && lane == 0) {
         for (int i = 0; i < kEiDepth && pf.valid; ++i) issue_prefetch();
@@ -551,7 +542,8 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
           uint2 mb = make_uint2(0u, 0u);
           if (has_mbits) {   // this chunk's mask words were loaded one chunk ago; start the load for my next chunk
             mb = mb_next;
-            nxt.step(p, nsets);
+            nxt.next(p);
+            if (nxt.valid) nxt.next(p);
             mb_next = load_mask_bits(nxt);
           }
           if (n_done >= kEoDepth) {   // the TMA store that last used this output slab must have drained it
@@ -691,7 +683,8 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
             in_phase ^= 1;
           }
           if (++out_slot == kEoDepth) out_slot = 0;
-          cur.step(p, nsets);           // skip the other warp sets' chunks
+          cur.next(p);
+          if (cur.valid) cur.next(p);   // skip the other warp set's chunk
         }
         // all of this warp's TMEM reads of the tile are complete: release the accumulator stage (8 arrivals)
         tc_fence_before();
@@ -803,7 +796,7 @@ __global__ void __launch_bounds__(512, 1) conv_gemm_kernel(const __grid_constant
       }
     }
     if (p.colsum != nullptr) {
-      const int n_epi = p.epi_tma ? 128 * p.epi_sets : 128;         // the epilogue warps only
+      const int n_epi = p.epi_tma ? 256 : 128;         // the epilogue warps only
       asm volatile("bar.sync 5, %0;" ::"r"(n_epi) : "memory");
       for (int c = threadIdx.x - 128; c < p.ncols; c += n_epi) {
         const float s = s_colacc[c];
@@ -839,7 +832,7 @@ static int launch_conv_gemm_f(const urso_convgemm* h, cudaStream_t stream) {
                                       227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N, FLAVOR><<<h->grid, 512, h->smem_bytes, stream>>>(h->params);
+  urso::conv_gemm_kernel<BLOCK_N, FLAVOR><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1001,26 +994,16 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
     p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
     if (n_in > 0 && epi_bound) p.ei_depth = 2;
-    // epilogue-bound launches (short K, several chunks per tile): three warp sets per quadrant instead of two.  ncu: the
-    // epilogue warps issue only ~0.35 instructions per cycle and scheduler with two of them resident (dependent
-    // tcgen05.ld -> ALU -> st.shared chains), and a third warp per scheduler fits the register file (<= 128 registers).
-    p.epi_sets = (epi_bound && d->b_rows >= 128) ? 3 : 2;
-    if (p.epi_sets == 3) {      // same bytes in flight as two sets with deeper rings
-      p.ei_depth = 1;
-      p.eo_depth = n_in == 2 ? 1 : 2;
-    }
-    const int nw = 4 * p.epi_sets;
-    epi_bytes = nw * p.ei_depth * n_in * kSlabBytes + nw * p.eo_depth * kSlabBytes;
+    epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
     const int bn_min = bn == 256 ? 128 : bn;   // the narrowest tile this launch may fall back to must still get 2 stages
     if (p.ei_depth == 2 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
       p.ei_depth = 1;
-      epi_bytes = nw * p.ei_depth * n_in * kSlabBytes + nw * p.eo_depth * kSlabBytes;
+      epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
     }
     const int min_stages = (n_in > 0 && epi_bound) ? 2 : 3;
     if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
   } else {
     epi_bytes = kLegacyScratchBytes;
-    p.epi_sets = 1;
   }
   h->block_n = bn;
   p.n_tiles_n = (d->b_rows + bn - 1) / bn;
@@ -1066,7 +1049,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     if (attempt == 1) {
       if (!p.epi_tma || (p.ei_depth == 1 && p.eo_depth == 1)) break;
       p.ei_depth = p.eo_depth = 1;
-      epi_bytes = 4 * p.epi_sets * (n_in + 1) * kSlabBytes;
+      epi_bytes = 8 * n_in * kSlabBytes + 8 * kSlabBytes;
     }
     const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes;
     if (d->halo) {
@@ -1107,8 +1090,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   const int fixed = p.ctrl_off + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
-    p.eo_off = p.ei_off + 4 * p.epi_sets * p.ei_depth * n_in * kSlabBytes;
-    h->smem_bytes = p.eo_off + 4 * p.epi_sets * p.eo_depth * kSlabBytes;
+    p.eo_off = p.ei_off + 8 * p.ei_depth * n_in * kSlabBytes;
+    h->smem_bytes = p.eo_off + 8 * p.eo_depth * kSlabBytes;
   } else {
     h->smem_bytes = fixed + kLegacyScratchBytes;
   }
