@@ -116,8 +116,9 @@ def test_bench_workload_gets_the_intended_modes(dry):
     for name in ("conv1", "res2a_branch2b", "res2b_branch2b", "res2c_branch2b"):
         assert infos[name]["halo"] == 1 and infos[name]["bres"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
     # the 3x3 input gradients plan like their forward twins now that the ReLU mask is bit-packed (no smem ring for it)
-    # (the last block of a stage has a sparse output gradient: its 3x3 dgrad runs as 4 decimated phase launches instead)
-    for name in ("d:res2a_branch2a", "d:res2b_branch2a"):
+    # (the last block of a stage has a sparse output gradient: from 128 channels on its 3x3 dgrad runs as 4 decimated phase
+    # launches instead; the 64-channel one stays dense, which is faster)
+    for name in ("d:res2a_branch2a", "d:res2b_branch2a", "d:res2c_branch2a"):
         assert infos[name]["halo"] == 1 and infos[name]["bres"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
     for name in ("d:res3a_branch2a", "d:res3c_branch2a"):
         assert infos[name]["halo"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])

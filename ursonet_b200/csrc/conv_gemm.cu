@@ -95,6 +95,8 @@ struct ConvGemmParams {
   int eo_depth;      // per-warp output slabs (TMA stores in flight)
   int ei_off, eo_off;  // byte offsets of the epilogue input ring / output slabs from the aligned smem base
   int colacc_bytes;    // per-CTA column-sum accumulator (0 when the launch has no colsum: the space goes to stages)
+  int shift_bytes;     // TMA epilogue: shared-memory copy of shift[] (the epilogue read it with 16 global loads per chunk whose
+                       // L2 latency sat on every warp's critical path: ncu long-scoreboard stalls on the shift FADDs)
   PixDev out, addend, mask;
   PixDev bits_out, mask_bits;   // bit-packed ReLU masks (1 bit per element, 32-channel words): strides in BYTES
   int out_fp32, relu;
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* ei_bar = bres_bar + 1;                                   // [8 warps][kMaxEiDepth]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ei_bar + 8 * kMaxEiDepth);
   float* s_colacc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
-  float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes);   // legacy epilogue only
+  float* s_shift = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes);
+  float* s_tr = reinterpret_cast<float*>(ctrl + kCtrlBytes + p.colacc_bytes + p.shift_bytes);   // legacy epilogue only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,6 +232,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   if (p.colsum != nullptr) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_colacc[c] = 0.0f;
+  }
+  if (p.shift_bytes) {
+    for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_shift[c] = __ldg(p.shift + c);
   }
   tc_fence_before();
   __syncthreads();
@@ -565,10 +571,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
             if (kFwdOps && p.shift != nullptr) {
-              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0 + hf * 32);
+              const float4* sp = reinterpret_cast<const float4*>(s_shift + col0 + hf * 32);    // broadcast LDS.128
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 s4 = __ldg(sp + i);
+                const float4 s4 = sp[i];
                 v[4 * i + 0] += s4.x;
                 v[4 * i + 1] += s4.y;
                 v[4 * i + 2] += s4.z;
@@ -602,12 +608,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               // ReLU mask of the stored output, 1 bit per element: channel c (0..31) of this half  <->  bit
               // (7 - (c >> 2)) + 8 (c & 3).  The stored values are >= 0, so "!= 0" is the carry of (half + 0x7FFF) into
               // the half's top bit; PRMT gathers the four flag bytes of a word pair, 2.5 instructions per word.
-              uint32_t bw = 0u;
+              uint32_t bw0 = 0u, bw1 = 0u;      // two independent dependency chains (even / odd word pairs)
 #pragma unroll
-              for (int sp = 7; sp >= 0; --sp) {
+              for (int sp = 6; sp >= 0; sp -= 2) {
                 const uint32_t ya = pk[2 * sp] + 0x7FFF7FFFu, yb = pk[2 * sp + 1] + 0x7FFF7FFFu;
-                bw = (bw >> 1) | (prmt(ya, yb, 0x7531u) & 0x80808080u);
+                const uint32_t yc = pk[2 * sp + 2] + 0x7FFF7FFFu, yd = pk[2 * sp + 3] + 0x7FFF7FFFu;
+                bw0 = (bw0 >> 2) | (prmt(ya, yb, 0x7531u) & 0x80808080u);
+                bw1 = (bw1 >> 2) | (prmt(yc, yd, 0x7531u) & 0x80808080u);
               }
+              const uint32_t bw = bw0 | (bw1 >> 1);
               if (hf == 0) obits.x = bw; else obits.y = bw;
             }
             if (has_mbits) {
@@ -967,11 +976,13 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     return 2;
   }
   // epilogue flavour and its shared memory
-  const int kColAcc = d->colsum != nullptr ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
-  p.colacc_bytes = kColAcc;
+  const int kColAccOnly = d->colsum != nullptr ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
+  p.colacc_bytes = kColAccOnly;
   p.has_add = d->addend.ptr != nullptr;
   p.has_mask = d->mask.ptr != nullptr;
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
+  p.shift_bytes = (p.epi_tma && d->shift != nullptr) ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
+  const int kColAcc = kColAccOnly + p.shift_bytes;     // everything between the control block and the epilogue rings
   if ((d->relu_bits.ptr != nullptr || d->mask_bits.ptr != nullptr) && !p.epi_tma) {
     set_error("bit-packed masks need the bf16 TMA epilogue (bf16 output, channels a multiple of 64)");
     delete h;

@@ -538,6 +538,10 @@ class Engine:
         # 9 -> 2.25 taps on average for a 3x3.  The never-written odd phases stay zero from allocation (torch.zeros), so
         # any launch that reads such a buffer densely (e.g. as the gradient fan-in addend) is still exact.
         sparse_in = self.sparse_bwd and all(c.dst in self.sparse and c.stride == 1 for c in convs)
+        if sparse_in and all(c.k == 3 for c in convs) and cin <= 64:
+            # measured (profiles/r02_progress.md): for the 64-channel 3x3 the dense launch (halo + resident weights + two
+            # pipelines, 0.088 ms) beats the four decimated phase launches (0.104 ms); it just multiplies the zeros
+            sparse_in = False
         stride = convs[0].stride * (2 if sparse_in else 1)
         assert all(c.stride == convs[0].stride for c in convs)
         assert not (adds and convs[0].stride != 1)

@@ -204,6 +204,8 @@ def backward_groups(g: Graph, sparse_bwd: bool = True):
         need_cs = prod is not None and bool(prod.bias or prod.bn or prod.addend in
                                             [c.dst for c in g.convs if not c.relu and (c.bias or c.bn)])
         sparse_in = sparse_bwd and all(c.dst in sparse and c.stride == 1 for c in convs)
+        if sparse_in and all(c.k == 3 for c in convs) and g.shapes[X][2] <= 64:
+            sparse_in = False          # the dense halo / resident-weight launch is faster for the 64-channel 3x3
         stride = convs[0].stride * (2 if sparse_in else 1)
         only_phase0 = stride == 2 and all(c.k == 1 for c in convs)
         h, w, _ = g.shapes[X]
