@@ -242,3 +242,45 @@ def test_first_graph_step_equals_eager_step():
         # a doubled update would give d_graph ~ 2 * d_eager (SGD: 1.9x with momentum), i.e. a relative difference ~ 1;
         # atomic summation order + the chaotic random net give ~2e-3 (measured)
         assert (d_eager - d_graph).norm().item() <= 5e-2 * d_eager.norm().item(), opt
+
+
+@pytest.mark.parametrize("nr_dense", [0, 2])
+def test_nr_dense_layers_0_and_2_train_parity(nr_dense):
+    """build_loc_graph / build_ori_graph allow NR_DENSE_LAYERS in {0, 1, 2} (net.py:293,327); the CLI fixes 1.  Forward,
+    losses and every head gradient against the fp64 oracle (heads are fp32: 1e-4), conv stack layer-local."""
+    from ursonet_b200.engine import Engine
+    cfg = make_cfg("resnet18", True)
+    cfg.NR_DENSE_LAYERS = nr_dense
+    cfg.update()
+    B = 2
+    p64 = O.init_weights(cfg, seed=81, pretrained_like=True)
+    eng = Engine(cfg, B, training=True)
+    load_oracle_weights(eng, p64)
+    img, gt_loc, gt_ori = make_batch(cfg, B, seed=82)
+    eng.img_u8.copy_(img); eng.gt_loc.copy_(gt_loc); eng.gt_ori.copy_(gt_ori)
+    eng._phase_train()
+    torch.cuda.synchronize()
+    rep = local_backward_check(eng, p64, cfg)
+    bad = [(n, round(e, 5)) for n, e in rep if e > 4e-3]
+    assert not bad, bad[:12]
+    # heads: recompute in fp64 from the engine's own bottleneck output, with autograd for the head gradients
+    P64 = {k: v.double().clone().requires_grad_(k.split("/")[0].startswith(("loc_", "ori_"))) for k, v in p64.items()}
+    feat = eng.act["bottleneck_layer"].double().cpu().reshape(B, -1).requires_grad_(True)
+    outs = {}
+    for branch in ("loc", "ori"):
+        x = feat
+        for i in range(nr_dense):
+            x = torch.relu(x @ P64[f"{branch}_dense_{i}/kernel"] + P64[f"{branch}_dense_{i}/bias"])
+        outs[branch] = x
+    loc = outs["loc"] @ P64["loc_final/kernel"] + P64["loc_final/bias"]
+    z = torch.relu(outs["ori"] @ P64["ori_final/kernel"] + P64["ori_final/bias"])
+    loss = O.rel_loss(gt_loc.double(), loc) + O.softmax_loss(gt_ori.double(), z)
+    names = [k for k, v in P64.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [P64[k] for k in names] + [feat])
+    assert rel(eng.head["loc_final"].double().cpu(), loc.detach()) <= 1e-4
+    assert rel(eng.head["ori_final"].double().cpu(), z.detach()) <= 1e-4
+    for k, gref in zip(names, grads[:-1]):
+        got = eng.params.view(k, eng.grads).double().cpu()
+        assert (got - gref).norm().item() <= 1e-4 * max(gref.norm().item(), 1e-12) + 1e-9, k
+    dfeat = (eng.dfeat[0] + eng.dfeat[1]).double().cpu()
+    assert rel(dfeat, grads[-1]) <= 1e-4

@@ -450,8 +450,7 @@ class Engine:
             op_d = self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
             self._add(self.ops_bwd, OpRec(run_w, "dense_wgrad", d.name, 2.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 2,
                                           lane=self.aux_lane, after=[op_d]))
-        if cfg.NR_DENSE_LAYERS == 0:
-            raise NotImplementedError("NR_DENSE_LAYERS=0 backward")   # CLI fixes it to 1 (pose_estimator.py:820)
+        assert cfg.NR_DENSE_LAYERS in range(3)      # net.py:293,327 (the CLI fixes it to 1, pose_estimator.py:820)
 
         # ---- gradient buffers of activations
         bw = g.shapes["bottleneck_layer"][2]
@@ -696,7 +695,12 @@ class Engine:
                 op()
             return
         main, streams = self._main, self._lane_streams
+        skip_aux = os.environ.get("URSO_TIMING_SKIP_AUX") == "1"      # timing experiment only: results are garbage
         for op in ops:
+            if skip_aux and op.lane == self.aux_lane and op.kind in ("stage", "param_grads", "dense_wgrad"):
+                op.event = op.event or torch.cuda.Event()
+                op.event.record(main)
+                continue
             st = main if op.lane == 0 else streams[op.lane]
             for a in op.after:
                 # Only in the split schedule does an earlier segment end with a full join (and live in another captured
