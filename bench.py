@@ -152,6 +152,8 @@ def main():
                          "micro-batches of --batch with gradient accumulation; reported as strong scaling")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
     args = ap.parse_args()
@@ -193,7 +195,8 @@ def main():
         args.batch = min(args.batch, per_rank)
         n_micro = per_rank // args.batch
         workload += f", global batch {args.global_batch} = {world} ranks x {n_micro} micro-batches x {args.batch}"
-    eng = Engine(cfg, args.batch, training=True, world_size=world, seed=0)
+    eng = Engine(cfg, args.batch, training=True, world_size=world, seed=0,
+                 reserve_sms=args.reserve_sms if (world > 1 and args.overlap) else 0)
     img, loc, ori = synth_batch(cfg, args.batch, seed=rank)
     h_img, h_loc, h_ori = img.pin_memory(), loc.pin_memory(), ori.pin_memory()
     eng.img_u8.copy_(h_img)

@@ -172,6 +172,8 @@ int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream);
 int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream);
 void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h);
 int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9); /* see urso_convgemm_plan_info */
+/* the staging work of this operator as a job of urso_stage_weights_multi (declared below) */
+int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* stage_job_out);
 
 /* Input gradient with fused fan-in: dx = mask( sum_i dgrad_i(dy_i, w_i) + addend ), one launch per output phase
  * (stride^2 phases), the convolutions' reduction ranges concatenated.  All consumers share x's shape and stride.
@@ -208,6 +210,9 @@ int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream);
 int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h);
 int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h);
 int urso_conv2d_dgrad_plan_info(const urso_conv2d_dgrad_t* h, int32_t launch, int32_t* out9); /* see urso_convgemm_plan_info */
+/* the staging work of this operator as jobs of urso_stage_weights_multi: writes up to max_jobs urso_stage_job structs,
+ * returns how many the operator has (negative on error) */
+int urso_conv2d_dgrad_stage_jobs(const urso_conv2d_dgrad_t* h, void* stage_jobs_out, int32_t max_jobs);
 void urso_conv2d_dgrad_destroy(urso_conv2d_dgrad_t* h);
 
 /* Raw weight gradient G[k*k*C, K] (fp32, HWIO order, accumulated with atomics: the caller zeroes it) of the UNSCALED
@@ -288,6 +293,48 @@ int urso_conv_param_grads(const float* G, const int32_t* g_row_map_dev, const fl
                           const float* scale, const float* gamma, const float* mean, const float* var,
                           const float* bias, float eps, float* dW, float* dbias, float* dgamma, float* dbeta,
                           float* s_scratch, int32_t R, int32_t CO, void* stream);
+
+/* ---- Multi-tensor versions of the three small per-layer kernels above: ONE launch covers every layer of the network
+ * through a device-resident job table (host code fills the structs, copies the table to the device once at plan time).
+ * Next to the persistent convolution CTAs ~330 tiny launches per step effectively serialised with the convolutions
+ * (1.4 ms of a 13.7 ms RN-50 step); the tables bring that to a handful of launches.
+ *   urso_bn_fold_multi           one job per convolution (gamma == NULL: no BN)
+ *   urso_stage_weights_multi     kind 0 = urso_stage_weight_rows (tile transpose through shared memory), kind 1 =
+ *                                urso_stage_weight_cols; urso_conv2d_{fwd,dgrad}_stage_job(s) export the jobs of operators
+ *   urso_conv_param_grads_multi  urso_conv_param_grads for many convolutions (S zeroed by the caller)
+ * *_jobs_finalize assign each job its first block and return the grid size; begins[] is the same list as an array. */
+typedef struct {
+  const float *gamma, *beta, *mean, *var, *bias;
+  float *scale, *shift;
+  int32_t C, pad_;
+} urso_bn_job;
+typedef struct {
+  const float* w;
+  const float* scale;
+  void* out;
+  const int32_t* index; /* kind 0: idx[K]; kind 1: tap[n_slots] (device) */
+  int32_t kind, K;      /* K: kind 0 = columns of the operand; kind 1 = number of tap slots */
+  int32_t CI, CO, COp, rows_out;
+  int64_t ld_out;
+  int32_t part, block_begin;
+} urso_stage_job;
+typedef struct {
+  const float* G;
+  const int32_t* g_row_map;
+  const float *w, *colsum, *scale, *gamma, *mean, *var, *bias;
+  float *dW, *dbias, *dgamma, *dbeta, *S;
+  int32_t R, CO, rows_per_slab, cblocks, block_begin, pad_;
+} urso_pgrad_job;
+int urso_sizeof_bn_job(void);
+int urso_sizeof_stage_job(void);
+int urso_sizeof_pgrad_job(void);
+int urso_bn_fold_multi(const urso_bn_job* jobs_dev, int32_t n_jobs, int32_t max_c, float eps, void* stream);
+int32_t urso_stage_jobs_finalize(urso_stage_job* jobs_host, int32_t n, int32_t* begins_out);
+int urso_stage_weights_multi(const urso_stage_job* jobs_dev, const int32_t* begins_dev, int32_t n_jobs, int32_t total_blocks,
+                             void* stream);
+int32_t urso_pgrad_jobs_finalize(urso_pgrad_job* jobs_host, int32_t n, int32_t* begins_out);
+int urso_conv_param_grads_multi(const urso_pgrad_job* jobs_dev, const int32_t* begins_dev, int32_t n_jobs,
+                                int32_t total_blocks, int32_t max_co, float eps, void* stream);
 
 /* ---- Optimizer (net.py:979-983,1008-1012; Keras-2 SGD / Adam(amsgrad) with global-norm clipnorm) over flat arenas.
  * chunk_coef[i] applies to elements [256 i, 256 i + 256): reg gradient 2*wd/size(w) (0 for gamma/beta);

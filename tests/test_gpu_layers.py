@@ -186,6 +186,81 @@ def test_bn_fold_stage_and_param_grads():
     assert torch.allclose(dgamma.double().cpu(), gg, rtol=1e-3, atol=1e-3)
 
 
+def test_multi_tensor_job_tables_equal_the_per_layer_kernels():
+    """urso_bn_fold_multi / urso_stage_weights_multi / urso_conv_param_grads_multi (one launch for all layers through a
+    device job table) give bit-identical results to the per-layer entry points, for layers of different shapes
+    (with / without BN, with / without bias, stem-style row map, odd channel counts)."""
+    import ctypes as C
+    lib = L()
+    from ursonet_b200 import convplan as P
+    g = torch.Generator().manual_seed(7)
+    s = lib.stream_ptr()
+    d = lambda t: None if t is None else t.to(DEV).contiguous()
+    layers = [(3, 64, 96, True, True), (1, 128, 64, True, False), (3, 64, 32, False, True), (1, 256, 512, True, True)]
+    bn_jobs, stage_jobs, pg_jobs, singles = [], [], [], []
+    keep = []
+    for kh, CI, CO, has_bn, has_bias in layers:
+        w = d(torch.randn(kh, kh, CI, CO, generator=g) * 0.1)
+        gamma = d(torch.rand(CO, generator=g) + 0.5) if has_bn else None
+        beta = d(torch.randn(CO, generator=g)) if has_bn else None
+        mean = d(torch.randn(CO, generator=g)) if has_bn else None
+        var = d(torch.rand(CO, generator=g) + 0.5) if has_bn else None
+        bias = d(torch.randn(CO, generator=g)) if has_bias else None
+        sc_m, sh_m, sc_s, sh_s = (torch.empty(CO, device=DEV) for _ in range(4))
+        bn_jobs.append((gamma, beta, mean, var, bias, sc_m, sh_m, CO))
+        lib.call("urso_bn_fold", lib.ptr(gamma), lib.ptr(beta), lib.ptr(mean), lib.ptr(var), lib.ptr(bias), 1e-3,
+                 sc_s.data_ptr(), sh_s.data_ptr(), CO, s)
+        geom = P.make_geom(kh, 1, "same", CI, CO, 8, 8)
+        _, idx = P.fwd_segments(geom)
+        (_, _, _, tap_map), = P.dgrad_phases(geom)
+        cop, K = P.ceil64(CO), len(idx)
+        idx_d = torch.tensor(idx, dtype=torch.int32, device=DEV)
+        tap_d = torch.tensor(tap_map, dtype=torch.int32, device=DEV)
+        rows_out = P.ceil64(CO) if CO % 64 else CO
+        o_rows_m, o_rows_s = (torch.zeros(rows_out, K, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+        o_cols_m, o_cols_s = (torch.zeros(CI, len(tap_map) * cop, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+        stage_jobs.append(lib.StageJob(w.data_ptr(), sc_s.data_ptr(), o_rows_m.data_ptr(), idx_d.data_ptr(), 0, K, 0, CO, 0,
+                                       rows_out, K, 0, 0))
+        stage_jobs.append(lib.StageJob(w.data_ptr(), sc_s.data_ptr(), o_cols_m.data_ptr(), tap_d.data_ptr(), 1, len(tap_map),
+                                       CI, CO, cop, CI, len(tap_map) * cop, 0, 0))
+        lib.call("urso_stage_weight_rows", w.data_ptr(), sc_s.data_ptr(), o_rows_s.data_ptr(), idx_d.data_ptr(), K, CO,
+                 rows_out, K, 0, s)
+        lib.call("urso_stage_weight_cols", w.data_ptr(), sc_s.data_ptr(), o_cols_s.data_ptr(), tap_d.data_ptr(), len(tap_map),
+                 CI, CO, cop, CI, len(tap_map) * cop, s)
+        R = kh * kh * CI
+        G = d(torch.randn(R, CO, generator=g))
+        colsum = d(torch.randn(CO, generator=g))
+        outs_m = [torch.zeros(R * CO, device=DEV)] + [torch.zeros(CO, device=DEV) for _ in range(4)]
+        outs_s = [torch.zeros(R * CO, device=DEV)] + [torch.zeros(CO, device=DEV) for _ in range(4)]
+        pg_jobs.append(dict(G=G, w=w, colsum=colsum, scale=sc_s, gamma=gamma, mean=mean, var=var, bias=bias, dW=outs_m[0],
+                            dbias=outs_m[1] if has_bias else None, dgamma=outs_m[2] if has_bn else None,
+                            dbeta=outs_m[3] if has_bn else None, S=outs_m[4] if has_bn else None, R=R, CO=CO))
+        lib.call("urso_conv_param_grads", G.data_ptr(), None, w.data_ptr(), colsum.data_ptr(), sc_s.data_ptr(),
+                 lib.ptr(gamma), lib.ptr(mean), lib.ptr(var), lib.ptr(bias), 1e-3, outs_s[0].data_ptr(),
+                 outs_s[1].data_ptr() if has_bias else None, outs_s[2].data_ptr() if has_bn else None,
+                 outs_s[3].data_ptr() if has_bn else None, outs_s[4].data_ptr() if has_bn else None, R, CO, s)
+        singles.append((sc_m, sc_s, sh_m, sh_s, o_rows_m, o_rows_s, o_cols_m, o_cols_s, outs_m, outs_s, has_bn, has_bias))
+        keep += [w, idx_d, tap_d, G, colsum]
+    bn_t = lib.BnFoldTable(bn_jobs, DEV)
+    bn_t.launch(1e-3)
+    arr = (lib.StageJob * len(stage_jobs))(*stage_jobs)
+    begins = (C.c_int32 * len(stage_jobs))()
+    total = lib.load().urso_stage_jobs_finalize(arr, len(stage_jobs), begins)
+    jd, bd = lib._table_to_device(arr, DEV), lib._table_to_device(begins, DEV)
+    lib.call("urso_stage_weights_multi", jd.data_ptr(), bd.data_ptr(), len(stage_jobs), total, s)
+    pg_t = lib.PgradTable(pg_jobs, DEV)
+    pg_t.launch(1e-3)
+    torch.cuda.synchronize()
+    for sc_m, sc_s, sh_m, sh_s, orm, ors, ocm, ocs, om, os_, has_bn, has_bias in singles:
+        assert torch.equal(sc_m, sc_s) and torch.equal(sh_m, sh_s)
+        assert torch.equal(orm, ors) and torch.equal(ocm, ocs)
+        assert torch.equal(om[0], os_[0])
+        if has_bias:
+            assert torch.equal(om[1], os_[1])
+        if has_bn:
+            assert torch.allclose(om[2], os_[2], rtol=1e-5, atol=1e-5) and torch.equal(om[3], os_[3])   # S: atomic order
+
+
 @pytest.mark.parametrize("opt", ["SGD", "ADAM"])
 def test_optimizer_matches_keras_restatement(opt):
     lib = L()

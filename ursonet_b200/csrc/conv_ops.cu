@@ -289,6 +289,14 @@ extern "C" int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_launch(h->plan, stream);
 }
+extern "C" int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* out_) {
+  URSO_REQUIRE(h != nullptr && out_ != nullptr, "null argument");
+  urso_stage_job* j = static_cast<urso_stage_job*>(out_);
+  memset(j, 0, sizeof(*j));
+  j->w = h->w; j->scale = h->scale; j->out = h->bmat; j->index = h->idx;
+  j->kind = 0; j->K = h->K; j->CO = h->cout; j->rows_out = h->cout; j->ld_out = h->K;
+  return 0;
+}
 extern "C" int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_plan_info(h->plan, out9);
@@ -484,6 +492,26 @@ extern "C" int urso_conv2d_dgrad_stage_weights(urso_conv2d_dgrad_t* h, void* str
         return rc;
     }
   return 0;
+}
+extern "C" int urso_conv2d_dgrad_stage_jobs(const urso_conv2d_dgrad_t* h, void* out_, int32_t max_jobs) {
+  if (h == nullptr || out_ == nullptr) return -1;
+  urso_stage_job* jobs = static_cast<urso_stage_job*>(out_);
+  int n = 0;
+  for (const DgradPhase& ph : h->phases)
+    for (const DgradPart& pt : ph.parts) {
+      if (n < max_jobs) {
+        const Geom& g = h->geoms[pt.conv];
+        urso_stage_job* j = &jobs[n];
+        memset(j, 0, sizeof(*j));
+        j->w = h->w[pt.conv]; j->scale = h->scale[pt.conv];
+        j->out = static_cast<char*>(ph.bmat) + (int64_t)pt.koff * 2;
+        j->index = pt.tap_dev;
+        j->kind = 1; j->K = (int32_t)pt.tap_map.size(); j->CI = g.cin; j->CO = g.cout; j->COp = pt.cop; j->rows_out = g.cin;
+        j->ld_out = ph.ktot;
+      }
+      ++n;
+    }
+  return n;
 }
 extern "C" int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream) {
   URSO_REQUIRE(h != nullptr, "null handle");

@@ -312,7 +312,7 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   int cols = p.taps_per_cta * bq;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols *= 2;
-  int sms = num_sms();
+  int sms = max_ctas();      // urso_set_max_ctas: leave SMs to a concurrent kernel (overlapped NCCL all-reduce)
   if (sms <= 0) sms = 148;
   int items = p.n_seg_groups * p.p_tiles * p.q_tiles;
   int split = d->split_k;

@@ -143,7 +143,7 @@ class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
-                 parity=None):
+                 parity=None, reserve_sms: int = 0):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -151,6 +151,10 @@ class Engine:
         self.parity = bool(getattr(cfg, "PARITY_MODE", False)) if parity is None else bool(parity)
         if self.parity and training:
             raise NotImplementedError("PARITY_MODE (split-bf16 operands) is forward-only")
+        # reserve_sms > 0: the convolution launches of the SECOND backward segment (the part that runs while the gradient
+        # all-reduce of the arena tail is in flight, see train_step(allreduce_async=...)) are planned with that many SMs
+        # left free, so that NCCL's kernel has somewhere to run: the persistent conv CTAs otherwise hold every SM
+        self.reserve_sms = int(reserve_sms)
         self.graph: Graph = build_graph(cfg)
         # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
         # chain); the weight-gradient launches run on their own lane(s) (wgrad of a layer only needs the du its dgrad
@@ -238,6 +242,32 @@ class Engine:
         self.zero_arena = torch.zeros(max(off, ALIGN), dtype=torch.float32, device=self.device)
         for fn in self._late_binds:
             fn()
+        if self.parity:
+            return
+        # multi-tensor job tables (one launch each for: BN fold, weight-operand staging, parameter gradients per segment)
+        self._bn_table = lib.BnFoldTable(self._bn_jobs, self.device)
+        self._stage_table = lib.StageTable(list(self.fwd_ops.values()), [b["p"] for b in self._dgrad_boxes], self.device)
+        self.ops_pgrad = []
+        if self.training:
+            for seg in (0, 1):
+                specs = [(mk, nb) for op, mk, nb in self._pgrad_specs if op.segment == seg]
+                if not specs:
+                    continue
+                table = lib.PgradTable([mk() for mk, _ in specs], self.device)
+                op = OpRec(lambda table=table: table.launch(BN_EPS), "param_grads", "segment %d" % seg, 0.0,
+                           sum(nb for _, nb in specs), launches=2)
+                op.segment = seg
+                self.ops_pgrad.append(op)
+
+    def _run_stage_tables(self):
+        self._bn_table.launch(BN_EPS)
+        self._stage_table.launch()
+
+    def _run_pgrad(self, segments=(0, 1)):
+        """Parameter gradients of all convolutions from the raw wgrads (main stream, after the lanes have joined)."""
+        for op in self.ops_pgrad:
+            if op.segment in segments:
+                op()
 
     # ------------------------------------------------------------------ plan helpers
     def _idx(self, values):
@@ -277,15 +307,18 @@ class Engine:
         self._late_binds = []
         self._last = {}
         self.fwd_ops: Dict[str, lib.Conv2dFwd] = {}
+        # BN fold + weight-operand staging of ALL layers: two multi-tensor launches (job tables built in
+        # _finalise_zero_arena, once the gradient operators exist too) instead of ~170 tiny per-layer launches
+        self._bn_jobs, self._dgrad_boxes, self._pgrad_specs = [], [], []
+        self._stage_op = self._add(self.ops_stage, OpRec(self._run_stage_tables, "stage", "all layers", launches=2,
+                                                         lane=self.aux_lane))
         self.relu_bits: Dict[str, torch.Tensor] = {}
         self.use_mask_bits = int(os.environ.get("URSO_MASK_BITS", "1")) != 0     # 0: bf16 activation as the mask (A/B runs)
         aux = self.aux_lane
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
             sc, sh = self.scale[c.name], self.shift[c.name]
-            self._add(self.ops_stage, OpRec(lambda bn=bn, bias=bias, sc=sc, sh=sh, c=c: lib.call(
-                "urso_bn_fold", lib.ptr(bn[0]), lib.ptr(bn[1]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
-                sc.data_ptr(), sh.data_ptr(), c.cout, S()), "stage", c.name, lane=aux))
+            self._bn_jobs.append((bn[0], bn[1], bn[2], bn[3], bias, sc, sh, c.cout))
             shape = self._conv_shape(c)
             oh, ow = lib.out_hw(shape)
             assert (oh, ow) == tuple(g.shapes[c.dst][:2]), (c.name, oh, ow, g.shapes[c.dst])
@@ -299,7 +332,7 @@ class Engine:
                 bits = self.relu_bits[c.dst] = torch.zeros((B, oh, ow, c.cout // 32), dtype=torch.int32, device=self.device)
             op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu, relu_bits=bits)
             self.fwd_ops[c.name] = op
-            staged = self._add(self.ops_stage, OpRec(op.stage, "stage", c.name, lane=aux))
+            staged = self._stage_op
             if c.stem:
                 ph, pw, _ = g.shapes[c.dst]
                 self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
@@ -571,7 +604,8 @@ class Engine:
         touched = dX.numel() / (4 if only_phase0 else 1)
         nbytes = 2.0 * (a_elems + touched * (1 + (mask is not None) + (addend is not None))
                         + sum(c.cout * c.k * c.k * c.cin for c in convs)) + (touched / 8 if mask_bits is not None else 0)
-        stage_op = self._add(self.ops_stage, OpRec(lambda: box["p"].stage(), "stage", "d:" + X, lane=self.aux_lane))
+        stage_op = self._stage_op
+        self._dgrad_boxes.append(box)
         if stride == 2 and not self.sparse_bwd:      # phases no filter tap reaches must read as zero
             self._add(self.ops_bwd, OpRec(lambda: box["p"].untouched and dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(),
                                           after=self._bwd_deps()))
@@ -580,9 +614,10 @@ class Engine:
 
         def bind():
             cs = self._zero_view(key) if key else None
-            box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs, dy_sparse=sparse_in,
-                                       mask_bits=mask_bits)
-            op.launches = stage_op.launches = box["p"].n_launches
+            with self._cta_limit(op):
+                box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs,
+                                           dy_sparse=sparse_in, mask_bits=mask_bits)
+            op.launches = box["p"].n_launches
             assert (box["p"].untouched == 0b1110) == only_phase0, (X, box["p"].untouched)
         self._late_binds.append(bind)
         self.dgrad_ops[X] = box
@@ -591,6 +626,22 @@ class Engine:
                                     colsum=key is not None, sparse_in=sparse_in, stride=stride, only_phase0=only_phase0))
         if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)
+
+    def _cta_limit(self, op):
+        """Context manager: plan the operator of a second-segment backward op with `reserve_sms` SMs left free."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            limit = self.reserve_sms > 0 and op.segment == 1
+            if limit:
+                lib.load().urso_set_max_ctas(max(1, lib.load().urso_num_sms() - self.reserve_sms))
+            try:
+                yield
+            finally:
+                if limit:
+                    lib.load().urso_set_max_ctas(0)
+        return cm()
 
     def _bwd_deps(self):
         """Cross-lane dependencies of a main-lane backward op: none (lane 0 is ordered by its stream); kept as a hook."""
@@ -617,7 +668,8 @@ class Engine:
         box = {}
 
         def bind():
-            box["p"] = lib.Conv2dWgrad(shape, x, du, self._zero_view(gkey), dy_sparse=sparse_du)
+            with self._cta_limit(wg_op):
+                box["p"] = lib.Conv2dWgrad(shape, x, du, self._zero_view(gkey), dy_sparse=sparse_du)
         self._late_binds.append(bind)
         fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
         sub = 4 if ((c.k == 1 and c.stride == 2) or (sparse_du and c.k == 1)) else 1     # pixels a strided 1x1 samples
@@ -642,14 +694,11 @@ class Engine:
         sc = self.scale[c.name]
         R = c.k * c.k * c.cin
 
-        def run():
-            cs = self._zero_view(cs_key) if cs_key else None
-            lib.call("urso_conv_param_grads", self._zero_view(gkey).data_ptr(), lib.ptr(row_map), w.data_ptr(),
-                     lib.ptr(cs), sc.data_ptr(), lib.ptr(bn[0]), lib.ptr(bn[2]), lib.ptr(bn[3]), lib.ptr(bias), BN_EPS,
-                     dW.data_ptr(), lib.ptr(dbias), lib.ptr(dgamma), lib.ptr(dbeta),
-                     self._zero_view(skey).data_ptr() if c.bn else None, R, c.cout, S())
-        self._add(self.ops_bwd, OpRec(run, "param_grads", c.name, 0.0, 12.0 * R * c.cout, 2, lane=self.aux_lane,
-                                      after=[wg_op]))
+        def make_job():
+            return dict(G=self._zero_view(gkey), row_map=row_map, w=w, colsum=self._zero_view(cs_key) if cs_key else None,
+                        scale=sc, gamma=bn[0], mean=bn[2], var=bn[3], bias=bias, dW=dW, dbias=dbias, dgamma=dgamma,
+                        dbeta=dbeta, S=self._zero_view(skey) if c.bn else None, R=R, CO=c.cout)
+        self._pgrad_specs.append((wg_op, make_job, 12.0 * R * c.cout))
 
     def _build_update(self):
         S = lib.stream_ptr
@@ -758,6 +807,7 @@ class Engine:
         self._run(self.ops_loss)
         self._run(self.ops_bwd)
         self._join()
+        self._run_pgrad()
 
     def _phase_train_a(self):      # forward + losses + the first part of backward (gradients of the arena tail)
         self._split_run = True
@@ -766,6 +816,7 @@ class Engine:
             self._run(self.ops_loss)
             self._run(self.ops_bwd[:self._bwd_split[0]])
             self._join()
+            self._run_pgrad((0,))
         finally:
             self._split_run = False
 
@@ -775,6 +826,7 @@ class Engine:
             self._fork()
             self._run(self.ops_bwd[self._bwd_split[0]:])
             self._join()
+            self._run_pgrad((1,))
         finally:
             self._split_run = False
 
@@ -937,7 +989,7 @@ class Engine:
             return sum(getattr(o, "launches", 1) for o in ops)
         total = n(self.ops_stage) + 1 + n(self.ops_fwd)
         if train and self.training:
-            total += n(self.ops_loss) + n(self.ops_bwd) + n(self.ops_update)
+            total += n(self.ops_loss) + n(self.ops_bwd) + n(self.ops_update) + n(getattr(self, "ops_pgrad", []))
         return total
 
     def profile_ops(self, train=True, reps=3):
@@ -945,7 +997,7 @@ class Engine:
         which is what a real step sees).  Returns [dict(kind, name, ms, flops, bytes)] for OpRec-tagged launches."""
         ops = list(self.ops_fwd)
         if train and self.training:
-            ops += list(self.ops_loss) + list(self.ops_bwd)
+            ops += list(self.ops_loss) + list(self.ops_bwd) + list(self.ops_pgrad)
         self._phase_train() if (train and self.training) else self._phase_fwd()    # valid buffers everywhere
         torch.cuda.synchronize()
         recs = {}

@@ -70,6 +70,23 @@ class Conv2dWgradDesc(C.Structure):
                 ("G", C.c_void_p)]
 
 
+class BnJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("gamma", "beta", "mean", "var", "bias", "scale", "shift")] + \
+               [("C", C.c_int32), ("pad_", C.c_int32)]
+
+
+class StageJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("scale", C.c_void_p), ("out", C.c_void_p), ("index", C.c_void_p),
+                ("kind", C.c_int32), ("K", C.c_int32), ("CI", C.c_int32), ("CO", C.c_int32), ("COp", C.c_int32),
+                ("rows_out", C.c_int32), ("ld_out", C.c_int64), ("part", C.c_int32), ("block_begin", C.c_int32)]
+
+
+class PgradJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("G", "g_row_map", "w", "colsum", "scale", "gamma", "mean", "var", "bias",
+                                          "dW", "dbias", "dgamma", "dbeta", "S")] + \
+               [(n, C.c_int32) for n in ("R", "CO", "rows_per_slab", "cblocks", "block_begin", "pad_")]
+
+
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes (all return int unless listed in _RESTYPES); kept in sync with include/urso_b200.h
@@ -123,6 +140,16 @@ SIGNATURES = {
     "urso_stage_weight_rows": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp],
     "urso_stage_weight_cols": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp],
     "urso_conv_param_grads": [_vp] * 9 + [_f32] + [_vp] * 5 + [_i32, _i32, _vp],
+    "urso_sizeof_bn_job": [],
+    "urso_sizeof_stage_job": [],
+    "urso_sizeof_pgrad_job": [],
+    "urso_bn_fold_multi": [_vp, _i32, _i32, _f32, _vp],
+    "urso_stage_jobs_finalize": [_vp, _i32, _vp],
+    "urso_stage_weights_multi": [_vp, _vp, _i32, _i32, _vp],
+    "urso_pgrad_jobs_finalize": [_vp, _i32, _vp],
+    "urso_conv_param_grads_multi": [_vp, _vp, _i32, _i32, _i32, _f32, _vp],
+    "urso_conv2d_fwd_stage_job": [_vp, _vp],
+    "urso_conv2d_dgrad_stage_jobs": [_vp, _vp, _i32],
     "urso_grad_accumulate": [_vp, _vp, _vp, _f32, _f32, _i64, _vp],
     "urso_add_reg_sumsq": [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "urso_sgd_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
@@ -169,6 +196,9 @@ def load():
             or lib.urso_sizeof_conv2d_dgrad_desc() != C.sizeof(Conv2dDgradDesc)
             or lib.urso_sizeof_conv2d_wgrad_desc() != C.sizeof(Conv2dWgradDesc)):
         raise UrsoError("ctypes conv2d operator structs do not match include/urso_b200.h (rebuild the library)")
+    if (lib.urso_sizeof_bn_job() != C.sizeof(BnJob) or lib.urso_sizeof_stage_job() != C.sizeof(StageJob)
+            or lib.urso_sizeof_pgrad_job() != C.sizeof(PgradJob)):
+        raise UrsoError("ctypes job-table structs do not match include/urso_b200.h (rebuild the library)")
     _lib = lib
     return lib
 
@@ -424,3 +454,77 @@ def stem_grad_row_map():
     m = (_i32 * 147)()
     load().urso_stem_grad_row_map(m)
     return list(m)
+
+
+# ------------------------------------------------------------------------------------------------ multi-tensor job tables
+def _table_to_device(arr, device):
+    """ctypes array of structs -> uint8 device tensor holding the same bytes."""
+    import torch
+    buf = (C.c_char * C.sizeof(arr)).from_buffer(arr)
+    return torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(device)
+
+
+class BnFoldTable:
+    """urso_bn_fold_multi over a list of (gamma, beta, mean, var, bias, scale, shift, C) tensor tuples (None allowed)."""
+
+    def __init__(self, jobs, device):
+        arr = (BnJob * len(jobs))()
+        for i, (gm, bt, mu, vr, bias, sc, sh, c) in enumerate(jobs):
+            arr[i] = BnJob(ptr(gm), ptr(bt), ptr(mu), ptr(vr), ptr(bias), ptr(sc), ptr(sh), int(c), 0)
+        self.n, self.max_c = len(jobs), max(int(j[7]) for j in jobs)
+        self.dev = _table_to_device(arr, device)
+        self._keep = jobs
+
+    def launch(self, eps):
+        call("urso_bn_fold_multi", self.dev.data_ptr(), self.n, self.max_c, eps, stream_ptr())
+
+
+class StageTable:
+    """urso_stage_weights_multi over the staging jobs of a list of Conv2dFwd / Conv2dDgrad operators."""
+
+    def __init__(self, fwd_ops, dgrad_ops, device):
+        jobs = []
+        for op in fwd_ops:
+            j = StageJob()
+            check(load().urso_conv2d_fwd_stage_job(op._h, C.byref(j)), "urso_conv2d_fwd_stage_job")
+            jobs.append(j)
+        for op in dgrad_ops:
+            tmp = (StageJob * 64)()
+            n = load().urso_conv2d_dgrad_stage_jobs(op._h, tmp, 64)
+            if n < 0 or n > 64:
+                raise UrsoError("urso_conv2d_dgrad_stage_jobs failed")
+            jobs.extend(tmp[i] for i in range(n))
+        arr = (StageJob * len(jobs))()
+        for i, j in enumerate(jobs):
+            arr[i] = j
+        begins = (_i32 * len(jobs))()
+        self.total = load().urso_stage_jobs_finalize(arr, len(jobs), begins)
+        self.n = len(jobs)
+        self.dev = _table_to_device(arr, device)
+        self.begins = _table_to_device(begins, device)
+        self._keep = (fwd_ops, dgrad_ops)
+
+    def launch(self):
+        call("urso_stage_weights_multi", self.dev.data_ptr(), self.begins.data_ptr(), self.n, self.total, stream_ptr())
+
+
+class PgradTable:
+    """urso_conv_param_grads_multi over a list of dicts with the tensors of urso_conv_param_grads."""
+
+    def __init__(self, jobs, device):
+        arr = (PgradJob * len(jobs))()
+        for i, j in enumerate(jobs):
+            arr[i] = PgradJob(ptr(j["G"]), ptr(j.get("row_map")), ptr(j["w"]), ptr(j.get("colsum")), ptr(j.get("scale")),
+                              ptr(j.get("gamma")), ptr(j.get("mean")), ptr(j.get("var")), ptr(j.get("bias")),
+                              ptr(j["dW"]), ptr(j.get("dbias")), ptr(j.get("dgamma")), ptr(j.get("dbeta")), ptr(j.get("S")),
+                              int(j["R"]), int(j["CO"]), 0, 0, 0, 0)
+        begins = (_i32 * len(jobs))()
+        self.total = load().urso_pgrad_jobs_finalize(arr, len(jobs), begins)
+        self.n, self.max_co = len(jobs), max(int(j["CO"]) for j in jobs)
+        self.dev = _table_to_device(arr, device)
+        self.begins = _table_to_device(begins, device)
+        self._keep = jobs
+
+    def launch(self, eps):
+        call("urso_conv_param_grads_multi", self.dev.data_ptr(), self.begins.data_ptr(), self.n, self.total, self.max_co,
+             eps, stream_ptr())
