@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
     args = ap.parse_args()
@@ -185,6 +186,9 @@ def main():
     import torch
     import torch.distributed as dist
     from ursonet_b200.engine import Engine
+    from ursonet_b200 import lib as _lib
+    if args.no_pdl:
+        _lib.load().urso_set_pdl(0)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -298,9 +302,11 @@ def main():
     f_fl = agg.get("conv_fwd", {}).get("flops", 0) + agg.get("conv_dgrad", {}).get("flops", 0)
     f_n = agg.get("conv_fwd", {}).get("n", 0) + agg.get("conv_dgrad", {}).get("n", 0)
     achieved = f_fl / (f_ms * 1e-3) / 1e12 if f_ms else None
-    # DRAM bytes per Engine-F launch from the committed ncu pass over the same step (profiles/r01_traffic.json)
+    # DRAM bytes per Engine-F launch from the committed ncu pass over the same step (profiles/r0N_traffic.json, newest)
     traffic, traffic_note = None, "no ncu traffic capture for this configuration"
-    tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_traffic.json")))
+    tj = cands[-1] if cands else ""
     if os.path.exists(tj) and args.backbone == "resnet50" and args.width == 960 and args.batch == 32 and not args.regress_ori:
         t = json.load(open(tj))["engines"]["conv_gemm"]
         traffic = t["dram_bytes_per_launch"]

@@ -29,6 +29,10 @@ void urso_set_max_ctas(int n);
 /* Dry run (tests of the host-side planners on a machine without a GPU): while on, *_create calls plan tiles, shared
  * memory and pipelines for a 148-SM device but encode no tensor maps and touch no device memory; launches fail. */
 void urso_set_dry_run(int on);
+/* Programmatic dependent launch of the two tcgen05 engines (default on): a launch may run its prologue (barrier init, TMEM
+ * allocation, tensor-map prefetch) while the previous kernel of the stream drains; it reads that kernel's results only after
+ * griddepcontrol.wait.  0 = plain stream order. */
+void urso_set_pdl(int on);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);
@@ -344,6 +348,10 @@ int urso_conv_param_grads_multi(const urso_pgrad_job* jobs_dev, const int32_t* b
  * acc = beta * acc + grad (beta = 0 on the first micro-batch); when out != NULL the result alpha * acc is written to out
  * (the last micro-batch: out = the gradient arena, alpha = 1 / number of micro-batches) and acc is left untouched. */
 int urso_grad_accumulate(float* acc, const float* grad, float* out, float beta, float alpha, int64_t n, void* stream);
+/* sumsq_out: device fp32[URSO_SUMSQ_SCRATCH]; [0] receives sum(g^2), the rest is scratch for per-block partial sums, which
+ * are combined in a fixed order: the norm (and with it the clip factor and every updated weight) is bit-reproducible, so
+ * data-parallel ranks that hold the same all-reduced gradient apply the IDENTICAL update. */
+#define URSO_SUMSQ_SCRATCH 2048
 int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef, const float* chunk_lr,
                        float grad_scale, float* sumsq_out, int64_t n, void* stream);
 int urso_sgd_step(float* param, float* vel, const float* grad, const float* chunk_lr, const float* sumsq,

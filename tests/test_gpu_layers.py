@@ -278,7 +278,7 @@ def test_optimizer_matches_keras_restatement(opt):
     pd = p.to(DEV)
     coef_d, mask_d = coef.to(DEV), lr_mask.to(DEV)
     st = [torch.zeros(n, device=DEV) for _ in range(3)]
-    sumsq = torch.zeros(1, device=DEV)
+    sumsq = torch.zeros(2048, device=DEV)      # URSO_SUMSQ_SCRATCH
     hyper = torch.zeros(8, device=DEV)
     pref = p.double().clone()
     sref = {}
@@ -288,7 +288,7 @@ def test_optimizer_matches_keras_restatement(opt):
         lib.call("urso_add_reg_sumsq", gd.data_ptr(), pd.data_ptr(), coef_d.data_ptr(), mask_d.data_ptr(),
                  0.5, sumsq.data_ptr(), n, s)
         gref = (grad.double() * 0.5 + coef_e * pref) * mask_e
-        assert math.isclose(sumsq.item(), (gref * gref).sum().item(), rel_tol=1e-4)
+        assert math.isclose(sumsq[0].item(), (gref * gref).sum().item(), rel_tol=1e-4)
         if opt == "SGD":
             hyper.copy_(torch.tensor([0.01, 0.9, 0, 0, 5.0, 0, 0, 0]))
             lib.call("urso_sgd_step", pd.data_ptr(), st[0].data_ptr(), gd.data_ptr(), mask_d.data_ptr(),

@@ -240,6 +240,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above ran while the previous kernel of the stream was still draining;
+  // from here on its results are read.  (No-ops when the launch carries no programmatic dependency.)
+  pdl_wait();
+  pdl_launch_dependents();
 
   // Producers and MMA issuers: ALL lanes of the warp run the (warp-uniform) control flow and barrier waits; one elected
   // lane issues the TMA / tcgen05 instructions.  Keeping the loop state warp-uniform lets the compiler hold it in
@@ -841,8 +845,17 @@ static int launch_conv_gemm_f(const urso_convgemm* h, cudaStream_t stream) {
                                       227 * 1024));
     attr_set = true;
   }
-  urso::conv_gemm_kernel<BLOCK_N, FLAVOR><<<h->grid, 384, h->smem_bytes, stream>>>(h->params);
-  URSO_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h->grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = h->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = urso::pdl_enabled() ? 1 : 0;
+  URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::conv_gemm_kernel<BLOCK_N, FLAVOR>, h->params));
   return 0;
 }
 template <int BLOCK_N>

@@ -154,8 +154,23 @@ __global__ void __launch_bounds__(256) add_reg_sumsq_kernel(float* __restrict__ 
     t += __shfl_xor_sync(0xffu, t, 4);
     t += __shfl_xor_sync(0xffu, t, 2);
     t += __shfl_xor_sync(0xffu, t, 1);
-    if (threadIdx.x == 0) atomicAdd(sumsq, t);
+    // per-block partial, summed in a FIXED order by sumsq_finish_kernel: with atomics the last bits of the norm (hence of
+    // the clip factor, hence of every weight) depended on arrival order and data-parallel ranks drifted apart by ulps
+    if (threadIdx.x == 0) sumsq[1 + blockIdx.x] = t;
   }
+}
+
+__global__ void __launch_bounds__(256) sumsq_finish_kernel(float* __restrict__ sumsq, int nparts) {
+  __shared__ float sh[256];
+  float t = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) t += sumsq[1 + i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sumsq[0] = sh[0];
 }
 
 // hyper: [0]=lr  [1]=momentum|beta1  [2]=beta2  [3]=eps  [4]=clipnorm   (device memory: CUDA-graph replays see updates)
@@ -406,9 +421,10 @@ int urso_add_reg_sumsq(float* grad, const float* param, const float* chunk_coef,
                        float grad_scale, float* sumsq_out, int64_t n, void* stream) {
   URSO_REQUIRE(grad && param && chunk_coef && chunk_lr && sumsq_out, "null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  URSO_CUDA_OK(cudaMemsetAsync(sumsq_out, 0, sizeof(float), s));
-  add_reg_sumsq_kernel<<<grid_for_p((n + 1023) / 1024, 1, num_sms() * 8), 256, 0, s>>>(grad, param, chunk_coef, chunk_lr,
-                                                                                    grad_scale, sumsq_out, n);
+  int nblocks = grid_for_p((n + 1023) / 1024, 1, num_sms() * 8);
+  if (nblocks > URSO_SUMSQ_SCRATCH - 1) nblocks = URSO_SUMSQ_SCRATCH - 1;
+  add_reg_sumsq_kernel<<<nblocks, 256, 0, s>>>(grad, param, chunk_coef, chunk_lr, grad_scale, sumsq_out, n);
+  sumsq_finish_kernel<<<1, 256, 0, s>>>(sumsq_out, nblocks);
   URSO_CUDA_OK(cudaGetLastError());
   return 0;
 }

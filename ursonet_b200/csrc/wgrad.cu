@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   // Producer / MMA issuer: warp-uniform control flow in all lanes, one elected lane issues (keeps the loop state in
   // uniform registers; a loop inside `if (lane == 0)` costs >100 SASS instructions per K step in R2UR shuffling).
@@ -240,8 +242,17 @@ static int launch_wgrad(const urso_wgrad* h, cudaStream_t stream) {
                                       220 * 1024));
     attr_smem = 220 * 1024;
   }
-  urso::wgrad_kernel<BLOCK_Q><<<h->grid, 256, h->smem_bytes, stream>>>(h->params);
-  URSO_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h->grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = h->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = urso::pdl_enabled() ? 1 : 0;
+  URSO_CUDA_OK(cudaLaunchKernelEx(&cfg, urso::wgrad_kernel<BLOCK_Q>, h->params));
   return 0;
 }
 

@@ -224,7 +224,7 @@ class Engine:
             self.dact: Dict[str, torch.Tensor] = {}
             self.dhead: Dict[str, torch.Tensor] = {}
             self.hyper = self._new((8,), torch.float32)
-            self.sumsq = self._new((1,), torch.float32)
+            self.sumsq = self._new((2048,), torch.float32)     # [0] = sum g^2, rest: per-block partials (URSO_SUMSQ_SCRATCH)
             self.opt_state = [torch.zeros_like(self.params.flat) for _ in range(1 if self.cfg.OPTIMIZER == "SGD" else 3)]
             self.opt_t = 0
 
