@@ -141,8 +141,8 @@ void urso_wgrad_destroy(urso_wgrad_t* h);
  * *_workspace_bytes() bytes (staged operand + gather indices), which must stay valid while the handle lives.
  * `*_stage_weights` re-stages the operand from the fp32 masters (call it after every weight update, any stream order
  * before the launch); `*_launch` is graph-capturable and never synchronises.
- * The 7x7/stride-2 stem (net.py:170-171,254-255) is the same operator with ksize = 7: x is then the staged tensor E of
- * urso_stem_stage ([N, H/2+3, W/2, 64]) and H, W are the IMAGE dimensions. */
+ * The 7x7/stride-2 stem (net.py:170-171,254-255) is the same operator with ksize = 7: x is then the compact staged tensor
+ * of urso_stem_stage ([N, H/2+3, W/2+3, 16]) and H, W are the IMAGE dimensions. */
 typedef struct {
   int32_t N, H, W, C; /* input activation */
   int32_t K;          /* output channels */
@@ -238,8 +238,11 @@ void urso_conv2d_wgrad_destroy(urso_conv2d_wgrad_t* h);
 void urso_stem_grad_row_map(int32_t* map147);
 
 /* ---- Stem input staging (replaces mold_image net.py:1337-1348 + ZeroPadding2D(3) net.py:170,254 + the im2col TF does
- * internally): uint8 or fp32 RGB [B,H,W,3] -> bf16 E[B, H/2+3, W/2, 64], E[b,h2,wo,(s2,ph,pw,c)] =
- * (img[2*h2+ph-3, 2*(wo+s2)+pw-3, c] - mean[c]) or 0 outside the image / for c==3. */
+ * internally): uint8 or fp32 RGB [B,H,W,3] -> compact bf16 space-to-depth tensor S[B, H/2+3, W/2+3, 16],
+ * S[b,h2,w2,(ph,pw,c)] = (img[2*h2+ph-3, 2*w2+pw-3, c] - mean[c]) or 0 outside the image / for c==3.
+ * The 7x7/s2 stem reads S through an overlapping 64-"channel" view E[b,h2,wo,k] = S_flat[(h2*(W/2+3) + wo)*16 + k]
+ * (pixel stride 16 elements: k = s2*16 + ph*8 + pw*4 + c covers the staged pixels wo..wo+3, the four horizontal taps);
+ * urso_conv2d_{fwd,wgrad} with ksize 7 build that view themselves from the pointer to S. */
 int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, const float* mean3, void* e_out,
                     int32_t B, int32_t H, int32_t W, int32_t part, void* stream);
 /* part: 0 = bf16(v) (normal); 1 = bf16(v - bf16(v)), the low half of a split-bf16 pair (parity mode, see below). */

@@ -90,7 +90,7 @@ def test_conv2d_fwd_stem_operator():
     wk = bf16_exact(7, 7, 3, 64, scale=0.05, seed=5)
     scale = 0.5 + torch.rand(64, dtype=torch.float64)
     shift = torch.randn(64, dtype=torch.float64)
-    E = torch.zeros(N, H // 2 + 3, W // 2, 64, dtype=torch.bfloat16, device=DEV)
+    E = torch.zeros(N, H // 2 + 3, W // 2 + 3, 16, dtype=torch.bfloat16, device=DEV)      # compact staged tensor
     imgd = img.to(DEV)
     lib.call("urso_stem_stage", imgd.data_ptr(), 1, 1, mean.to(DEV).data_ptr(), E.data_ptr(), N, H, W, 0, lib.stream_ptr())
     shape = lib.conv_shape(N, H, W, 3, 64, 7, 2, 3)

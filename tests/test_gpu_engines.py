@@ -257,18 +257,19 @@ def test_stem_stage_and_conv():
     img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     mean = torch.tensor(O.MEAN_PIXEL, dtype=torch.float32)
     e_ref = E.stem_stage(img.double(), mean.double())
-    e_out = torch.empty(B, H // 2 + 3, W // 2, 64, dtype=torch.bfloat16, device=DEV)
+    s_out = torch.empty(B, H // 2 + 3, W // 2 + 3, 16, dtype=torch.bfloat16, device=DEV)   # compact staging ...
+    e_out = lib.stem_view(s_out)              # ... read through the overlapping 64-"channel" view
     img_d, img_f, mean_d = img.to(DEV), img.float().to(DEV), mean.to(DEV)   # keep device buffers alive across calls
-    lib.call("urso_stem_stage", img_d.data_ptr(), 1, 1, mean_d.data_ptr(), e_out.data_ptr(), B, H, W,
+    lib.call("urso_stem_stage", img_d.data_ptr(), 1, 1, mean_d.data_ptr(), s_out.data_ptr(), B, H, W,
              0, lib.stream_ptr())
     torch.cuda.synchronize()
     assert (e_out.double().cpu() - e_ref.to(torch.bfloat16).double()).abs().max().item() <= 1.0  # 1 bf16 ulp at 255
     # fp32 image input path gives the same staging
-    e2 = torch.empty_like(e_out)
-    lib.call("urso_stem_stage", img_f.data_ptr(), 0, 1, mean_d.data_ptr(), e2.data_ptr(), B, H, W,
+    s2 = torch.empty_like(s_out)
+    lib.call("urso_stem_stage", img_f.data_ptr(), 0, 1, mean_d.data_ptr(), s2.data_ptr(), B, H, W,
              0, lib.stream_ptr())
     torch.cuda.synchronize()
-    assert torch.equal(e2, e_out)
+    assert torch.equal(s2, s_out)
     # 7x7/s2 conv through Engine F on the staged tensor
     wk = bf16_exact(7, 7, 3, 64, scale=0.05, seed=14)
     bmat = E.stage_rows(wk, None, P.stem_weight_index(3)).to(torch.bfloat16).to(DEV).contiguous()

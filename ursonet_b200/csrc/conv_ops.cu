@@ -101,6 +101,15 @@ urso_view4 strided_view(const void* base, int n, int h, int w, int c, int ph, in
   v.stride_w = (int64_t)step * c; v.stride_h = (int64_t)step * w * c; v.stride_n = (int64_t)h * w * c;
   return v;
 }
+// The stem's operand: an OVERLAPPING view over the compact staged tensor S[N, H/2+3, W/2+3, 16] of urso_stem_stage: view pixel
+// (h2, wo) has 64 "channels" = the staged pixels wo .. wo+3 (pixel stride 16 elements), the four horizontal filter taps.
+urso_view4 stem_view(const void* base, int n, int H, int W) {
+  const int64_t h2 = H / 2 + 3, w2 = W / 2 + 3;
+  urso_view4 v;
+  v.base = base; v.C = 64; v.W = W / 2; v.H = (int32_t)h2; v.N = n;
+  v.stride_w = 16; v.stride_h = w2 * 16; v.stride_n = h2 * w2 * 16;
+  return v;
+}
 urso_view4 flat_view(const void* base, int64_t m, int c) {
   urso_view4 v;
   v.base = base; v.C = c; v.W = (int32_t)m; v.H = 1; v.N = 1;
@@ -208,7 +217,7 @@ extern "C" int urso_conv2d_fwd_create(const urso_conv2d_fwd_desc* d, urso_conv2d
   if (is_stem(s)) {
     if (int rc = check_stem(s)) return rc;
     URSO_REQUIRE(d->addend == nullptr, "the stem has no residual input");
-    cd.a[0] = dense_view(d->x, s.N, s.H / 2 + 3, s.W / 2, 64);
+    cd.a[0] = stem_view(d->x, s.N, s.H, s.W);
     cd.n_a = 1;
     for (int r2 = 0; r2 < 4; ++r2) cd.seg[r2] = urso_seg{0, r2, 0, 1};
     cd.n_seg = 4;
@@ -548,7 +557,7 @@ extern "C" int urso_conv2d_wgrad_create(const urso_conv2d_wgrad_desc* d, urso_co
   wd.g = d->G;
   if (is_stem(s)) {
     if (int rc = check_stem(s)) return rc;
-    wd.p[0] = dense_view(d->x, s.N, s.H / 2 + 3, s.W / 2, 64);
+    wd.p[0] = stem_view(d->x, s.N, s.H, s.W);
     wd.n_p = 1;
     for (int r2 = 0; r2 < 4; ++r2) wd.seg[r2] = urso_seg{0, r2, 0, 0};
     wd.n_seg = 4;

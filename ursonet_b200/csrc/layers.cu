@@ -38,25 +38,29 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 }
 
 // ------------------------------------------------------------------------------------------ stem staging
-// E[b, h2, wo, k]  k = s2*16 + ph*8 + pw*4 + c ; one thread writes one 16-byte group (fixed s2,ph: 8 values).
+// Compact space-to-depth staging S[b, h2, w2, ph*8 + pw*4 + c] = img[2*h2+ph-3, 2*w2+pw-3, c] - mean (0 outside the image and
+// for c == 3), h2 < H/2+3, w2 < W/2+3: 16 bf16 = 32 bytes per staged pixel.  The 7x7/s2 stem reads it through an OVERLAPPING
+// tensor view E[b, h2, wo, 64] with a pixel stride of 16 elements: the 64 "channels" of view pixel wo are the staged pixels
+// wo .. wo+3, i.e. the four horizontal taps of the space-to-depth filter, without storing them four times (round 1 did:
+// 635 MB instead of 160 MB per step at the bench shape, written once and read by the stem's forward and weight gradient).
+// One thread writes one 16-byte group (fixed ph: 8 values).
 template <bool U8>
 __global__ void stem_stage_kernel(const void* __restrict__ img, int subtract_mean, const float* __restrict__ mean3,
                                   __nv_bfloat16* __restrict__ e, int B, int H, int W, int part) {
-  const int H2 = H / 2 + 3, WO = W / 2;
-  const long long total = (long long)B * H2 * WO * 8;
+  const int H2 = H / 2 + 3, W2 = W / 2 + 3;
+  const long long total = (long long)B * H2 * W2 * 2;
   const float m0 = subtract_mean ? mean3[0] : 0.f, m1 = subtract_mean ? mean3[1] : 0.f, m2 = subtract_mean ? mean3[2] : 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);  // group: s2 = g>>1, ph = g&1
-    long long r = i >> 3;
-    const int wo = (int)(r % WO); r /= WO;
+    const int ph = (int)(i & 1);
+    long long r = i >> 1;
+    const int w2 = (int)(r % W2); r /= W2;
     const int h2 = (int)(r % H2);
     const int b = (int)(r / H2);
-    const int s2 = g >> 1, ph = g & 1;
     const int y = 2 * h2 + ph - 3;
     float v[8];
 #pragma unroll
     for (int pw = 0; pw < 2; ++pw) {
-      const int x = 2 * (wo + s2) + pw - 3;
+      const int x = 2 * w2 + pw - 3;
       const bool in = (y >= 0) && (y < H) && (x >= 0) && (x < W);
       float c0 = 0.f, c1 = 0.f, c2 = 0.f;
       if (in) {
@@ -412,7 +416,7 @@ int urso_stem_stage(const void* img, int32_t img_is_u8, int32_t subtract_mean, c
                     int32_t B, int32_t H, int32_t W, int32_t part, void* stream) {
   URSO_REQUIRE(img && e_out && (!subtract_mean || mean3), "null pointer");
   URSO_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem input must have even H, W");
-  const long long total = (long long)B * (H / 2 + 3) * (W / 2) * 8;
+  const long long total = (long long)B * (H / 2 + 3) * (W / 2 + 3) * 2;
   const int grid = grid_for(total, 256, num_sms() * 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (img_is_u8)

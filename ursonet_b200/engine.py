@@ -196,7 +196,7 @@ class Engine:
         self.img_u8 = self._new((B, self.H, self.W, 3), torch.uint8)
         self.img_f32 = None      # allocated on demand (reference-style molded fp32 input)
         self.mean3 = torch.tensor(np.asarray(self.cfg.MEAN_PIXEL), dtype=torch.float32, device=self.device)
-        self.E = self._new((B, self.H // 2 + 3, self.W // 2, 64))
+        self.E = self._new((B, self.H // 2 + 3, self.W // 2 + 3, 16))    # compact space-to-depth staging of the image
         self.act: Dict[str, torch.Tensor] = {}
         for name, (h, w, c) in g.shapes.items():
             f32 = name == "bottleneck_layer" or self.parity       # parity mode: fp32 master + (hi, lo) bf16 pair
@@ -391,7 +391,7 @@ class Engine:
                 sc.data_ptr(), sh.data_ptr(), c.cout, S()))
             if c.stem:
                 segs, idx = P.stem_segments(), P.stem_weight_index(3)
-                views_hi, views_lo = [self.E], [self.E_lo]
+                views_hi, views_lo = [lib.stem_view(self.E)], [lib.stem_view(self.E_lo)]
             else:
                 h, w_, _ = g.shapes[c.src]
                 geom = P.make_geom(c.k, c.stride, c.padding, c.cin, c.cout, h, w_)

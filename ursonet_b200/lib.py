@@ -241,6 +241,14 @@ def pix(t):
     return Pix(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
 
 
+def stem_view(s):
+    """The overlapping operand view E[N, H/2+3, W/2, 64] (pixel stride 16 elements) over the compact staged stem tensor
+    S[N, H/2+3, W/2+3, 16] of urso_stem_stage -- what the ksize-7 operators build internally (see include/urso_b200.h)."""
+    n, h2, w2, c = s.shape
+    assert c == 16 and s.is_contiguous()
+    return s.as_strided((n, h2, w2 - 3, 64), (h2 * w2 * 16, w2 * 16, 16, 1))
+
+
 def bits_pix(t):
     """urso_pix (BYTE strides) of a bit-packed mask tensor/view: int32 [N,H,W,C/32]."""
     import torch
