@@ -12,7 +12,6 @@ Memory layout (HBM):
   staged GEMM operands             : bf16 K-major weight matrices with the frozen-BN scale folded in (rebuilt per step)
 """
 import math
-import os
 import re
 from typing import Dict, List, Optional
 
@@ -143,7 +142,8 @@ class Engine:
     """One model replica on one GPU. `training=True` also allocates gradient buffers and builds the backward plan."""
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
-                 parity=None, reserve_sms: int = 0):
+                 parity=None, reserve_sms: int = 0, lanes: bool = True, wgrad_lanes: int = 1, sparse_bwd: bool = True,
+                 mask_bits: bool = True):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -159,16 +159,17 @@ class Engine:
         # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
         # chain); the weight-gradient launches run on their own lane(s) (wgrad of a layer only needs the du its dgrad
         # predecessor produced, so it overlaps the dgrad chain below it and fills its tail waves); the small per-layer
-        # kernels (BN fold, weight staging, parameter gradients) run on the last, "aux" lane.  URSO_LANES=0 puts
+        # kernels (BN fold, weight staging, parameter gradients) run on the last, "aux" lane.  lanes=False puts
         # everything on one stream.  (Batch slices -- independent half-batch chains -- were measured slower in round 1:
         # smaller kernels lose more to wave quantisation than the overlap returns; removed.)
-        multi = (not self.parity) and int(os.environ.get("URSO_LANES", "1")) != 0
-        # URSO_WLANE = number of wgrad lanes (0: wgrad stays in the main chain)
-        self.wgrad_lanes = int(os.environ.get("URSO_WLANE", "1")) if (multi and training) else 0
+        multi = (not self.parity) and bool(lanes)
+        # wgrad_lanes = number of weight-gradient lanes (0: wgrad stays in the main chain)
+        self.wgrad_lanes = int(wgrad_lanes) if (multi and training) else 0
         self.aux_lane = (1 + self.wgrad_lanes) if multi else 0
         self._wgrad_rr = 0
         self._lane_streams = None
-        self.sparse_bwd = training and int(os.environ.get("URSO_SPARSE_BWD", "1")) != 0
+        self.sparse_bwd = training and bool(sparse_bwd)
+        self.use_mask_bits = bool(mask_bits)     # False: the bf16 activation itself is the ReLU mask of backward (A/B runs)
         self.sparse = set()      # buffers whose gradient lives on the even-even pixels only
         self.H, self.W = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
         self.params = ParamStore(self.graph, device, cfg.WEIGHT_DECAY)
@@ -313,7 +314,6 @@ class Engine:
         self._stage_op = self._add(self.ops_stage, OpRec(self._run_stage_tables, "stage", "all layers", launches=2,
                                                          lane=self.aux_lane))
         self.relu_bits: Dict[str, torch.Tensor] = {}
-        self.use_mask_bits = int(os.environ.get("URSO_MASK_BITS", "1")) != 0     # 0: bf16 activation as the mask (A/B runs)
         aux = self.aux_lane
         for c in g.convs:
             w, bias, bn = self._conv_weight_ptrs(c)
@@ -744,12 +744,7 @@ class Engine:
                 op()
             return
         main, streams = self._main, self._lane_streams
-        skip_aux = os.environ.get("URSO_TIMING_SKIP_AUX") == "1"      # timing experiment only: results are garbage
         for op in ops:
-            if skip_aux and op.lane == self.aux_lane and op.kind in ("stage", "param_grads", "dense_wgrad"):
-                op.event = op.event or torch.cuda.Event()
-                op.event.record(main)
-                continue
             st = main if op.lane == 0 else streams[op.lane]
             for a in op.after:
                 # Only in the split schedule does an earlier segment end with a full join (and live in another captured
