@@ -27,7 +27,7 @@ out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__
                  "-k regex:conv_gemm|wgrad, one eager train step (scripts/profile_step.py), RN-50 640x960 B=32; algorithmic "
                  "bytes = Engine.profile_ops accounting (inputs + outputs + addend + mask bits + weights)", "engines": {}}
 for eng in ("conv_gemm", "wgrad"):
-    ks = [d for d in per.values() if eng in d["name"]]
+    ks = [d for d in per.values() if (eng + "_kernel") in d["name"] and "dense" not in d["name"]]
     n = len(ks)
     dram = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in ks)
     out["engines"][eng] = {"launches": n, "dram_bytes_per_launch": dram / max(n, 1),
