@@ -353,9 +353,14 @@ class Engine:
     def _build_heads_forward(self):
         g, B = self.graph, self.B
         S = lib.stream_ptr
-        # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332); whole batch, lane 0
+        # ---- heads: fp32 Dense layers on the flattened NHWC bottleneck output (net.py:298,332).  The two branches are
+        # independent: the location branch runs on lane 1 (idle between forward and backward), the orientation branch on
+        # lane 0 -- the heads sit on the critical path between the two conv stacks with every SM otherwise idle
+        self.head_lane = 1 if self.aux_lane else 0
+        feat_op = self._last.get(0)
         for d in g.dense:
             w, b = self.params.view(d.name + "/kernel"), self.params.view(d.name + "/bias")
+            lane = self.head_lane if d.name.startswith("loc") else 0
 
             def bind(d=d):
                 self.head[d.name] = self._zero_view("head:" + d.name).view(self.B, d.cout)
@@ -366,7 +371,8 @@ class Engine:
                 y = self.head[d.name]
                 lib.call("urso_dense_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), self.B, d.cin, d.cout, S())
                 lib.call("urso_dense_bias_act", y.data_ptr(), b.data_ptr(), self.B, d.cout, d.act, S())
-            self._add(self.ops_fwd, OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
+            self._add(self.ops_fwd, OpRec(run, "dense_fwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2,
+                                          lane=lane, after=[feat_op] if (lane and d.src == "bottleneck_layer") else ()))
         if g.ori_mode == "quaternion":   # inference output is the normalised quaternion (net.py:345-346)
             self._add(self.ops_fwd, OpRec(lambda: lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), None,
                                                            self.ori_q.data_ptr(), None, None, self.B, 1.0, S()),
@@ -443,7 +449,7 @@ class Engine:
         loc_l, ori_l = self.losses[0:1], self.losses[1:2]
 
         # ---- losses (net.py:656-669, 705-762) -> gradients w.r.t. the head outputs
-        def loss_ops():
+        def loss_loc():
             loc, dloc = self.head["loc_final"], self.dhead["loc_final"]
             if g.loc_mode == "regression":
                 lib.call("urso_rel_loss", loc.data_ptr(), self.gt_loc.data_ptr(), dloc.data_ptr(), loc_l.data_ptr(), B, 3,
@@ -451,6 +457,8 @@ class Engine:
             else:
                 lib.call("urso_softmax_xent", loc.data_ptr(), self.gt_loc.data_ptr(), dloc.data_ptr(), loc_l.data_ptr(),
                          B, loc.shape[1], wl, S())
+
+        def loss_ori():
             if g.ori_mode == "quaternion":
                 lib.call("urso_quat_head", self.head["ori_q"].data_ptr(), self.gt_ori.data_ptr(), self.ori_q.data_ptr(),
                          self.dhead["ori_q"].data_ptr(), ori_l.data_ptr(), B, wo, S())
@@ -458,7 +466,9 @@ class Engine:
                 z = self.head["ori_final"]
                 lib.call("urso_softmax_xent", z.data_ptr(), self.gt_ori.data_ptr(), self.dhead["ori_final"].data_ptr(),
                          ori_l.data_ptr(), B, z.shape[1], wo, S())
-        self._add(self.ops_loss, OpRec(loss_ops, "loss", "losses", launches=2))
+        hl = self.head_lane
+        self._add(self.ops_loss, OpRec(loss_loc, "loss", "loc_loss", lane=hl))       # behind loc_final on its lane
+        self._add(self.ops_loss, OpRec(loss_ori, "loss", "ori_loss"))
 
         # ---- heads backward (reverse order); dx of the first layer of each branch goes to dfeat[branch]
         for d in reversed(g.dense):
@@ -480,7 +490,10 @@ class Engine:
                 x = self.act["bottleneck_layer"] if d.src == "bottleneck_layer" else self.head[d.src]
                 lib.call("urso_dense_bwd", x.data_ptr(), w.data_ptr(), None, self.dhead[d.name].data_ptr(), None,
                          gw.data_ptr(), None, B, d.cin, d.cout, 0, S())
-            op_d = self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2))
+            op_d = self._add(self.ops_bwd, OpRec(run, "dense_bwd", d.name, 2.0 * B * d.cin * d.cout, 4.0 * d.cin * d.cout, 2,
+                                                 lane=hl if branch == 0 else 0))
+            if branch == 0:
+                last_loc_bwd = op_d
             self._add(self.ops_bwd, OpRec(run_w, "dense_wgrad", d.name, 2.0 * B * d.cin * d.cout, 8.0 * d.cin * d.cout, 2,
                                           lane=self.aux_lane, after=[op_d]))
         assert cfg.NR_DENSE_LAYERS in range(3)      # net.py:293,327 (the CLI fixes it to 1, pose_estimator.py:820)
@@ -491,7 +504,8 @@ class Engine:
         self.dact["bottleneck_layer"] = self._new((B, h6, w6, P.ceil64(bw)))   # zero padded bf16 operand
         self._add(self.ops_bwd, OpRec(lambda: lib.call(
             "urso_pad_cast_rows", self.dfeat[0].data_ptr(), self.dfeat[1].data_ptr(),
-            self.dact["bottleneck_layer"].data_ptr(), B * h6 * w6, bw, P.ceil64(bw), S()), "misc", "pad_cast"))
+            self.dact["bottleneck_layer"].data_ptr(), B * h6 * w6, bw, P.ceil64(bw), S()), "misc", "pad_cast",
+            after=[last_loc_bwd] if hl else ()))
         producers = {c.dst: c for c in g.convs}
         cons_conv: Dict[str, List[ConvSpec]] = {}
         cons_add: Dict[str, List[ConvSpec]] = {}
