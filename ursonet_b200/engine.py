@@ -143,7 +143,7 @@ class Engine:
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
                  parity=None, reserve_sms: int = 0, lanes: bool = True, wgrad_lanes: int = 1, sparse_bwd: bool = True,
-                 mask_bits: bool = True):
+                 mask_bits: bool = True, pair_l2: bool = False):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -155,6 +155,13 @@ class Engine:
         # all-reduce of the arena tail is in flight, see train_step(allreduce_async=...)) are planned with that many SMs
         # left free, so that NCCL's kernel has somewhere to run: the persistent conv CTAs otherwise hold every SM
         self.reserve_sms = int(reserve_sms)
+        # pair_l2: the HBM-bound 1x1 "expand" convolutions of stages 2-3 (64 -> 256, 128 -> 512 channels) have a weight
+        # gradient and an input gradient that BOTH stream the same large output gradient (629 / 314 MB at the bench shape).
+        # The two launches already sit next to each other on two lanes, but each wants every SM, so they serialise and the
+        # second one re-reads the tensor from HBM.  Paired, each is planned on half of the SMs and they start together:
+        # they run side by side and the follower finds the tensor in L2.
+        self.pair_l2 = bool(pair_l2) and training
+        self._pair = {}
         self.graph: Graph = build_graph(cfg)
         # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
         # chain); the weight-gradient launches run on their own lane(s) (wgrad of a layer only needs the du its dgrad
@@ -620,15 +627,16 @@ class Engine:
                         + sum(c.cout * c.k * c.k * c.cin for c in convs)) + (touched / 8 if mask_bits is not None else 0)
         stage_op = self._stage_op
         self._dgrad_boxes.append(box)
+        pair = self._pair.get(convs[0].name) if (len(convs) == 1 and not adds and not sparse_in) else None
         if stride == 2 and not self.sparse_bwd:      # phases no filter tap reaches must read as zero
             self._add(self.ops_bwd, OpRec(lambda: box["p"].untouched and dX.zero_(), "fill", X, 0.0, 2.0 * dX.numel(),
                                           after=self._bwd_deps()))
         op = self._add(self.ops_bwd, OpRec(lambda: box["p"].launch(), "conv_dgrad", X, fl, nbytes,
-                                           after=self._bwd_deps() + [stage_op]))
+                                           after=self._bwd_deps() + [stage_op] + ([pair] if pair is not None else [])))
 
         def bind():
             cs = self._zero_view(key) if key else None
-            with self._cta_limit(op):
+            with self._cta_limit(op, half=pair is not None):
                 box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs,
                                            dy_sparse=sparse_in, mask_bits=mask_bits)
             op.launches = box["p"].n_launches
@@ -641,15 +649,18 @@ class Engine:
         if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)
 
-    def _cta_limit(self, op):
-        """Context manager: plan the operator of a second-segment backward op with `reserve_sms` SMs left free."""
+    def _cta_limit(self, op, half=False):
+        """Context manager: plan the operator of a second-segment backward op with `reserve_sms` SMs left free, or (half)
+        on half of the SMs (an L2-sharing pair)."""
         import contextlib
 
         @contextlib.contextmanager
         def cm():
-            limit = self.reserve_sms > 0 and op.segment == 1
+            n_sm = lib.load().urso_num_sms()
+            limit = (self.reserve_sms > 0 and op.segment == 1) or half
             if limit:
-                lib.load().urso_set_max_ctas(max(1, lib.load().urso_num_sms() - self.reserve_sms))
+                n = n_sm - (self.reserve_sms if op.segment == 1 else 0)
+                lib.load().urso_set_max_ctas(max(1, n // 2 if half else n))
             try:
                 yield
             finally:
@@ -682,7 +693,7 @@ class Engine:
         box = {}
 
         def bind():
-            with self._cta_limit(wg_op):
+            with self._cta_limit(wg_op, half=paired):
                 box["p"] = lib.Conv2dWgrad(shape, x, du, self._zero_view(gkey), dy_sparse=sparse_du)
         self._late_binds.append(bind)
         fl = 2.0 * B * oh * ow * c.cout * c.k * c.k * c.cin
@@ -693,6 +704,10 @@ class Engine:
             deps = [self._last.get(0), self._bwd_root]
         else:
             lane, deps = 0, []
+        paired = (self.pair_l2 and self.wgrad_lanes == 1 and not c.stem and c.k == 1 and c.stride == 1 and not sparse_du
+                  and c.cin <= 128 and c.cout >= 4 * c.cin and 2.0 * du.numel() >= 2.5e8)
+        if paired:   # marker on the wgrad lane: the input-gradient launch that shares du starts when this lane gets here
+            self._pair[c.name] = self._add(self.ops_bwd, OpRec(lambda: None, "misc", "pair:" + c.name, launches=0, lane=lane))
         wg_op = self._add(self.ops_bwd, OpRec(lambda: box["p"].launch(), "conv_wgrad", c.name, fl, nb, lane=lane,
                                               after=deps))
         self._wgrad_rr += 1
