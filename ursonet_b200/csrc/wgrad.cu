@@ -26,6 +26,8 @@ struct WgradParams {
   WSegDev seg[URSO_MAX_SEGS];
   int n_seg, taps_per_cta, n_seg_groups;
   int order;       // work-item decode order (see kernel)
+  int interleave;  // split s takes pixel blocks s, s + split_k, ... instead of one contiguous range: all CTAs then walk the
+                   // tensor front to back together, like Engine F's round-robin tiles (an L2-sharing pair needs that)
   int pair_mode;   // PC <= 64: the two 64-row halves of the MMA M dimension carry two different filter taps
   int PC, QC;
   int p_tiles, q_tiles;
@@ -74,8 +76,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   const int n_units = p.pair_mode ? (p.n_seg + 1) / 2 : p.n_seg;
   const int seg0 = seg_group * p.taps_per_cta;
   const int T = min(p.taps_per_cta, n_units - seg0);
-  const int kb_begin = (int)((long long)p.n_pix_blocks * split / p.split_k);
-  const int kb_end = (int)((long long)p.n_pix_blocks * (split + 1) / p.split_k);
+  // my pixel blocks: kb = kb_begin + i * kb_step, i < kb_count
+  const int kb_step = p.interleave ? p.split_k : 1;
+  const int kb_begin = p.interleave ? split : (int)((long long)p.n_pix_blocks * split / p.split_k);
+  const int kb_count = p.interleave ? (p.n_pix_blocks - split + p.split_k - 1) / p.split_k
+                                    : (int)((long long)p.n_pix_blocks * (split + 1) / p.split_k) - kb_begin;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.p_maps[i]);
@@ -106,8 +111,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t bytes = (QA + 2 * T) * kAtomBytes;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      if (((kb - kb_begin) & 1) == par) {
+    for (int i = 0; i < kb_count; ++i) {
+      const int kb = kb_begin + i * kb_step;
+      if ((i & 1) == par) {
         const int twi = kb % p.tiles_w;
         const int rest = kb / p.tiles_w;
         const int thi = rest % p.tiles_h;
@@ -153,13 +159,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const uint32_t s_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
+    for (int i = 0; i < kb_count; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t q_addr = s_base + stage * p.stage_bytes;
         const uint64_t bd = kDescHi | (q_addr >> 4);
-        const uint32_t first = kb > kb_begin;
+        const uint32_t first = i > 0;
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
           const uint64_t ad = kDescHi | ((q_addr + (QA + 2 * t) * kAtomBytes) >> 4);
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    if (kb_end > kb_begin) {
+    if (kb_count > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
       for (int t = 0; t < T; ++t) {
@@ -340,6 +346,7 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   if (split > p.n_pix_blocks) split = p.n_pix_blocks;
   if (split < 1) split = 1;
   p.split_k = split;
+  p.interleave = max_ctas() < num_sms() ? 1 : 0;   // planned on a subset of the SMs = one half of an L2-sharing pair
   p.order = 1;   // output tiles fastest (measured +3.5 % over split-fastest: co-resident CTAs share operand tiles through L2)
   p.g = d->g;
   p.g_seg_stride = d->g_seg_stride;
