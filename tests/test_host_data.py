@@ -70,3 +70,28 @@ def test_rotation_augmentation_flags_run(tmp_path):
     (images, metas, locs, oris), _ = next(D.data_generator(ds, cfg, batch_size=2, raw_uint8=True))
     assert images.dtype == np.uint8 and images.shape[0] == 2 and np.isfinite(locs).all()
     assert np.allclose(oris.sum(1), 1.0, atol=1e-4)
+
+
+def test_parallel_loader_yields_batches_from_worker_threads(tmp_path):
+    """The multi-threaded host loader (fit_generator(workers=...) counterpart) produces well-formed batches, covers the
+    dataset across its workers and shuts down cleanly."""
+    from ursonet_b200 import data as D
+    from ursonet_b200.config import Config
+    root = tmp_path / "ds"
+    D.write_synthetic_urso(str(root), n_train=6, n_val=2, n_test=2, width=320, height=256)
+    cfg = Config()
+    cfg.BACKBONE, cfg.ORI_BINS_PER_DIM, cfg.REGRESS_ORI, cfg.ROT_AUG = "resnet18", 4, False, False
+    cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM, cfg.IMAGE_RESIZE_MODE = 256, 320, "pad64"
+    cfg.update()
+    ds = D.Urso()
+    ds.load_dataset(str(root), cfg, "train")
+    loader = D.ParallelLoader(ds, cfg, batch_size=2, workers=3, shuffle=True, raw_uint8=True)
+    assert loader.workers == 3
+    seen = set()
+    for _ in range(9):
+        (images, metas, locs, oris), _ = next(loader)
+        assert images.shape == (2, 256, 320, 3) and images.dtype.name == "uint8"
+        assert locs.shape == (2, 3) and oris.shape == (2, 64)
+        seen.update(int(m[0]) for m in metas)
+    loader.close()
+    assert seen == set(range(6))

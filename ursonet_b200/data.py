@@ -361,3 +361,66 @@ def data_generator(dataset, config, shuffle=True, batch_size=1, raw_uint8=False,
             error_count += 1
             if error_count > 5:
                 raise
+
+
+class ParallelLoader:
+    """Background batch producers for the train loop -- the counterpart of `fit_generator(workers=cpu_count,
+    use_multiprocessing=True, max_queue_size=100)` (net.py:1147-1163).  `workers` threads each run their own
+    `data_generator` over a disjoint share of the dataset (worker w of rank r takes share r*workers + w of
+    world*workers) and put finished batches into one bounded queue; image decoding, resizing and the warps are OpenCV /
+    numpy calls that release the GIL, so the threads really overlap.  Iterating yields the same ([images, meta, locs,
+    oris], []) tuples as the generator.  A single-threaded generator feeds ~60 images/s of 1280x960 PNGs -- two orders
+    below what one B200 consumes at the bench shape."""
+
+    def __init__(self, dataset, config, batch_size, workers=None, queue_size=16, rank=0, world=1, seed=0, **gen_kwargs):
+        import queue
+        import threading
+        n = len(dataset.image_ids)
+        if workers is None:
+            workers = max(1, (os.cpu_count() or 2) // max(1, world) - 1)
+        workers = max(1, min(int(workers), max(1, n // max(1, world))))
+        self.workers = workers
+        self._q = queue.Queue(maxsize=max(2, min(int(queue_size), 100)))
+        self._stop = threading.Event()
+        self._err = None
+        self._threads = []
+        for w in range(workers):
+            gen = data_generator(dataset, config, batch_size=batch_size, rank=rank * workers + w, world=world * workers,
+                                 seed=seed, **gen_kwargs)
+            t = threading.Thread(target=self._work, args=(gen,), daemon=True)
+            t.start()
+            self._threads.append(t)
+
+    def _work(self, gen):
+        try:
+            for batch in gen:
+                while not self._stop.is_set():
+                    try:
+                        self._q.put(batch, timeout=0.1)
+                        break
+                    except Exception:       # queue.Full
+                        continue
+                if self._stop.is_set():
+                    return
+        except BaseException as e:           # surfaced to the consumer: the train loop must not hang on a dead worker
+            self._err = e
+            self._stop.set()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        import queue
+        while True:
+            if self._err is not None:
+                raise self._err
+            try:
+                return self._q.get(timeout=0.5)
+            except queue.Empty:
+                if self._stop.is_set() and self._err is None:
+                    raise StopIteration
+
+    def close(self):
+        self._stop.set()
+        for t in self._threads:
+            t.join(timeout=2.0)

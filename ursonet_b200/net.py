@@ -232,10 +232,12 @@ class UrsoNet:
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         dev_aug = bool(raw_uint8 and getattr(cfg, "SIM2REAL_AUG", False))
         shard = dict(rank=rank, world=self.world, seed=int(getattr(cfg, "DATA_SEED", 0)))
-        train_gen = D.data_generator(train_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8,
+        # background producers (the reference: fit_generator(workers=cpu_count, max_queue_size=100), net.py:1147-1163)
+        nw = getattr(cfg, "DATA_WORKERS", None)
+        train_gen = D.ParallelLoader(train_dataset, cfg, e.B, workers=nw, shuffle=True, raw_uint8=raw_uint8,
                                      device_aug=dev_aug, **shard)
-        val_gen = D.data_generator(val_dataset, cfg, shuffle=True, batch_size=e.B, raw_uint8=raw_uint8,
-                                   device_aug=dev_aug, **shard)
+        val_gen = D.ParallelLoader(val_dataset, cfg, e.B, workers=1, shuffle=True, raw_uint8=raw_uint8,
+                                   device_aug=dev_aug, **shard) if len(val_dataset.image_ids) else None
         history = BatchLogger()
         log("\nStarting at epoch {}. LR={}\n".format(self.epoch, learning_rate))
         log("Checkpoint Path: {}".format(self.checkpoint_path))
@@ -275,6 +277,9 @@ class UrsoNet:
                     msg += " - val_loc_loss: {:.4f} - val_ori_loss: {:.4f}".format(*np.mean(np.asarray(val), 0))
                 print(msg)
                 self.save_weights(self.checkpoint_path.format(epoch=epoch + 1))
+        train_gen.close()
+        if val_gen is not None:
+            val_gen.close()
         self.epoch = max(self.epoch, epochs)
         return history
 
