@@ -24,7 +24,8 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 print("bn_fold table   %.4f ms (%d jobs)" % (timeit(lambda: eng._bn_table.launch(BN_EPS)), eng._bn_table.n))
-print("stage table     %.4f ms (%d jobs, %d blocks)" % (timeit(eng._stage_table.launch), eng._stage_table.n, eng._stage_table.total))
+print("stage table A   %.4f ms (%d jobs, %d blocks)" % (timeit(eng._stage_table_a.launch), eng._stage_table_a.n, eng._stage_table_a.total))
+print("stage table B   %.4f ms (%d jobs, %d blocks)" % (timeit(eng._stage_table.launch), eng._stage_table.n, eng._stage_table.total))
 for op in eng.ops_pgrad:
     print("pgrad %-10s %.4f ms" % (op.name, timeit(op)))
 print("zero arena      %.4f ms (%d MB)" % (timeit(lambda: eng.zero_arena.zero_()), eng.zero_arena.numel() * 4 // 2**20))

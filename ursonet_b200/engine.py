@@ -254,7 +254,12 @@ class Engine:
             return
         # multi-tensor job tables (one launch each for: BN fold, weight-operand staging, parameter gradients per segment)
         self._bn_table = lib.BnFoldTable(self._bn_jobs, self.device)
-        self._stage_table = lib.StageTable(list(self.fwd_ops.values()), [b["p"] for b in self._dgrad_boxes], self.device)
+        # two tables: the operands of the first layers (tiny) so that the stem can start at once, and everything else,
+        # which is staged while the stem runs
+        early = [op for n, op in self.fwd_ops.items() if n in self._early_layers]
+        late = [op for n, op in self.fwd_ops.items() if n not in self._early_layers]
+        self._stage_table_a = lib.StageTable(early, [], self.device)
+        self._stage_table = lib.StageTable(late, [b["p"] for b in self._dgrad_boxes], self.device)
         self.ops_pgrad = []
         if self.training:
             for seg in (0, 1):
@@ -267,8 +272,11 @@ class Engine:
                 op.segment = seg
                 self.ops_pgrad.append(op)
 
-    def _run_stage_tables(self):
+    def _run_stage_early(self):
         self._bn_table.launch(BN_EPS)
+        self._stage_table_a.launch()
+
+    def _run_stage_tables(self):
         self._stage_table.launch()
 
     def _run_pgrad(self, segments=(0, 1)):
@@ -318,7 +326,10 @@ class Engine:
         # BN fold + weight-operand staging of ALL layers: two multi-tensor launches (job tables built in
         # _finalise_zero_arena, once the gradient operators exist too) instead of ~170 tiny per-layer launches
         self._bn_jobs, self._dgrad_boxes, self._pgrad_specs = [], [], []
-        self._stage_op = self._add(self.ops_stage, OpRec(self._run_stage_tables, "stage", "all layers", launches=2,
+        self._early_layers = set(c.name for c in g.convs[:4])       # stem + the first block's convs
+        self._stage_op_a = self._add(self.ops_stage, OpRec(self._run_stage_early, "stage", "bn fold + first layers",
+                                                           launches=2, lane=self.aux_lane))
+        self._stage_op = self._add(self.ops_stage, OpRec(self._run_stage_tables, "stage", "all other layers", launches=1,
                                                          lane=self.aux_lane))
         self.relu_bits: Dict[str, torch.Tensor] = {}
         aux = self.aux_lane
@@ -339,7 +350,7 @@ class Engine:
                 bits = self.relu_bits[c.dst] = torch.zeros((B, oh, ow, c.cout // 32), dtype=torch.int32, device=self.device)
             op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu, relu_bits=bits)
             self.fwd_ops[c.name] = op
-            staged = self._stage_op
+            staged = self._stage_op_a if c.name in self._early_layers else self._stage_op
             if c.stem:
                 ph, pw, _ = g.shapes[c.dst]
                 self.argmax = self._new((B, ph // 2, pw // 2, 64), torch.uint8) if self.training else None
