@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
+    ap.add_argument("--stage-split", type=int, default=4, help="A/B: leading convs whose weight operands get their own staging launch")
     ap.add_argument("--pair-l2", action="store_true", help="A/B: co-run the dgrad / wgrad launches that share a large gradient tensor")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -201,7 +202,7 @@ def main():
         n_micro = per_rank // args.batch
         workload += f", global batch {args.global_batch} = {world} ranks x {n_micro} micro-batches x {args.batch}"
     eng = Engine(cfg, args.batch, training=True, world_size=world, seed=0,
-                 reserve_sms=args.reserve_sms if (world > 1 and args.overlap) else 0, pair_l2=args.pair_l2)
+                 reserve_sms=args.reserve_sms if (world > 1 and args.overlap) else 0, pair_l2=args.pair_l2, stage_split=args.stage_split)
     img, loc, ori = synth_batch(cfg, args.batch, seed=rank)
     h_img, h_loc, h_ori = img.pin_memory(), loc.pin_memory(), ori.pin_memory()
     eng.img_u8.copy_(h_img)

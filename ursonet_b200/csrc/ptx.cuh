@@ -187,6 +187,13 @@ __device__ __forceinline__ void tma_store_4d_u32(const CUtensorMap* m, uint32_t 
                "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// fp32 add-reduction of a contiguous shared-memory span into global memory by the bulk-copy engine (16-byte aligned
+// addresses, size a multiple of 16): the L2 performs the adds on whole sectors, the SM issues ONE instruction per span
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t smem_addr, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr),
+               "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {   // <= N most recent groups may still be reading smem

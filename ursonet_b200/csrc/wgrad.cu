@@ -35,6 +35,9 @@ struct WgradParams {
   int n_pix_blocks, split_k;
   int stages, stage_bytes;
   int tmem_cols;
+  int bulk_red;    // epilogue: accumulator rows go through shared memory and one cp.reduce.async.bulk (fp32 add) per row
+                   // instead of 16-byte REDG instructions (measured 1.29 cycles per LANE on the SM side: 11 us per launch)
+  int red_bufs;    // row buffers in the (idle) operand ring: 1 or 2
   float* g;
   long long g_seg_stride, g_sp, g_sq;
 };
@@ -192,12 +195,34 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     if (kb_count > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
+      // bulk-reduce path: the operand ring is idle now (every MMA that read it has completed); lane = accumulator row
+      // owns one padded row buffer (pitch = row bytes + 16: conflict-free 16-byte stores of 8 consecutive lanes)
+      const int ncols = min(BLOCK_Q, p.QC - q_tile * BLOCK_Q);
+      constexpr uint32_t kPitch = BLOCK_Q * 4 + 16;
       for (int t = 0; t < T; ++t) {
         // accumulator row -> (filter tap, P channel)
         const int tap = p.pair_mode ? 2 * (seg0 + t) + (row >> 6) : seg0 + t;
         const int pch = p.pair_mode ? (row & 63) : p_tile * 128 + row;
         const bool row_ok = pch < p.PC && tap < p.n_seg;
         float* grow = p.g + (long long)tap * p.g_seg_stride + (long long)pch * p.g_sp;
+        if (p.bulk_red) {
+          const uint32_t rbuf = smem_u32(smem) + (uint32_t)((t % p.red_bufs) * 128 + row) * kPitch;
+          if (t >= p.red_bufs) tma_store_wait_read<0>();   // my own earlier reduction has finished reading this row buffer
+#pragma unroll 1
+          for (int j = 0; j < BLOCK_Q / 32; ++j) {
+            if (j * 32 >= ncols) break;
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + t * BLOCK_Q + j * 32, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              sts128(rbuf + j * 128 + i * 16, acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          }
+          fence_proxy_async();
+          if (row_ok) bulk_reduce_add_f32(grow + q_tile * BLOCK_Q, rbuf, (uint32_t)ncols * 4u);
+          tma_store_commit();
+          continue;
+        }
         const bool vec_ok = (reinterpret_cast<uintptr_t>(grow) & 15) == 0;
 #pragma unroll 1
         for (int j = 0; j < BLOCK_Q / 32; ++j) {
@@ -222,6 +247,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           }
         }
       }
+      if (p.bulk_red) tma_store_wait_all();
     }
   }
 
@@ -352,6 +378,11 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   p.g_seg_stride = d->g_seg_stride;
   p.g_sp = d->g_sp;
   p.g_sq = d->g_sq;
+  // bulk-reduce epilogue: rows contiguous along q and 16-byte aligned, row buffers fit into the operand ring
+  const long long row_buf = 128LL * (bq * 4 + 16);
+  p.bulk_red = (d->g_sq == 1 && d->QC % 4 == 0 && d->g_sp % 4 == 0 && d->g_seg_stride % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(d->g) & 15) == 0 && (long long)p.stages * p.stage_bytes >= row_buf) ? 1 : 0;
+  p.red_bufs = (long long)p.stages * p.stage_bytes >= 2 * row_buf ? 2 : 1;
   h->grid = items * split;
   h->smem_bytes = p.stages * p.stage_bytes + 256 + 1024;
   *out = h;

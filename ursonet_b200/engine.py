@@ -143,7 +143,7 @@ class Engine:
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
                  parity=None, reserve_sms: int = 0, lanes: bool = True, wgrad_lanes: int = 1, sparse_bwd: bool = True,
-                 mask_bits: bool = True, pair_l2: bool = False):
+                 mask_bits: bool = True, pair_l2: bool = False, stage_split: int = 4):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -161,6 +161,9 @@ class Engine:
         # second one re-reads the tensor from HBM.  Paired, each is planned on half of the SMs and they start together:
         # they run side by side and the follower finds the tensor in L2.
         self.pair_l2 = bool(pair_l2) and training
+        # the weight operands of the first stage_split convolutions are staged by their own small launch, so that the stem
+        # does not wait for the operands of all layers at the start of a step (0 = one table)
+        self.stage_split = int(stage_split)
         self._pair = {}
         self.graph: Graph = build_graph(cfg)
         # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
@@ -326,7 +329,7 @@ class Engine:
         # BN fold + weight-operand staging of ALL layers: two multi-tensor launches (job tables built in
         # _finalise_zero_arena, once the gradient operators exist too) instead of ~170 tiny per-layer launches
         self._bn_jobs, self._dgrad_boxes, self._pgrad_specs = [], [], []
-        self._early_layers = set(c.name for c in g.convs[:4])       # stem + the first block's convs
+        self._early_layers = set(c.name for c in g.convs[:self.stage_split])     # stem + the first block's convs
         self._stage_op_a = self._add(self.ops_stage, OpRec(self._run_stage_early, "stage", "bn fold + first layers",
                                                            launches=2, lane=self.aux_lane))
         self._stage_op = self._add(self.ops_stage, OpRec(self._run_stage_tables, "stage", "all other layers", launches=1,

@@ -469,6 +469,8 @@ def stem_grad_row_map():
 def _table_to_device(arr, device):
     """ctypes array of structs -> uint8 device tensor holding the same bytes."""
     import torch
+    if C.sizeof(arr) == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
     buf = (C.c_char * C.sizeof(arr)).from_buffer(arr)
     return torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(device)
 
@@ -514,6 +516,8 @@ class StageTable:
         self._keep = (fwd_ops, dgrad_ops)
 
     def launch(self):
+        if self.n == 0:
+            return
         call("urso_stage_weights_multi", self.dev.data_ptr(), self.begins.data_ptr(), self.n, self.total, stream_ptr())
 
 
