@@ -50,6 +50,38 @@ def test_config1_train_then_resume_then_evaluate(workdir, capsys):
     assert model3.mode == "inference"
 
 
+def test_keras_h5_checkpoints(workdir):
+    """The reference's checkpoint format (Keras HDF5 weight files, net.py:964-967,1120) through ursonet_b200/hdf5.py:
+    save_weights('.h5') -> load_weights by name with an exclude list (net.py:816-852) -> identical tensors; `--weights
+    <file>.h5` resumes from it with the epoch parsed from the name (net.py:956)."""
+    from ursonet_b200 import hdf5
+    model = run_cli(workdir, "train", "--weights", "none", "--batch_size", "1", "--epochs", "1", "--steps_per_epoch", "1")
+    sd = model.engine.params.state_dict()
+    h5 = os.path.join(model.log_dir, "weights_synth_0007.h5")
+    model.save_weights(h5)
+    with hdf5.File(h5, strict=True) as f:
+        assert [bytes(x).decode() for x in f.attrs["layer_names"]][0] == "conv0"
+        assert f["conv0/conv0/kernel:0"].shape == (7, 7, 3, 64)
+    other = run_cli(workdir, "train", "--weights", h5, "--batch_size", "1", "--epochs", "7", "--steps_per_epoch", "1")
+    assert other.epoch == 7 and other.log_dir == model.log_dir       # nothing left to train: weights are the file's
+    got = other.engine.params.state_dict()
+    assert set(got) == set(sd)
+    for k in sd:
+        assert np.array_equal(got[k], sd[k]), k
+    # by-name load with an exclude pattern keeps the excluded layers' own initialisation
+    from ursonet_b200 import net
+    fresh = net.UrsoNet("training", model.config, str(workdir / "logs"))
+    before = fresh.engine.params.state_dict()
+    fresh.load_weights(h5, h5, by_name=True, exclude=["ori_final", "loc_final"])
+    after = fresh.engine.params.state_dict()
+    assert np.array_equal(after["ori_final/kernel"], before["ori_final/kernel"])
+    assert np.array_equal(after["conv0/kernel"], sd["conv0/kernel"])
+    # CHECKPOINT_FORMAT = 'h5' makes train() write Keras files
+    model.config.CHECKPOINT_FORMAT = "h5"
+    model.set_log_dir()
+    assert model.checkpoint_path.endswith("weights_synth_{epoch:04d}.h5")
+
+
 def test_train_with_device_sim2real(workdir):
     """--sim2real (BASELINE configs[3] turns it on): the uploaded uint8 frames go through the augmentation kernel when
     they are swapped in; what the network then sees is grey (3 equal channels) and matches the oracle for the drawn

@@ -28,6 +28,7 @@ _DEFAULTS = dict(
     # --- additions of this build (not in the reference) ---
     COMPUTE_DTYPE="bf16",   # activation / MMA operand type of the tcgen05 conv stack ("bf16")
     PARITY_MODE=False,      # forward-only split-bf16 (hi+lo) operands: ~fp32 accuracy at 3x MMA cost
+    CHECKPOINT_FORMAT="npz",  # "npz" or "h5" (Keras weight-file layout, the reference's ModelCheckpoint format)
 )
 
 

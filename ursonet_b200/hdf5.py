@@ -403,8 +403,18 @@ class _Reader:
 LEAF_K, INTERNAL_K = 4, 16          # libhdf5 defaults (H5Pset_sym_k), stored in the superblock
 
 
-def encode_datatype(dt):
-    """Datatype message, version 1 (spec IV.A.2.d); float / int / fixed string as libhdf5 encodes the native LE types."""
+def _c_order(x):
+    a = np.asarray(x)                     # (np.ascontiguousarray would turn a scalar into shape (1,))
+    if a.ndim:
+        a = np.ascontiguousarray(a)
+    if a.dtype.byteorder == ">":
+        a = a.astype(a.dtype.newbyteorder("<"))
+    return a
+
+
+def encode_datatype(dt, strpad=1):
+    """Datatype message, version 1 (spec IV.A.2.d); float / int / fixed string as libhdf5 encodes the native LE types.
+    strpad: string padding, 1 = null-padded (what h5py maps numpy 'S' to), 0 = null-terminated (C strings)."""
     dt = np.dtype(dt)
     if dt.kind == "f":
         props = {2: (15, 10, 5, 0, 10, 15), 4: (31, 23, 8, 0, 23, 127), 8: (63, 52, 11, 0, 52, 1023)}[dt.itemsize]
@@ -415,7 +425,7 @@ def encode_datatype(dt):
         return (bytes([0x10, 0x08 if dt.kind == "i" else 0x00, 0, 0]) + struct.pack("<I", dt.itemsize) +
                 struct.pack("<HH", 0, 8 * dt.itemsize))
     if dt.kind == "S":
-        return bytes([0x13, 0x01, 0, 0]) + struct.pack("<I", dt.itemsize)      # null-padded ASCII, as h5py maps numpy S
+        return bytes([0x13, strpad, 0, 0]) + struct.pack("<I", dt.itemsize)     # ASCII
     raise Hdf5Error("cannot encode dtype %s" % dt)
 
 
@@ -424,17 +434,15 @@ def encode_dataspace(shape):
     return bytes([1, len(shape), 0, 0, 0, 0, 0, 0]) + b"".join(struct.pack("<Q", int(s)) for s in shape)
 
 
-def encode_attribute(name, value):
+def encode_attribute(name, value, strpad=1):
     """Attribute message, version 1 (spec IV.A.2.m): every part padded to 8 bytes."""
     if isinstance(value, (bytes, str)):
         value = np.array(value.encode("utf-8") if isinstance(value, str) else value, dtype="S")
-    a = np.ascontiguousarray(value)
+    a = _c_order(value)
     if a.dtype.kind == "U":
         a = np.char.encode(a, "utf-8")
-    if a.dtype.byteorder == ">":
-        a = a.astype(a.dtype.newbyteorder("<"))
     nm = name.encode("utf-8") + b"\0"
-    t, s = encode_datatype(a.dtype), encode_dataspace(a.shape)
+    t, s = encode_datatype(a.dtype, strpad), encode_dataspace(a.shape)
 
     def pad(b):
         return b + b"\0" * (_pad8(len(b)) - len(b))
@@ -464,9 +472,7 @@ class _Writer:
         return addr
 
     def write_dataset(self, arr, attrs):
-        a = np.ascontiguousarray(arr)
-        if a.dtype.byteorder == ">":
-            a = a.astype(a.dtype.newbyteorder("<"))
+        a = _c_order(arr)
         raw = self.alloc(a.tobytes()) if a.size else UNDEF
         msgs = [(MSG_DATASPACE, 0, encode_dataspace(a.shape)),
                 (MSG_DATATYPE, 1, encode_datatype(a.dtype)),

@@ -5,9 +5,10 @@ detect / mold_inputs / load_weights / find_last / get_last_checkpoint / set_log_
 (`config`, `epoch`, `log_dir`, `checkpoint_path`).  `keras_model` is a small handle exposing `predict()` and by-name
 weight access -- there is no Keras.  Everything numeric runs in `engine.Engine` through liburso_b200.so.
 
-Deviations: checkpoints are `.npz` keyed by Keras weight names (h5py is unavailable; `.h5` is read /
-written when h5py can be imported); pretrained-weight downloads raise (no network); multi-GPU is real (one process per
-GPU under torchrun, NCCL all-reduce of the flat gradient arena) instead of the reference's commented-out stub.
+Deviations: checkpoints are `.npz` keyed by Keras weight names by default; Keras `.h5` weight files are
+read and (config.CHECKPOINT_FORMAT = 'h5') written by the pure-Python ursonet_b200/hdf5.py; pretrained-weight downloads
+raise (no network); multi-GPU is real (one process per GPU under torchrun, NCCL all-reduce of the flat gradient arena)
+instead of the reference's commented-out stub.
 """
 import datetime
 import os
@@ -102,7 +103,8 @@ class UrsoNet:
             if m:
                 self.log_dir = os.path.dirname(model_path)
                 self.epoch = int(m.group(1))
-        self.checkpoint_path = os.path.join(self.log_dir, "weights_{}_*epoch*.npz".format(self.config.NAME.lower()))
+        ext = "h5" if getattr(self.config, "CHECKPOINT_FORMAT", "npz") == "h5" else "npz"
+        self.checkpoint_path = os.path.join(self.log_dir, "weights_{}_*epoch*.{}".format(self.config.NAME.lower(), ext))
         self.checkpoint_path = self.checkpoint_path.replace("*epoch*", "{epoch:04d}")
 
     def get_last_checkpoint(self, model_name):
@@ -126,22 +128,13 @@ class UrsoNet:
 
     @staticmethod
     def _read_weight_file(path):
+        """'.npz' (this build's own format) or a Keras HDF5 weight file (`model.save_weights`, or a full `model.save`
+        file with a 'model_weights' group, net.py:831-832), read by ursonet_b200/hdf5.py (no h5py needed)."""
         if path.endswith(".npz"):
             with np.load(path) as z:
                 return {k: z[k] for k in z.files}
-        try:
-            import h5py
-        except ImportError as e:
-            raise ImportError("reading Keras .h5 weights needs h5py, which is not installed in this image") from e
-        out = {}
-        with h5py.File(path, "r") as f:
-            root = f["model_weights"] if "model_weights" in f else f
-            for layer in root:
-                def visit(name, obj, layer=layer):
-                    if isinstance(obj, h5py.Dataset):
-                        out[layer + "/" + name.split("/")[-1].split(":")[0]] = np.asarray(obj)
-                root[layer].visititems(visit)
-        return out
+        from . import hdf5
+        return hdf5.keras_to_state_dict(hdf5.read_keras_weights(path))
 
     def load_weights(self, weights_in_path, weights_out_path, by_name=False, exclude=None):
         """By-name load with an exclude list (net.py:816-852); then set_log_dir(weights_out_path)."""
@@ -153,8 +146,14 @@ class UrsoNet:
         self.set_log_dir(weights_out_path)
 
     def save_weights(self, path):
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        np.savez(path, **self.engine.params.state_dict())
+        """Weights only, like ModelCheckpoint(save_weights_only=True) (net.py:1120): '.npz', or a Keras-layout HDF5 file
+        when the path ends in '.h5' (config.CHECKPOINT_FORMAT = 'h5' makes train() write those)."""
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        if path.endswith(".h5"):
+            from . import hdf5
+            hdf5.write_keras_weights(path, self.engine.params.state_dict())
+        else:
+            np.savez(path, **self.engine.params.state_dict())
 
     def get_imagenet_weights(self, backbone):
         raise RuntimeError("pretrained ImageNet weights must be downloaded (net.py:854-893): no network in this build; "
