@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--overlap", action="store_true", help="overlapped two-part gradient all-reduce (N > 1, experimental)")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
+    ap.add_argument("--no-residual-mma", action="store_true", help="A/B: residual / fan-in addends added by the epilogue warps instead of the tensor core")
     ap.add_argument("--stage-split", type=int, default=4, help="A/B: leading convs whose weight operands get their own staging launch")
     ap.add_argument("--pair-l2", action="store_true", help="A/B: co-run the dgrad / wgrad launches that share a large gradient tensor")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
@@ -191,6 +192,8 @@ def main():
     from ursonet_b200 import lib as _lib
     if args.no_pdl:
         _lib.load().urso_set_pdl(0)
+    if args.no_residual_mma:
+        _lib.load().urso_set_residual_mma(0)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

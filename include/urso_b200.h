@@ -33,6 +33,10 @@ void urso_set_dry_run(int on);
  * allocation, tensor-map prefetch) while the previous kernel of the stream drains; it reads that kernel's results only after
  * griddepcontrol.wait.  0 = plain stream order. */
 void urso_set_pdl(int on);
+/* Engine F launches planned while this is on (default) accumulate their addend (residual / gradient fan-in) on the tensor
+ * core -- per 64-channel chunk one extra K step "addend tile x 64x64 identity" into the chunk's TMEM columns -- instead of
+ * loading, unpacking and adding it in the epilogue warps; bit-exact products, fp32 accumulation.  0 = epilogue add. */
+void urso_set_residual_mma(int on);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);

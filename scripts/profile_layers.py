@@ -10,6 +10,9 @@ class A: pass
 a = A(); a.batch = int(os.environ.get("BATCH", "32")); a.backbone = os.environ.get("BACKBONE", "resnet50")
 a.width, a.height, a.ori_resolution, a.regress_ori = 960, 600, 16, False
 from ursonet_b200.engine import Engine
+from ursonet_b200 import lib as _lib
+if os.environ.get("RESIDUAL_MMA", "1") == "0":
+    _lib.load().urso_set_residual_mma(0)
 cfg = bench.make_cfg(a)
 eng = Engine(cfg, a.batch, training=True)
 img, loc, ori = bench.synth_batch(cfg, a.batch, 0)

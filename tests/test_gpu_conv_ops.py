@@ -23,6 +23,16 @@ def cta_limit(request):
     lib.load().urso_set_max_ctas(0)
 
 
+@pytest.fixture(params=[1, 0], ids=["addend_mma", "addend_epilogue"])
+def residual_mma(request):
+    """Launches with an addend run both ways: accumulated on the tensor core as an extra identity K step (default), or
+    loaded and added by the epilogue warps (urso_set_residual_mma)."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_residual_mma(request.param)
+    yield request.param
+    lib.load().urso_set_residual_mma(1)
+
+
 def bf16_exact(*shape, scale=1.0, seed=0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(torch.float64)
@@ -51,7 +61,7 @@ CASES = [  # k, stride, padding, cin, cout, h, w
 
 
 @pytest.mark.parametrize("k,stride,padding,cin,cout,h,w", CASES)
-def test_conv2d_fwd_operator(k, stride, padding, cin, cout, h, w):
+def test_conv2d_fwd_operator(k, stride, padding, cin, cout, h, w, residual_mma):
     from ursonet_b200 import lib
     N = 2
     x = bf16_exact(N, h, w, cin, seed=1)
@@ -127,7 +137,7 @@ DGRAD_CASES = [  # list of consumers (k, stride, padding, cout), cin, h, w, spar
 
 
 @pytest.mark.parametrize("consumers,cin,h,w,sparse,use_mask,use_addend", DGRAD_CASES)
-def test_conv2d_dgrad_operator(consumers, cin, h, w, sparse, use_mask, use_addend):
+def test_conv2d_dgrad_operator(consumers, cin, h, w, sparse, use_mask, use_addend, residual_mma):
     from ursonet_b200 import lib
     N = 2
     shapes, dys, ws, scs, ref_terms = [], [], [], [], []

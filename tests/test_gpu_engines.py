@@ -23,6 +23,16 @@ def cta_limit(request):
     lib.load().urso_set_max_ctas(0)
 
 
+@pytest.fixture(params=[1, 0], ids=["addend_mma", "addend_epilogue"])
+def residual_mma(request):
+    """Launches with an addend run both ways: accumulated on the tensor core as an extra identity K step (default), or
+    loaded and added by the epilogue warps (urso_set_residual_mma)."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_residual_mma(request.param)
+    yield request.param
+    lib.load().urso_set_residual_mma(1)
+
+
 def bf16_exact(*shape, scale=1.0, seed=0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(torch.float64)
@@ -113,7 +123,7 @@ def test_engine_f_forward(kh, stride, padding, cin, cout, h, w, flatten, block_n
 
 @pytest.mark.parametrize("which", ["addend", "mask", "both"])
 @pytest.mark.parametrize("flatten", [True, False])
-def test_engine_f_tma_epilogue_inputs_many_tiles(which, flatten):
+def test_engine_f_tma_epilogue_inputs_many_tiles(which, flatten, residual_mma):
     """more tiles than SMs x prefetch depth, N = 256 (4 chunks/tile): exercises the per-warp input ring phases"""
     N, H, W, CI, CO = 8, 40, 64, 64, 256
     x = bf16_exact(N, H, W, CI, seed=21)

@@ -29,7 +29,9 @@ int num_sms() {
 }
 
 static int g_pdl = 1;
+static int g_residual_mma = 1;
 bool pdl_enabled() { return g_pdl != 0; }
+bool residual_mma_enabled() { return g_residual_mma != 0; }
 static int g_max_ctas = 0;
 bool dry_run() { return g_dry_run != 0; }
 int max_ctas() {
@@ -98,6 +100,7 @@ int urso_num_sms(void) { return urso::num_sms(); }
 void urso_set_max_ctas(int n) { urso::g_max_ctas = n; }
 void urso_set_dry_run(int on) { urso::g_dry_run = on; }
 void urso_set_pdl(int on) { urso::g_pdl = on; }
+void urso_set_residual_mma(int on) { urso::g_residual_mma = on; }
 int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
 int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }
 }

@@ -13,6 +13,7 @@ namespace urso {
 void set_error(const char* fmt, ...);
 int num_sms();
 bool pdl_enabled();   // urso_set_pdl: launch the tcgen05 engines with programmatic stream serialization (default on)
+bool residual_mma_enabled();   // urso_set_residual_mma: Engine F accumulates the addend on the tensor core (default on)
 bool dry_run();   // urso_set_dry_run(1): create-calls plan only (CPU-side tests of the planners)
 int max_ctas();   // num_sms() or the urso_set_max_ctas() limit: grid size of the persistent Engine-F kernels
 

@@ -73,6 +73,7 @@ struct ConvGemmParams {
   CUtensorMap a_halo_map;                   // halo mode: box {64, halo_w, halo_h, 1} of view 0
   CUtensorMap b_map;                        // box {64, BLOCK_N}
   CUtensorMap out_map, add_map, mask_map;   // epilogue slabs: box {64, bw, bh, 1}
+  CUtensorMap radd_map;                     // addend as an A operand: box {64, TW, TH, 1} on the output grid
   SegDev seg[URSO_MAX_SEGS];
   int n_seg, ksteps;
   int OW, OH, NB;
@@ -89,6 +90,12 @@ struct ConvGemmParams {
   int pipe_bytes;    // shared memory of one pipeline (its A ring followed by its B ring)
   int b_ring_off;    // offset of a pipeline's B ring from its base
   int bres_off, ctrl_off;
+  int radd;          // the addend is accumulated by the tensor core: per 64-channel chunk of the tile one extra K step
+                     // A = addend tile, B = 64x64 identity (resident, ident_off), N = 64 at the chunk's TMEM columns.
+                     // The epilogue then has no input stream at all (no ring, no unpack, no add).  One pipeline only
+                     // (BLOCK_N = 256): producer warp 3 feeds the addend tiles through their own ring of kRaddStages
+                     // (barriers: the halo mode's A-ring pair), producer warp 0 owns every operand round.
+  int ident_off, radd_off;
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
   int ei_depth;      // per-warp prefetch ring depth of the epilogue inputs (chunks ahead)
@@ -116,6 +123,7 @@ constexpr int kTrStride = 36;                       // legacy colsum transpose s
 constexpr int kLegacyScratchBytes = 4 * 32 * kTrStride * 4;
 constexpr int kSmemBudget = 227 * 1024;             // the dynamic smem base is 1 KB aligned by declaration: no slack
 constexpr int kMaxBresBytes = 100 * 1024;
+constexpr int kRaddStages = 4;                      // addend ring: one BLOCK_N = 256 tile (4 chunks of 64 channels)
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
@@ -128,6 +136,10 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, i
   img = (int)im;
   h0 = thi * p.TH;
   w0 = twi * p.TW;
+}
+
+__device__ __forceinline__ int fdiv_ntile(const ConvGemmParams& p, int tile) {
+  return tile - (int)fdiv((uint32_t)tile, p.fd_ntn) * p.n_tiles_n;
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.a_maps[i]);
     tma_prefetch_desc(&p.b_map);
     if (p.halo) tma_prefetch_desc(&p.a_halo_map);
+    if (p.radd) tma_prefetch_desc(&p.radd_map);
     if (p.epi_tma) {
       tma_prefetch_desc(&p.out_map);
       tma_prefetch_desc(&p.add_map);
@@ -235,6 +248,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   }
   if (p.shift_bytes) {
     for (int c = threadIdx.x; c < p.ncols; c += blockDim.x) s_shift[c] = __ldg(p.shift + c);
+  }
+  if (p.radd) {
+    // 64 x 64 bf16 identity as a K-major SWIZZLE_128B operand tile: row n = 128 bytes, its 16-byte chunk j (k = 8j..8j+7)
+    // stored at chunk position j ^ (n & 7)
+    const uint32_t ident = smem_u32(smem + p.ident_off);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+      const int n = i >> 3, j = (i & 7) ^ (n & 7);
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if ((n >> 3) == j) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;
+      sts128(ident + i * 16, w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async();     // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
   }
   tc_fence_before();
   __syncthreads();
@@ -310,9 +335,34 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
+    } else if (p.radd && pw == 1) {
+      // addend ring (one pipeline): a whole tile's 64-channel chunks ahead of the MMA warp, which consumes them after the
+      // tile's operand rounds
+      int slot = 0;
+      uint32_t rphase = 0;
+      uint8_t* ring = smem + p.radd_off;
+      for (int wk = (int)blockIdx.x; wk < p.total_tiles; wk += (int)gridDim.x) {
+        int n_tile, img, h0, w0;
+        decode_tile(p, wk, n_tile, img, h0, w0);
+        const int n0 = n_tile * BLOCK_N;
+        const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
+        for (int r = 0; r < rn; ++r) {
+          mbar_wait(&aempty_bar[slot], rphase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull_bar[slot], kATileBytes);
+            tma_load_4d(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img);
+          }
+          __syncwarp();
+          if (++slot == kRaddStages) {
+            slot = 0;
+            rphase ^= 1;
+          }
+        }
+      }
     } else {
       // stream mode: a stage holds kpack K steps (A tile + B tile each); the owning producer arms the barrier once
       // with the bytes of the whole round and issues its tile loads
+      const bool own_all = npipe == 2 || p.radd != 0;      // (with an addend ring producer 0 issues every operand round)
       int stage = 0, gg = 0;
       uint32_t phase = 0;
       const int kp = p.kpack;
@@ -324,7 +374,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
-            if (npipe == 2 || (gg & 1) == pw) {
+            if (own_all || (gg & 1) == pw) {
               if (slot == 0) mbar_wait(&emptyb[stage], phase ^ 1);
               if (elect_one()) {
                 if (slot == 0) {
@@ -432,8 +482,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         __syncwarp();
       }
     } else {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, rslot = 0;
+      uint32_t phase = 0, rphase = 0;
+      const uint32_t radd_base = smem_u32(smem + p.radd_off);
       const int kp = p.kpack;
       const int ksteps = p.ksteps;
       int li = 0;
@@ -460,6 +511,27 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if (p.radd) {       // D[:, 64r .. 64r+63] += addend chunk r x I
+          constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 64, 0, 0);
+          const uint64_t bd = kDescHiB | (smem_u32(smem + p.ident_off) >> 4);
+          const int n0 = fdiv_ntile(p, wk) * BLOCK_N;
+          const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
+          for (int r = 0; r < rn; ++r) {
+            mbar_wait(&afull_bar[rslot], rphase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad = kDescHiB | ((radd_base + rslot * kATileBytes) >> 4);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d_tmem + r * 64, ad + 2 * k, bd + 2 * k, idesc64, 1u);
+              umma_commit(&aempty_bar[rslot]);
+            }
+            __syncwarp();
+            if (++rslot == kRaddStages) {
+              rslot = 0;
+              rphase ^= 1;
+            }
           }
         }
         if (elect_one()) umma_commit(&tfullb[as]);      // accumulator complete -> epilogue
@@ -579,10 +651,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 s4 = sp[i];
-                v[4 * i + 0] += s4.x;
-                v[4 * i + 1] += s4.y;
-                v[4 * i + 2] += s4.z;
-                v[4 * i + 3] += s4.w;
+                fadd2(v[4 * i + 0], v[4 * i + 1], s4.x, s4.y);
+                fadd2(v[4 * i + 2], v[4 * i + 3], s4.z, s4.w);
               }
             }
             if (p.has_add) {
@@ -885,7 +955,7 @@ struct PipePlan {
   int pipe_bytes, b_ring_off, bres_bytes;
 };
 
-bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, long long tiles_per_cta, PipePlan* pl) {
+bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, long long tiles_per_cta, PipePlan* pl) {
   const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2;
   // preference order: two pipelines (hides the issue-side cost of a barrier round, the bound of the N <= 128 launches),
   // two K steps per round where the ring still gets >= 2 stages per pipeline
@@ -897,6 +967,7 @@ bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, long long tiles
     if (kp == 2 && (ksteps < 4 || bn > 128)) continue;
     if (kp == 2 && np == 2 && bn == 128) continue;     // N = 128: 4 MMAs per round already run at the full rate with 2 issuers
     if (kp == 2 && np == 1 && epi_inputs) continue;    // measured in round 1: loses where the epilogue rings squeeze the ring
+    if (kp == 2 && radd) continue;                     // the addend rounds are single K steps
     int stages = avail / (np * kp * step_bytes);
     if (stages > urso::kMaxStages) stages = urso::kMaxStages;
     const int need = (np == 2 || kp == 2) ? 2 : 2;
@@ -991,9 +1062,12 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   // epilogue flavour and its shared memory
   const int kColAccOnly = d->colsum != nullptr ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
   p.colacc_bytes = kColAccOnly;
-  p.has_add = d->addend.ptr != nullptr;
   p.has_mask = d->mask.ptr != nullptr;
   p.epi_tma = (!d->out_fp32 && d->b_rows % 64 == 0 && bn >= 64) ? 1 : 0;
+  // residual / fan-in addend through the tensor core (see ConvGemmParams::radd): stream mode with the TMA epilogue, one
+  // pipeline (BLOCK_N = 256), short K loops -- the store-bound launches, whose epilogue warps are the bottleneck.  (With
+  // >= 8 K steps the third operand stage that the addend ring displaces is worth more: res5x_2c 54 -> 67 us measured.)
+  p.radd = (residual_mma_enabled() && d->addend.ptr != nullptr && p.epi_tma && !d->halo && bn == 256 && ksteps <= 4) ? 1 : 0;
   p.shift_bytes = (p.epi_tma && d->shift != nullptr) ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
   const int kColAcc = kColAccOnly + p.shift_bytes;     // everything between the control block and the epilogue rings
   if ((d->relu_bits.ptr != nullptr || d->mask_bits.ptr != nullptr) && !p.epi_tma) {
@@ -1006,28 +1080,34 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     delete h;
     return 2;
   }
-  const int n_in = p.has_add + p.has_mask;
-  int epi_bytes;
-  if (p.epi_tma) {
-    // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight).
-    // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to the operand pipelines.  Launches
-    // with a short K loop (<= 6 K steps: the MMAs of a tile take less time than its epilogue) are epilogue / store bound:
-    // a depth-1 input ring would expose the full TMA latency of every chunk (measured per layer in round 1).
-    const bool heavy = ksteps >= 4;
-    const bool epi_bound = ksteps <= 6;
-    p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
-    p.eo_depth = (heavy || n_in == 2) ? 1 : 2;
-    if (n_in > 0 && epi_bound) p.ei_depth = 2;
-    epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
-    const int bn_min = bn == 256 ? 128 : bn;   // the narrowest tile this launch may fall back to must still get 2 stages
-    if (p.ei_depth == 2 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
-      p.ei_depth = 1;
+  int n_in = 0, radd_bytes = 0, epi_bytes = 0;
+  for (const int bn_asked = bn;; p.radd = 0, bn = bn_asked) {       // second pass: the addend ring did not fit
+    p.has_add = d->addend.ptr != nullptr && !p.radd;
+    n_in = p.has_add + p.has_mask;
+    radd_bytes = p.radd ? 8192 + kRaddStages * kATileBytes : 0;     // identity tile + addend ring
+    if (p.epi_tma) {
+      // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight).
+      // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to the operand pipelines.  Launches
+      // with a short K loop (<= 6 K steps: the MMAs of a tile take less time than its epilogue) are epilogue / store bound:
+      // a depth-1 input ring would expose the full TMA latency of every chunk (measured per layer in round 1).
+      const bool heavy = ksteps >= 4;
+      const bool epi_bound = ksteps <= 6;
+      p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
+      p.eo_depth = (heavy || n_in == 2 || p.radd) ? 1 : 2;
+      if (n_in > 0 && epi_bound) p.ei_depth = 2;
       epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
+      const int room = kSmemBudget - kCtrlBytes - kColAcc - radd_bytes;
+      const int bn_min = bn == 256 ? 128 : bn;   // the narrowest tile this launch may fall back to must still get 2 stages
+      if (p.ei_depth == 2 && room - epi_bytes < 2 * (kATileBytes + bn_min * kBlockK * 2)) {
+        p.ei_depth = 1;
+        epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
+      }
+      const int min_stages = ((n_in > 0 && epi_bound) || p.radd) ? 2 : 3;
+      if (bn == 256 && room - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
+    } else {
+      epi_bytes = kLegacyScratchBytes;
     }
-    const int min_stages = (n_in > 0 && epi_bound) ? 2 : 3;
-    if (bn == 256 && kSmemBudget - kCtrlBytes - kColAcc - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
-  } else {
-    epi_bytes = kLegacyScratchBytes;
+    if (!p.radd || bn == 256) break;
   }
   h->block_n = bn;
   p.n_tiles_n = (d->b_rows + bn - 1) / bn;
@@ -1075,7 +1155,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       p.ei_depth = p.eo_depth = 1;
       epi_bytes = 8 * n_in * kSlabBytes + 8 * kSlabBytes;
     }
-    const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes;
+    const int avail = kSmemBudget - kCtrlBytes - kColAcc - epi_bytes - radd_bytes;
     if (d->halo) {
       const int a_stage_bytes = (halo_w * halo_h * 128 + 1023) / 1024 * 1024;
       if (plan_halo(avail, bn, ksteps, p.n_tiles_n, a_stage_bytes, tiles_per_cta, &pl)) {
@@ -1089,7 +1169,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
         continue;
       }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
     }
-    planned = plan_stream(avail, bn, ksteps, n_in > 0, tiles_per_cta, &pl);
+    planned = plan_stream(avail, bn, ksteps, n_in > 0, p.radd != 0, tiles_per_cta, &pl);
   }
   if (!planned) {
     set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
@@ -1110,7 +1190,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.pipe_bytes = pl.pipe_bytes;
   p.b_ring_off = pl.b_ring_off;
   p.bres_off = pl.npipe * pl.pipe_bytes;
-  p.ctrl_off = p.bres_off + pl.bres_bytes;
+  p.ident_off = p.bres_off + pl.bres_bytes;
+  p.radd_off = p.ident_off + (p.radd ? 8192 : 0);
+  p.ctrl_off = p.radd_off + (p.radd ? kRaddStages * kATileBytes : 0);
   const int fixed = p.ctrl_off + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
@@ -1133,6 +1215,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     int rc = make_pix_map(&p.out_map, d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
     if (!rc) rc = make_pix_map(&p.add_map, p.has_add ? d->addend : d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
     if (!rc) rc = make_pix_map(&p.mask_map, p.has_mask ? d->mask : d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
+    if (!rc && p.radd) rc = make_pix_map(&p.radd_map, d->addend, d->b_rows, d->OW, d->OH, d->NB, d->TW, d->TH);
     if (rc) {
       delete h;
       return rc;

@@ -187,6 +187,16 @@ __device__ __forceinline__ void tma_store_4d_u32(const CUtensorMap* m, uint32_t 
                "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// two fp32 adds in one instruction (FADD2; round-to-nearest like FADD, so results are bit-identical): halves the issue
+// slots of the epilogue's per-element adds
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(x));
+}
+
 // fp32 add-reduction of a contiguous shared-memory span into global memory by the bulk-copy engine (16-byte aligned
 // addresses, size a multiple of 16): the L2 performs the adds on whole sectors, the SM issues ONE instruction per span
 __device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t smem_addr, uint32_t bytes) {
