@@ -37,6 +37,18 @@ void urso_set_pdl(int on);
  * core -- per 64-channel chunk one extra K step "addend tile x 64x64 identity" into the chunk's TMEM columns -- instead of
  * loading, unpacking and adding it in the epilogue warps; bit-exact products, fp32 accumulation.  0 = epilogue add. */
 void urso_set_residual_mma(int on);
+/* Tile order of the Engine-F launches planned from now on: 1 = the persistent CTAs walk the output tiles in DESCENDING
+ * order.  A host that alternates the order from one launch of a dependent chain to the next makes every launch start on
+ * the pixels its producer wrote LAST -- the part of that tensor still resident in the 126 MB L2.  Results are identical. */
+void urso_set_tile_reverse(int on);
+/* L2 eviction-priority hints on the operand loads of the Engine-F launches planned from now on (default 0 = none):
+ * bit 0: activation and addend tiles evict_first (streamed once; they must not displace the freshly written output),
+ * bit 1: weight tiles evict_last (re-read by every CTA). */
+void urso_set_l2_hints(int mask);
+/* Engine-F launches planned while on: the TMA producers also issue cp.async.bulk.prefetch.tensor (L2 only) for the
+ * activation / addend tiles of the CTA's NEXT output tile, so that DRAM latency is not bounded by the depth of the
+ * shared-memory ring (2-4 stages on the launches with large epilogue rings).  Scheduling only; results are identical. */
+void urso_set_l2_prefetch(int on);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);

@@ -14,6 +14,9 @@ void set_error(const char* fmt, ...);
 int num_sms();
 bool pdl_enabled();   // urso_set_pdl: launch the tcgen05 engines with programmatic stream serialization (default on)
 bool residual_mma_enabled();   // urso_set_residual_mma: Engine F accumulates the addend on the tensor core (default on)
+bool tile_reverse();   // urso_set_tile_reverse: Engine-F launches planned while on walk their tiles in DESCENDING order
+int l2_hints();        // urso_set_l2_hints: bit 0 = activation / addend loads evict_first, bit 1 = weight loads evict_last
+bool l2_prefetch();    // urso_set_l2_prefetch: Engine-F producers prefetch the next tile's activation tiles into L2
 bool dry_run();   // urso_set_dry_run(1): create-calls plan only (CPU-side tests of the planners)
 int max_ctas();   // num_sms() or the urso_set_max_ctas() limit: grid size of the persistent Engine-F kernels
 

@@ -81,6 +81,9 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   FastDiv fd_ntn, fd_tw, fd_th;
   int ncols;
+  int rev;           // 1: tiles are walked in descending order (urso_set_tile_reverse)
+  unsigned long long pol_a, pol_b;   // L2 eviction-priority hints of the activation / weight tile loads (0 = none)
+  int l2pf;          // 1: producers prefetch the activation (and addend) tiles of the CTA's NEXT tile into L2 (urso_set_l2_prefetch)
   int npipe;         // 1 or 2 producer -> MMA pipelines working on alternate tiles
   int stages;        // per pipeline: stream mode = ring of (A, B) stages; halo mode = ring of B tiles (unless resident)
   int kpack;         // stream mode: K steps (of 64) per stage / barrier round
@@ -127,6 +130,7 @@ constexpr int kRaddStages = 4;                      // addend ring: one BLOCK_N 
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
+  if (p.rev) tile = p.total_tiles - 1 - tile;
   const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntn);
   n_tile = tile - (int)m_tile * p.n_tiles_n;
   const uint32_t rest = fdiv(m_tile, p.fd_tw);
@@ -139,6 +143,7 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, i
 }
 
 __device__ __forceinline__ int fdiv_ntile(const ConvGemmParams& p, int tile) {
+  if (p.rev) tile = p.total_tiles - 1 - tile;
   return tile - (int)fdiv((uint32_t)tile, p.fd_ntn) * p.n_tiles_n;
 }
 
@@ -154,6 +159,17 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+
+// operand tile loads with an optional L2 eviction-priority hint (warp-uniform branch, one elected lane issues)
+__device__ __forceinline__ void load_a(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                       unsigned long long pol) {
+  if (pol) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
+  else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+}
+__device__ __forceinline__ void load_b(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, unsigned long long pol) {
+  if (pol) tma_load_2d_hint(dst, m, bar, c0, c1, pol);
+  else tma_load_2d(dst, m, bar, c0, c1);
 }
 
 // Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (elect_one()) {
           mbar_arrive_expect_tx(bres_bar, p.ksteps * kBTileBytes);
           for (int ks = 0; ks < p.ksteps; ++ks)
-            tma_load_2d(smem + p.bres_off + ks * kBTileBytes, &p.b_map, bres_bar, ks * kBlockK, 0);
+            load_b(smem + p.bres_off + ks * kBTileBytes, &p.b_map, bres_bar, ks * kBlockK, 0, p.pol_b);
         }
         __syncwarp();
       }
@@ -302,13 +318,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
         decode_tile(p, wk, n_tile, img, h0, w0);
+        const int wk_nx = wk + npipe * (int)gridDim.x;
+        const bool pf_on = p.l2pf && a_mine && wk_nx < p.total_tiles;
+        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
+        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         for (int c = 0; c < c_chunks; ++c) {
           if (a_mine) {
             mbar_wait(&aemptyb[a_stage], a_phase ^ 1);
             if (elect_one()) {
+              if (pf_on) tma_prefetch_4d(&p.a_halo_map, c * kBlockK, nx_w0 + p.halo_dw_min, nx_h0 + p.halo_dh_min, nx_img);
               mbar_arrive_expect_tx(&afullb[a_stage], p.halo_bytes);
-              tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afullb[a_stage], c * kBlockK,
-                          w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
+              load_a(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afullb[a_stage], c * kBlockK, w0 + p.halo_dw_min,
+                     h0 + p.halo_dh_min, img, p.pol_a);
             }
             __syncwarp();
           }
@@ -322,8 +343,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 mbar_wait(&emptyb[stage], phase ^ 1);
                 if (elect_one()) {
                   mbar_arrive_expect_tx(&fullb[stage], kBTileBytes);
-                  tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &fullb[stage], (s * c_chunks + c) * kBlockK,
-                              n_tile * BLOCK_N);
+                  load_b(sB + stage * kBTileBytes, &p.b_map, &fullb[stage], (s * c_chunks + c) * kBlockK, n_tile * BLOCK_N,
+                         p.pol_b);
                 }
                 __syncwarp();
               }
@@ -346,11 +367,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         decode_tile(p, wk, n_tile, img, h0, w0);
         const int n0 = n_tile * BLOCK_N;
         const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
+        // (the ring holds one tile: the loads below already run a tile ahead; the prefetch reaches two tiles further)
+        const int wk_nx = wk + 2 * (int)gridDim.x;
+        const bool pf_on = p.l2pf && wk_nx < p.total_tiles;
+        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
+        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         for (int r = 0; r < rn; ++r) {
           mbar_wait(&aempty_bar[slot], rphase ^ 1);
           if (elect_one()) {
+            if (pf_on && nx_n * BLOCK_N + r * kBlockK < p.ncols)
+              tma_prefetch_4d(&p.radd_map, nx_n * BLOCK_N + r * kBlockK, nx_w0, nx_h0, nx_img);
             mbar_arrive_expect_tx(&afull_bar[slot], kATileBytes);
-            tma_load_4d(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img);
+            load_a(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img, p.pol_a);
           }
           __syncwarp();
           if (++slot == kRaddStages) {
@@ -370,6 +398,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
         decode_tile(p, wk, n_tile, img, h0, w0);
+        const int wk_nx = wk + npipe * (int)gridDim.x;
+        const bool pf_on = p.l2pf && wk_nx < p.total_tiles;
+        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
+        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         int kcol = 0, ks = 0, slot = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
@@ -381,9 +413,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                   const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
                   mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes));
                 }
-                tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK,
-                            w0 + sg.dw, h0 + sg.dh, img);
-                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N);
+                load_a(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK, w0 + sg.dw,
+                       h0 + sg.dh, img, p.pol_a);
+                if (pf_on) tma_prefetch_4d(&p.a_maps[sg.map_id], c * kBlockK, nx_w0 + sg.dw, nx_h0 + sg.dh, nx_img);
+                load_b(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N, p.pol_b);
               }
               __syncwarp();
             }
@@ -577,7 +610,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         uint8_t* dst = ei + slot * slot_bytes;
         mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
         const int c = pf.n_tile * BLOCK_N + pf.j * 64;
-        if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
+        if (p.has_add) load_a(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img, p.pol_a);
         if (p.has_mask)
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         pf.next(p);
@@ -1221,6 +1254,10 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       return rc;
     }
   }
+  p.rev = tile_reverse() ? 1 : 0;
+  p.l2pf = l2_prefetch() ? 1 : 0;
+  p.pol_a = (l2_hints() & 1) ? kL2EvictFirst : 0ull;
+  p.pol_b = (l2_hints() & 2) ? kL2EvictLast : 0ull;
   p.n_seg = d->n_seg;
   p.OW = d->OW; p.OH = d->OH; p.NB = d->NB;
   p.TW = d->TW; p.TH = d->TH;

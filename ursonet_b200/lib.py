@@ -98,6 +98,9 @@ SIGNATURES = {
     "urso_set_dry_run": [_i32],
     "urso_set_pdl": [_i32],
     "urso_set_residual_mma": [_i32],
+    "urso_set_tile_reverse": [_i32],
+    "urso_set_l2_hints": [_i32],
+    "urso_set_l2_prefetch": [_i32],
     "urso_sizeof_convgemm_desc": [],
     "urso_sizeof_wgrad_desc": [],
     "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
@@ -168,7 +171,8 @@ SIGNATURES = {
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
-             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_set_tile_reverse": None,
+             "urso_set_l2_hints": None, "urso_set_l2_prefetch": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
              "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
              "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
