@@ -155,11 +155,14 @@ def main():
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
     ap.add_argument("--no-residual-mma", action="store_true", help="A/B: residual / fan-in addends added by the epilogue warps instead of the tensor core")
+    ap.add_argument("--residual-mma", type=int, default=-1, help="A/B: urso_set_residual_mma mode (0 epilogue, 1 addend ring, 2 addend chunks in the operand stages)")
     ap.add_argument("--stage-split", type=int, default=4, help="A/B: leading convs whose weight operands get their own staging launch")
     ap.add_argument("--pair-l2", action="store_true", help="A/B: co-run the dgrad / wgrad launches that share a large gradient tensor")
     ap.add_argument("--zigzag", type=int, default=0, help="A/B: alternate the tile order of consecutive conv launches (bit 0 forward, bit 1 gradient chain)")
     ap.add_argument("--l2-hints", type=int, default=0, help="A/B: L2 eviction hints of the operand loads (bits 0-1 forward, bits 2-3 gradient chain)")
     ap.add_argument("--l2-prefetch", type=int, default=0, help="A/B: producers prefetch the next tile into L2 (bit 0 forward, bit 1 gradient chain)")
+    ap.add_argument("--deep-addend-ring", action="store_true", help="A/B: left-over shared memory deepens the addend ring (urso_set_addend_ring_deep(1))")
+    ap.add_argument("--no-wgrad-halo", action="store_true", help="A/B: Engine W loads one operand atom per filter tap (urso_set_wgrad_halo(0))")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch CUDA-event table here")
@@ -197,6 +200,12 @@ def main():
         _lib.load().urso_set_pdl(0)
     if args.no_residual_mma:
         _lib.load().urso_set_residual_mma(0)
+    if args.deep_addend_ring:
+        _lib.load().urso_set_addend_ring_deep(1)
+    if args.no_wgrad_halo:
+        _lib.load().urso_set_wgrad_halo(0)
+    if args.residual_mma >= 0:
+        _lib.load().urso_set_residual_mma(args.residual_mma)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -9,6 +9,7 @@ import torch
 from oracle import ursonet_oracle as O
 
 pytestmark = pytest.mark.gpu
+DEFAULT_RESIDUAL_MMA = 1      # the library's default (urso_set_residual_mma)
 DEV = "cuda"
 
 
@@ -32,14 +33,14 @@ def cta_limit(request):
     lib.load().urso_set_l2_prefetch(0)
 
 
-@pytest.fixture(params=[1, 0], ids=["addend_mma", "addend_epilogue"])
+@pytest.fixture(params=[2, 1, 0], ids=["addend_mma_in_stage", "addend_mma_ring", "addend_epilogue"])
 def residual_mma(request):
     """Launches with an addend run both ways: accumulated on the tensor core as an extra identity K step (default), or
     loaded and added by the epilogue warps (urso_set_residual_mma)."""
     from ursonet_b200 import lib
     lib.load().urso_set_residual_mma(request.param)
     yield request.param
-    lib.load().urso_set_residual_mma(1)
+    lib.load().urso_set_residual_mma(DEFAULT_RESIDUAL_MMA)
 
 
 def bf16_exact(*shape, scale=1.0, seed=0):
@@ -205,11 +206,25 @@ WGRAD_CASES = [  # k, stride, padding, cin, cout, h, w, sparse
     (3, 2, 1, 64, 128, 16, 24, False),
     (1, 1, "valid", 64, 256, 16, 24, True),
     (3, 1, "same", 64, 64, 16, 24, True),
+    (3, 1, "same", 128, 128, 16, 24, False),      # halo mode, two 64-channel atoms per box (LBO = box pitch), 3 tap groups
+    (3, 1, "same", 128, 256, 24, 40, False),      # halo mode, block_q 256 (2 taps per CTA): not taken (boxes >= 70 % of the atoms)
+    (3, 1, "same", 64, 64, 23, 31, False),        # halo mode on a map that 8 x 8 blocks do not tile (clipped boxes)
+    (3, 1, 1, 64, 64, 10, 14, False),             # explicit padding 1 (shallow block conv2)
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["wgrad_halo", "wgrad_atom_per_tap"])
+def wgrad_halo(request):
+    """Engine W with and without its halo mode (urso_set_wgrad_halo): one box + halo per K step for all taps of a CTA, or
+    one operand atom per tap."""
+    from ursonet_b200 import lib
+    lib.load().urso_set_wgrad_halo(request.param)
+    yield request.param
+    lib.load().urso_set_wgrad_halo(1)
+
+
 @pytest.mark.parametrize("k,stride,padding,cin,cout,h,w,sparse", WGRAD_CASES)
-def test_conv2d_wgrad_operator(k, stride, padding, cin, cout, h, w, sparse):
+def test_conv2d_wgrad_operator(k, stride, padding, cin, cout, h, w, sparse, wgrad_halo):
     from ursonet_b200 import lib
     N = 2
     shape = lib.conv_shape(N, h, w, cin, cout, k, stride, padding)

@@ -62,6 +62,11 @@ def plan_network(l, cfg, B):
         wd.shape, wd.x, wd.dy, wd.G = d.shape, FAKE, FAKE, FAKE
         hw = C.c_void_p()
         assert l.urso_conv2d_wgrad_create(C.byref(wd), C.byref(hw)) == 0, (c.name, l.urso_last_error())
+        w10 = (C.c_int32 * 10)()
+        l.urso_conv2d_wgrad_plan_info(hw, w10)
+        infos["w:" + c.name] = dict(zip(("block_q", "halo", "halo_w", "stages", "stage_bytes", "units", "groups", "split_k",
+                                         "grid", "pair_mode"), w10))
+        assert w10[3] >= 2 and w10[3] * w10[4] <= 200 * 1024, (c.name, list(w10))
         l.urso_conv2d_wgrad_destroy(hw)
     groups, sparse = backward_groups(g)
     n_dgrad = 0
@@ -104,7 +109,7 @@ CONFIGS = [   # BASELINE.json configs[0..4] + the other backbones at the bench s
 def test_every_launch_of_the_network_plans(dry, backbone, h, w, B, classify, bins):
     cfg = make_cfg(backbone, h, w, classify, bins)
     g, infos, n_dgrad, sparse = plan_network(dry, cfg, B)
-    assert sum(1 for k in infos if not k.startswith("d:")) == len(g.convs) and n_dgrad >= len(g.convs) // 2
+    assert sum(1 for k in infos if k[:2] not in ("d:", "w:")) == len(g.convs) and n_dgrad >= len(g.convs) // 2
 
 
 def test_bench_workload_gets_the_intended_modes(dry):
@@ -124,7 +129,14 @@ def test_bench_workload_gets_the_intended_modes(dry):
         assert infos[name]["halo"] == 1 and infos[name]["npipe"] == 2, (name, infos[name])
     for name in ("res3a_branch2b", "res3d_branch2b"):
         assert infos[name]["halo"] == 1 and infos[name]["bres"] == 0 and infos[name]["npipe"] == 2, (name, infos[name])
+    # Engine W: the stem and the 64 / 128-channel 3x3 weight gradients read all taps of a CTA from one box + halo per K step
+    for name in ("w:conv1", "w:res2a_branch2b", "w:res2b_branch2b", "w:res3a_branch2b", "w:res3d_branch2b"):
+        assert infos[name]["halo"] == 1 and infos[name]["stages"] >= 5, (name, infos[name])
+    assert infos["w:res2a_branch2b"]["units"] == 5 and infos["w:res2a_branch2b"]["groups"] == 1      # all 9 taps in one CTA
+    assert infos["w:res4b_branch2b"]["halo"] == 0 and infos["w:res5b_branch2b"]["halo"] == 0
     for name, i in infos.items():
+        if name.startswith("w:"):
+            continue
         if i["block_n"] == 256:
             assert i["npipe"] == 1, (name, i)
         assert i["npipe"] == 1 or i["block_n"] <= 128

@@ -98,6 +98,11 @@ struct ConvGemmParams {
                      // The epilogue then has no input stream at all (no ring, no unpack, no add).  One pipeline only
                      // (BLOCK_N = 256): producer warp 3 feeds the addend tiles through their own ring of kRaddStages
                      // (barriers: the halo mode's A-ring pair), producer warp 0 owns every operand round.
+                     // radd == 2 (K steps divide the 4 chunks: 2 or 4 K steps): no separate ring -- every operand stage also
+                     // carries radd_cps = 4 / ksteps addend chunks, consumed in the same barrier round (half the rounds
+                     // per tile, and the addend no longer sits serially behind the operand rounds).
+  int radd_cps, r_ring_off;
+  int radd_stages;   // radd == 1: slots of the addend ring (>= one tile = 4, more where shared memory is left over)
   int ident_off, radd_off;
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
-    } else if (p.radd && pw == 1) {
+    } else if (p.radd == 1 && pw == 1) {
       // addend ring (one pipeline): a whole tile's 64-channel chunks ahead of the MMA warp, which consumes them after the
       // tile's operand rounds
       int slot = 0;
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             load_a(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img, p.pol_a);
           }
           __syncwarp();
-          if (++slot == kRaddStages) {
+          if (++slot == p.radd_stages) {
             slot = 0;
             rphase ^= 1;
           }
@@ -390,7 +395,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     } else {
       // stream mode: a stage holds kpack K steps (A tile + B tile each); the owning producer arms the barrier once
       // with the bytes of the whole round and issues its tile loads
-      const bool own_all = npipe == 2 || p.radd != 0;      // (with an addend ring producer 0 issues every operand round)
+      const bool own_all = npipe == 2 || p.radd == 1;      // (with an addend ring producer 0 issues every operand round)
+      const int cps = p.radd == 2 ? p.radd_cps : 0;        // addend chunks riding in every operand stage
+      uint8_t* sR = pbase + p.r_ring_off;
       int stage = 0, gg = 0;
       uint32_t phase = 0;
       const int kp = p.kpack;
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
         if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         int kcol = 0, ks = 0, slot = 0;
+        const int rn_tile = (p.ncols - n_tile * BLOCK_N < BLOCK_N ? p.ncols - n_tile * BLOCK_N : BLOCK_N) >> 6;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
@@ -411,12 +419,20 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               if (elect_one()) {
                 if (slot == 0) {
                   const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
-                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes));
+                  int n_r = rn_tile - ks * cps;                                // valid addend chunks of this round
+                  n_r = n_r < 0 ? 0 : (n_r > cps ? cps : n_r);
+                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes) + n_r * kATileBytes);
                 }
                 load_a(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK, w0 + sg.dw,
                        h0 + sg.dh, img, p.pol_a);
                 if (pf_on) tma_prefetch_4d(&p.a_maps[sg.map_id], c * kBlockK, nx_w0 + sg.dw, nx_h0 + sg.dh, nx_img);
                 load_b(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N, p.pol_b);
+                for (int i = 0; i < cps; ++i) {
+                  const int r = ks * cps + i;
+                  if (r < rn_tile)
+                    load_a(sR + (stage * cps + i) * kATileBytes, &p.radd_map, &fullb[stage], n_tile * BLOCK_N + r * kBlockK, w0,
+                           h0, img, p.pol_a);
+                }
               }
               __syncwarp();
             }
@@ -518,6 +534,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int stage = 0, rslot = 0;
       uint32_t phase = 0, rphase = 0;
       const uint32_t radd_base = smem_u32(smem + p.radd_off);
+      const uint32_t r_base = a_base + p.r_ring_off;
+      const int cps = p.radd == 2 ? p.radd_cps : 0;
+      constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 64, 0, 0);
+      const uint64_t ident_d = kDescHiB | (smem_u32(smem + p.ident_off) >> 4);
       const int kp = p.kpack;
       const int ksteps = p.ksteps;
       int li = 0;
@@ -526,6 +546,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         mbar_wait(&temptyb[as], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (pipe * 2 + as) * BLOCK_N;
+        int rn_tile = 0;
+        if (cps) {
+          const int n0 = fdiv_ntile(p, wk) * BLOCK_N;
+          rn_tile = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
+        }
         for (int ks = 0; ks < ksteps; ks += kp) {
           const int n = ksteps - ks < kp ? ksteps - ks : kp;
           mbar_wait(&fullb[stage], phase);
@@ -538,6 +563,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
             }
+            for (int i = 0; i < cps; ++i) {      // D[:, 64r .. 64r+63] += addend chunk r x I (after this tile's first MMA)
+              const int r = ks * cps + i;
+              if (r < rn_tile) {
+                const uint64_t ad = kDescHiB | ((r_base + (stage * cps + i) * kATileBytes) >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d_tmem + r * 64, ad + 2 * k, ident_d + 2 * k, idesc64, 1u);
+              }
+            }
             umma_commit(&emptyb[stage]);   // one commit per barrier round
           }
           __syncwarp();
@@ -546,9 +579,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             phase ^= 1;
           }
         }
-        if (p.radd) {       // D[:, 64r .. 64r+63] += addend chunk r x I
-          constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 64, 0, 0);
-          const uint64_t bd = kDescHiB | (smem_u32(smem + p.ident_off) >> 4);
+        if (p.radd == 1) {       // D[:, 64r .. 64r+63] += addend chunk r x I
+          const uint64_t bd = ident_d;
           const int n0 = fdiv_ntile(p, wk) * BLOCK_N;
           const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
           for (int r = 0; r < rn; ++r) {
@@ -561,7 +593,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               umma_commit(&aempty_bar[rslot]);
             }
             __syncwarp();
-            if (++rslot == kRaddStages) {
+            if (++rslot == p.radd_stages) {
               rslot = 0;
               rphase ^= 1;
             }
@@ -985,11 +1017,12 @@ static int make_pix_map(CUtensorMap* out, const urso_pix& px, int C, int W, int 
 namespace {
 struct PipePlan {
   int npipe, stages, kpack, a_stages, bres;
-  int pipe_bytes, b_ring_off, bres_bytes;
+  int pipe_bytes, b_ring_off, bres_bytes, r_ring_off;
 };
 
-bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, long long tiles_per_cta, PipePlan* pl) {
-  const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2;
+bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, int r_step_bytes, long long tiles_per_cta,
+                 PipePlan* pl) {
+  const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2 + r_step_bytes;   // + addend chunks riding in the stage
   // preference order: two pipelines (hides the issue-side cost of a barrier round, the bound of the N <= 128 launches),
   // two K steps per round where the ring still gets >= 2 stages per pipeline
   const bool dual_ok = bn <= 128 && tiles_per_cta >= 2;
@@ -1008,6 +1041,7 @@ bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, long
     if (np == 2 && kp == 1 && stages < 3 && avail / step_bytes >= 3) continue;   // prefer one deeper ring over two shallow ones
     pl->npipe = np; pl->kpack = kp; pl->stages = stages; pl->a_stages = 0; pl->bres = 0; pl->bres_bytes = 0;
     pl->b_ring_off = stages * kp * urso::kATileBytes;
+    pl->r_ring_off = stages * kp * (urso::kATileBytes + bn * urso::kBlockK * 2);
     pl->pipe_bytes = stages * kp * step_bytes;
     return true;
   }
@@ -1101,6 +1135,9 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   // pipeline (BLOCK_N = 256), short K loops -- the store-bound launches, whose epilogue warps are the bottleneck.  (With
   // >= 8 K steps the third operand stage that the addend ring displaces is worth more: res5x_2c 54 -> 67 us measured.)
   p.radd = (residual_mma_enabled() && d->addend.ptr != nullptr && p.epi_tma && !d->halo && bn == 256 && ksteps <= 4) ? 1 : 0;
+  // 2 or 4 K steps: the addend chunks ride in the operand stages (radd == 2) instead of a ring of their own
+  if (p.radd && residual_mma_mode() >= 2 && (ksteps == 2 || ksteps == 4) && d->b_rows % 256 == 0) p.radd = 2;
+  p.radd_cps = p.radd == 2 ? 4 / ksteps : 0;
   p.shift_bytes = (p.epi_tma && d->shift != nullptr) ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
   const int kColAcc = kColAccOnly + p.shift_bytes;     // everything between the control block and the epilogue rings
   if ((d->relu_bits.ptr != nullptr || d->mask_bits.ptr != nullptr) && !p.epi_tma) {
@@ -1117,7 +1154,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   for (const int bn_asked = bn;; p.radd = 0, bn = bn_asked) {       // second pass: the addend ring did not fit
     p.has_add = d->addend.ptr != nullptr && !p.radd;
     n_in = p.has_add + p.has_mask;
-    radd_bytes = p.radd ? 8192 + kRaddStages * kATileBytes : 0;     // identity tile + addend ring
+    radd_bytes = p.radd == 1 ? 8192 + kRaddStages * kATileBytes : (p.radd == 2 ? 8192 : 0);   // identity tile (+ addend ring)
+    const int r_step = p.radd_cps * kATileBytes;
     if (p.epi_tma) {
       // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight).
       // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to the operand pipelines.  Launches
@@ -1126,7 +1164,8 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       const bool heavy = ksteps >= 4;
       const bool epi_bound = ksteps <= 6;
       p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
-      p.eo_depth = (heavy || n_in == 2 || p.radd) ? 1 : 2;
+      p.eo_depth = (heavy || n_in == 2 || p.radd == 1) ? 1 : 2;
+      if (p.radd == 2) p.eo_depth = 2;      // store-bound launches: two output slabs per warp where they fit (checked below)
       if (n_in > 0 && epi_bound) p.ei_depth = 2;
       epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
       const int room = kSmemBudget - kCtrlBytes - kColAcc - radd_bytes;
@@ -1136,11 +1175,16 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
         epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
       }
       const int min_stages = ((n_in > 0 && epi_bound) || p.radd) ? 2 : 3;
-      if (bn == 256 && room - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
+      if (p.radd == 2 && p.eo_depth == 2 && room - epi_bytes < 2 * (kATileBytes + 256 * kBlockK * 2 + r_step)) {
+        p.eo_depth = 1;
+        epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
+      }
+      if (bn == 256 && room - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2 + r_step)) bn = 128;
     } else {
       epi_bytes = kLegacyScratchBytes;
     }
     if (!p.radd || bn == 256) break;
+    p.radd_cps = 0;
   }
   h->block_n = bn;
   p.n_tiles_n = (d->b_rows + bn - 1) / bn;
@@ -1157,7 +1201,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   if (sms <= 0) sms = 148;
   h->grid = p.total_tiles < sms ? p.total_tiles : sms;
   const long long tiles_per_cta = (total + h->grid - 1) / h->grid;
-  PipePlan pl;
+  PipePlan pl = {};
   bool planned = false;
   int halo_w = 0, halo_h = 0, dw_min = 0, dh_min = 0;
   if (d->halo) {
@@ -1202,7 +1246,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
         continue;
       }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
     }
-    planned = plan_stream(avail, bn, ksteps, n_in > 0, p.radd != 0, tiles_per_cta, &pl);
+    planned = plan_stream(avail, bn, ksteps, n_in > 0, p.radd != 0, p.radd_cps * kATileBytes, tiles_per_cta, &pl);
   }
   if (!planned) {
     set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
@@ -1222,10 +1266,21 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.bres = pl.bres;
   p.pipe_bytes = pl.pipe_bytes;
   p.b_ring_off = pl.b_ring_off;
+  p.r_ring_off = pl.r_ring_off;
   p.bres_off = pl.npipe * pl.pipe_bytes;
   p.ident_off = p.bres_off + pl.bres_bytes;
   p.radd_off = p.ident_off + (p.radd ? 8192 : 0);
-  p.ctrl_off = p.radd_off + (p.radd ? kRaddStages * kATileBytes : 0);
+  p.radd_stages = kRaddStages;
+  if (p.radd == 1 && radd_deep()) {
+    // shared memory the operand ring could not use (less than one more stage) goes to the addend ring: these launches
+    // are bound by the bytes they keep in flight (measured: time follows ring bytes), so every 16 KB slot counts
+    const int used = p.radd_off + kRaddStages * kATileBytes + (kCtrlBytes + kColAcc + 1023) / 1024 * 1024 + epi_bytes;
+    int extra = (kSmemBudget - used) / kATileBytes;
+    if (extra < 0) extra = 0;
+    if (extra > 8 - kRaddStages) extra = 8 - kRaddStages;       // afull / aempty barrier arrays hold 8
+    p.radd_stages = kRaddStages + extra;
+  }
+  p.ctrl_off = p.radd_off + (p.radd == 1 ? p.radd_stages * kATileBytes : 0);
   const int fixed = p.ctrl_off + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
@@ -1305,5 +1360,14 @@ extern "C" int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9) 
   const urso::ConvGemmParams& p = h->params;
   const int32_t v[9] = {h->block_n, p.npipe, p.stages, p.kpack, p.halo, p.bres, p.a_stages, h->smem_bytes, h->grid};
   for (int i = 0; i < 9; ++i) out9[i] = v[i];
+  return 0;
+}
+
+/* more plan introspection: writes {radd mode, addend chunks per stage, ei_depth, eo_depth, tile order reversed, L2 prefetch} */
+extern "C" int urso_convgemm_plan_extra(const urso_convgemm_t* h, int32_t* out6) {
+  URSO_REQUIRE(h != nullptr && out6 != nullptr, "null argument");
+  const urso::ConvGemmParams& p = h->params;
+  const int32_t v[6] = {p.radd, p.radd == 1 ? p.radd_stages : p.radd_cps, p.ei_depth, p.eo_depth, p.rev, p.l2pf};
+  for (int i = 0; i < 6; ++i) out6[i] = v[i];
   return 0;
 }

@@ -72,6 +72,16 @@ bool halo_patch_ok(int oh, int ow) {
   return halo * 100 <= best * 107;
 }
 
+// Engine W's halo mode wants 8 x 8 pixel blocks; take them when they cover the map with at most 7 % more pixels than the
+// best 64-pixel patch would.
+bool wgrad_block8_ok(int oh, int ow) {
+  int tw, th;
+  pick_patch(oh, ow, 64, &tw, &th);
+  const long long best = (long long)((ow + tw - 1) / tw) * tw * ((oh + th - 1) / th) * th;
+  const long long b8 = (long long)((ow + 7) / 8) * 8 * ((oh + 7) / 8) * 8;
+  return b8 * 100 <= best * 107;
+}
+
 struct Tap {
   int tap, map, dh, dw;
 };
@@ -309,6 +319,10 @@ extern "C" int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* out_)
 extern "C" int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_plan_info(h->plan, out9);
+}
+extern "C" int urso_conv2d_fwd_plan_extra(const urso_conv2d_fwd_t* h, int32_t* out6) {
+  URSO_REQUIRE(h != nullptr, "null handle");
+  return urso_convgemm_plan_extra(h->plan, out6);
 }
 extern "C" void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h) {
   if (h == nullptr) return;
@@ -564,6 +578,7 @@ extern "C" int urso_conv2d_wgrad_create(const urso_conv2d_wgrad_desc* d, urso_co
     wd.q = dense_view(d->dy, s.N, g.oh, g.ow, ceil64(s.K));
     wd.PC = 64; wd.QC = s.K; wd.OW = g.ow; wd.OH = g.oh; wd.NB = s.N;
     pick_patch(g.oh, g.ow, 64, &wd.TW, &wd.TH);
+    if (urso::wgrad_halo_enabled() && wgrad_block8_ok(g.oh, g.ow)) wd.TW = wd.TH = 8;     // the 4 row taps read one 8 x 11 box
     wd.g_seg_stride = (int64_t)64 * s.K; wd.g_sp = s.K; wd.g_sq = 1;
   } else {
     URSO_REQUIRE(s.C % 64 == 0, "input channels %d must be a multiple of 64", s.C);
@@ -603,6 +618,7 @@ extern "C" int urso_conv2d_wgrad_create(const urso_conv2d_wgrad_desc* d, urso_co
       wd.q = d->dy_sparse ? strided_view(d->dy, s.N, g.oh, g.ow, kc, 0, 0, 2) : dense_view(d->dy, s.N, g.oh, g.ow, kc);
       wd.PC = s.C; wd.QC = s.K; wd.OW = ge.ow; wd.OH = ge.oh; wd.NB = s.N;
       pick_patch(ge.oh, ge.ow, 64, &wd.TW, &wd.TH);
+      if (urso::wgrad_halo_enabled() && ge.stride == 1 && wd.n_seg >= 2 && wgrad_block8_ok(ge.oh, ge.ow)) wd.TW = wd.TH = 8;
       wd.g_seg_stride = (int64_t)s.C * s.K; wd.g_sp = s.K; wd.g_sq = 1;
     }
   }
@@ -617,6 +633,10 @@ extern "C" int urso_conv2d_wgrad_create(const urso_conv2d_wgrad_desc* d, urso_co
 extern "C" int urso_conv2d_wgrad_launch(urso_conv2d_wgrad_t* h, void* stream) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_wgrad_launch(h->plan, stream);
+}
+extern "C" int urso_conv2d_wgrad_plan_info(const urso_conv2d_wgrad_t* h, int32_t* out10) {
+  URSO_REQUIRE(h != nullptr, "null handle");
+  return urso_wgrad_plan_info(h->plan, out10);
 }
 extern "C" void urso_conv2d_wgrad_destroy(urso_conv2d_wgrad_t* h) {
   if (h == nullptr) return;

@@ -10,6 +10,12 @@
 // One CTA owns a 128-channel P tile x BLOCK_Q-channel Q tile for up to T filter taps (T*BLOCK_Q <= 512 TMEM columns,
 // all taps reuse the single Q tile per K step) over a contiguous range of pixel blocks (split-K); results are
 // reduced into the fp32 gradient with atomics.
+// HALO MODE (several filter taps on one stride-1 view, 8 x 8 pixel blocks): the tap-shifted P operands of a CTA's taps are
+// overlapping windows of ONE box per 64-channel atom (block + halo, e.g. 10 x 10 pixels for a 3x3 filter) instead of one
+// 8 KB atom per tap: the MN-major descriptor of tap (dh, dw) starts (dh * halo_w + dw) pixel rows into the box, its
+// 8-pixel groups are halo_w rows apart (SBO) -- UMMA descriptors swizzle on absolute shared-memory address bits, so a
+// start shifted by whole 128-byte rows reads what TMA wrote (the trick of Engine F's halo mode).  The 64-channel 3x3
+// layers go from 88 KB to 21 KB per K step (94 -> 22 B/clk of operand supply, against ~67 B/clk the SM can ingest).
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -23,12 +29,14 @@ struct WSegDev {
 struct WgradParams {
   CUtensorMap p_maps[URSO_MAX_AMAPS];
   CUtensorMap q_map;
+  CUtensorMap p_halo_map;   // halo mode: box {64, halo_w, halo_h, 1} of view 0
   WSegDev seg[URSO_MAX_SEGS];
   int n_seg, taps_per_cta, n_seg_groups;
   int order;       // work-item decode order (see kernel)
   int interleave;  // split s takes pixel blocks s, s + split_k, ... instead of one contiguous range: all CTAs then walk the
                    // tensor front to back together, like Engine F's round-robin tiles (an L2-sharing pair needs that)
   int pair_mode;   // PC <= 64: the two 64-row halves of the MMA M dimension carry two different filter taps
+  int halo, halo_w, halo_box_bytes, halo_tx_bytes;   // box pitch in the stage (1 KB multiple) / bytes one box load delivers
   int PC, QC;
   int p_tiles, q_tiles;
   int tiles_w, tiles_h, TW, TH;
@@ -79,6 +87,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   const int n_units = p.pair_mode ? (p.n_seg + 1) / 2 : p.n_seg;
   const int seg0 = seg_group * p.taps_per_cta;
   const int T = min(p.taps_per_cta, n_units - seg0);
+  // halo mode: origin of this CTA's box = the smallest tap offsets of its group
+  int hdh = 0, hdw = 0;
+  if (p.halo) {
+    const int t_first = p.pair_mode ? 2 * seg0 : seg0;
+    const int t_last = min(p.pair_mode ? 2 * (seg0 + T) : seg0 + T, p.n_seg);
+    hdh = hdw = 1 << 20;
+    for (int t = t_first; t < t_last; ++t) {
+      hdh = min(hdh, (int)p.seg[t].dh);
+      hdw = min(hdw, (int)p.seg[t].dw);
+    }
+  }
   // my pixel blocks: kb = kb_begin + i * kb_step, i < kb_count
   const int kb_step = p.interleave ? p.split_k : 1;
   const int kb_begin = p.interleave ? split : (int)((long long)p.n_pix_blocks * split / p.split_k);
@@ -88,6 +107,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < URSO_MAX_AMAPS; ++i) tma_prefetch_desc(&p.p_maps[i]);
     tma_prefetch_desc(&p.q_map);
+    if (p.halo) tma_prefetch_desc(&p.p_halo_map);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -113,7 +133,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     const int par = warp == 0 ? 0 : 1;
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t bytes = (QA + 2 * T) * kAtomBytes;
+    const int n_pa = p.pair_mode ? 1 : 2;      // 64-channel atoms of the P tile
+    const uint32_t bytes = p.halo ? QA * kAtomBytes + n_pa * p.halo_tx_bytes : (QA + 2 * T) * kAtomBytes;
     for (int i = 0; i < kb_count; ++i) {
       const int kb = kb_begin + i * kb_step;
       if ((i & 1) == par) {
@@ -130,8 +151,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
           for (int a = 0; a < QA; ++a)
             tma_load_4d(base + a * kAtomBytes, &p.q_map, &full_bar[stage], q_tile * BLOCK_Q + a * 64, w0, h0, img);
           uint8_t* pbase = base + QA * kAtomBytes;
+          if (p.halo) {
+            for (int a = 0; a < n_pa; ++a)
+              tma_load_4d(pbase + a * p.halo_box_bytes, &p.p_halo_map, &full_bar[stage],
+                          (p.pair_mode ? 0 : p_tile * 128) + a * 64, w0 + hdw, h0 + hdh, img);
+          }
 #pragma unroll 1
-          for (int t = 0; t < T; ++t) {
+          for (int t = 0; t < (p.halo ? 0 : T); ++t) {
             if (p.pair_mode) {
               const int ta = 2 * (seg0 + t), tb = min(ta + 1, p.n_seg - 1);   // odd tap count: the last atom repeats a tap
               const WSegDev sa = p.seg[ta], sb = p.seg[tb];
@@ -160,6 +186,28 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     // MN-major SW128 descriptor: LBO = distance between 64-channel atoms (8 KB), SBO = 1 KB between 8-pixel groups
     constexpr uint64_t kDescHi = (uint64_t(1024 >> 4) << 32) | (uint64_t(kAtomBytes >> 4) << 16) | (1ull << 46) | (2ull << 61);
     const uint32_t s_base = smem_u32(smem);
+    // halo mode: per unit the window's byte offset into the box and the LBO of its descriptor (the second 64-row atom of M
+    // is the next 64 channels = the next box, or -- pair mode -- the unit's second tap = another window of the same box)
+    uint32_t h_off[8], h_lbo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      h_off[t] = h_lbo[t] = 0;
+      if (p.halo && t < T) {
+        if (p.pair_mode) {
+          const int ta = 2 * (seg0 + t), tb = min(ta + 1, p.n_seg - 1);
+          const uint32_t oa = (uint32_t)(((int)p.seg[ta].dh - hdh) * p.halo_w + ((int)p.seg[ta].dw - hdw)) * 128u;
+          const uint32_t ob = (uint32_t)(((int)p.seg[tb].dh - hdh) * p.halo_w + ((int)p.seg[tb].dw - hdw)) * 128u;
+          h_off[t] = oa;
+          h_lbo[t] = ob - oa;      // taps are listed row-major: ob >= oa
+        } else {
+          const WSegDev sg = p.seg[seg0 + t];
+          h_off[t] = (uint32_t)(((int)sg.dh - hdh) * p.halo_w + ((int)sg.dw - hdw)) * 128u;
+          h_lbo[t] = (uint32_t)p.halo_box_bytes;
+        }
+      }
+    }
+    const uint32_t h_kadv = (uint32_t)p.halo_w * 16u;     // 16 pixels = 2 block rows = 2 * halo_w box rows of 128 B, in 16-byte units
+    const uint64_t h_sbo = uint64_t((uint32_t)p.halo_w * 128u >> 4) << 32;
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < kb_count; ++i) {
@@ -169,8 +217,22 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         const uint32_t q_addr = s_base + stage * p.stage_bytes;
         const uint64_t bd = kDescHi | (q_addr >> 4);
         const uint32_t first = i > 0;
+        if (p.halo) {
+          const uint32_t pbox = q_addr + QA * kAtomBytes;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            if (t < T) {
+              const uint64_t ad = h_sbo | (uint64_t(h_lbo[t] >> 4) << 16) | (1ull << 46) | (2ull << 61) | ((pbox + h_off[t]) >> 4);
+              const uint32_t d = tmem_base + t * BLOCK_Q;
+              umma_bf16(d, ad, bd, idesc, first);
+              umma_bf16(d, ad + h_kadv, bd + 128, idesc, 1u);
+              umma_bf16(d, ad + 2 * h_kadv, bd + 256, idesc, 1u);
+              umma_bf16(d, ad + 3 * h_kadv, bd + 384, idesc, 1u);
+            }
+          }
+        }
 #pragma unroll 1
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < (p.halo ? 0 : T); ++t) {
           const uint64_t ad = kDescHi | ((q_addr + (QA + 2 * t) * kAtomBytes) >> 4);
           const uint32_t d = tmem_base + t * BLOCK_Q;
           // 64 pixels = 4 x UMMA_K(16); 16 pixels = two 8-pixel groups = 2 KB -> +128 in descriptor units
@@ -328,12 +390,60 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
   p.pair_mode = (d->PC <= 64 && d->n_seg >= 2) ? 1 : 0;
   const int n_units = p.pair_mode ? (d->n_seg + 1) / 2 : d->n_seg;
   int tmax = 512 / bq;
-  // smem: each stage holds the Q tile + 2 atoms per unit; keep at least 3 stages
   const int qa = bq / 64;
-  while (tmax > 1 && (qa + 2 * tmax) * kAtomBytes * 3 > 200 * 1024) --tmax;
-  // balanced groups: e.g. 9 taps with room for 4 per CTA -> 3 + 3 + 3 instead of 4 + 4 + 1
-  p.n_seg_groups = (n_units + tmax - 1) / tmax;
-  p.taps_per_cta = (n_units + p.n_seg_groups - 1) / p.n_seg_groups;
+  // ---- halo mode: every tap on one stride-1 view, 8 x 8 pixel blocks.  The units of a CTA are then limited by tensor
+  // memory only (the stage holds one box per P atom, not two atoms per unit); taken when the boxes are < 70 % of the bytes.
+  p.halo = 0;
+  bool one_view = d->n_seg >= 2 && d->TW == 8 && d->TH == 8 && wgrad_halo_enabled();
+  for (int s2 = 1; s2 < d->n_seg && one_view; ++s2) one_view = d->seg[s2].map_id == d->seg[0].map_id;
+  if (one_view) {
+    const int t_units = tmax > 8 ? 8 : tmax;          // the kernel unrolls at most 8 units
+    const int groups = (n_units + t_units - 1) / t_units;
+    const int per = (n_units + groups - 1) / groups;
+    int span_w = 0, span_h = 0;
+    for (int g0 = 0; g0 < groups; ++g0) {
+      const int first = (p.pair_mode ? 2 : 1) * g0 * per;
+      int last = (p.pair_mode ? 2 : 1) * (g0 + 1) * per;
+      if (last > d->n_seg) last = d->n_seg;
+      int lo_w = 1 << 20, hi_w = -(1 << 20), lo_h = 1 << 20, hi_h = -(1 << 20);
+      for (int t = first; t < last; ++t) {
+        lo_w = d->seg[t].dw < lo_w ? d->seg[t].dw : lo_w; hi_w = d->seg[t].dw > hi_w ? d->seg[t].dw : hi_w;
+        lo_h = d->seg[t].dh < lo_h ? d->seg[t].dh : lo_h; hi_h = d->seg[t].dh > hi_h ? d->seg[t].dh : hi_h;
+      }
+      if (last > first) {
+        span_w = hi_w - lo_w > span_w ? hi_w - lo_w : span_w;
+        span_h = hi_h - lo_h > span_h ? hi_h - lo_h : span_h;
+      }
+    }
+    // taps must be listed in row-major (dh, dw) order: pair mode takes LBO = offset(second tap) - offset(first tap) >= 0
+    bool ordered = true;
+    for (int t = 1; t < d->n_seg && ordered; ++t)
+      ordered = d->seg[t].dh > d->seg[t - 1].dh || (d->seg[t].dh == d->seg[t - 1].dh && d->seg[t].dw >= d->seg[t - 1].dw);
+    const int hw = 8 + span_w, hh = 8 + span_h;
+    const int box = hw * hh * 128, box_pad = (box + 1023) / 1024 * 1024;
+    const int n_pa = p.pair_mode ? 1 : 2;
+    if (ordered && span_w <= 8 && span_h <= 8 && n_pa * box_pad * 10 < 2 * per * kAtomBytes * 7) {
+      p.halo = 1;
+      p.halo_w = hw;
+      p.halo_box_bytes = box_pad;
+      p.halo_tx_bytes = box;
+      p.n_seg_groups = groups;
+      p.taps_per_cta = per;
+      p.stage_bytes = qa * kAtomBytes + n_pa * box_pad;
+      if (int rc = make_view_map(&p.p_halo_map, d->p[d->seg[0].map_id], hw, hh)) {
+        delete h;
+        return rc;
+      }
+    }
+  }
+  if (!p.halo) {
+    // smem: each stage holds the Q tile + 2 atoms per unit; keep at least 3 stages
+    while (tmax > 1 && (qa + 2 * tmax) * kAtomBytes * 3 > 200 * 1024) --tmax;
+    // balanced groups: e.g. 9 taps with room for 4 per CTA -> 3 + 3 + 3 instead of 4 + 4 + 1
+    p.n_seg_groups = (n_units + tmax - 1) / tmax;
+    p.taps_per_cta = (n_units + p.n_seg_groups - 1) / p.n_seg_groups;
+    p.stage_bytes = (qa + 2 * p.taps_per_cta) * kAtomBytes;
+  }
   p.PC = d->PC;
   p.QC = d->QC;
   p.p_tiles = (d->PC + 127) / 128;
@@ -349,7 +459,6 @@ extern "C" int urso_wgrad_create(const urso_wgrad_desc* d, urso_wgrad_t** out) {
     return 2;
   }
   p.n_pix_blocks = (int)nblk;
-  p.stage_bytes = (qa + 2 * p.taps_per_cta) * kAtomBytes;
   p.stages = (200 * 1024) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
   int cols = p.taps_per_cta * bq;
@@ -403,3 +512,13 @@ extern "C" int urso_wgrad_launch(urso_wgrad_t* h, void* stream) {
 }
 
 extern "C" void urso_wgrad_destroy(urso_wgrad_t* h) { delete h; }
+
+/* plan introspection: writes {block_q, halo, halo_w, stages, stage_bytes, units per CTA, tap groups, split_k, grid, pair_mode} */
+extern "C" int urso_wgrad_plan_info(const urso_wgrad_t* h, int32_t* out10) {
+  URSO_REQUIRE(h != nullptr && out10 != nullptr, "null argument");
+  const urso::WgradParams& p = h->params;
+  const int32_t v[10] = {h->block_q, p.halo, p.halo_w, p.stages, p.stage_bytes, p.taps_per_cta, p.n_seg_groups, p.split_k,
+                         h->grid, p.pair_mode};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return 0;
+}
