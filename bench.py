@@ -155,13 +155,8 @@ def main():
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="with --overlap: SMs the second backward segment leaves free for NCCL's all-reduce kernel")
     ap.add_argument("--no-residual-mma", action="store_true", help="A/B: residual / fan-in addends added by the epilogue warps instead of the tensor core")
-    ap.add_argument("--residual-mma", type=int, default=-1, help="A/B: urso_set_residual_mma mode (0 epilogue, 1 addend ring, 2 addend chunks in the operand stages)")
     ap.add_argument("--stage-split", type=int, default=4, help="A/B: leading convs whose weight operands get their own staging launch")
     ap.add_argument("--pair-l2", action="store_true", help="A/B: co-run the dgrad / wgrad launches that share a large gradient tensor")
-    ap.add_argument("--zigzag", type=int, default=0, help="A/B: alternate the tile order of consecutive conv launches (bit 0 forward, bit 1 gradient chain)")
-    ap.add_argument("--l2-hints", type=int, default=0, help="A/B: L2 eviction hints of the operand loads (bits 0-1 forward, bits 2-3 gradient chain)")
-    ap.add_argument("--l2-prefetch", type=int, default=0, help="A/B: producers prefetch the next tile into L2 (bit 0 forward, bit 1 gradient chain)")
-    ap.add_argument("--deep-addend-ring", action="store_true", help="A/B: left-over shared memory deepens the addend ring (urso_set_addend_ring_deep(1))")
     ap.add_argument("--no-wgrad-halo", action="store_true", help="A/B: Engine W loads one operand atom per filter tap (urso_set_wgrad_halo(0))")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -200,12 +195,8 @@ def main():
         _lib.load().urso_set_pdl(0)
     if args.no_residual_mma:
         _lib.load().urso_set_residual_mma(0)
-    if args.deep_addend_ring:
-        _lib.load().urso_set_addend_ring_deep(1)
     if args.no_wgrad_halo:
         _lib.load().urso_set_wgrad_halo(0)
-    if args.residual_mma >= 0:
-        _lib.load().urso_set_residual_mma(args.residual_mma)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -217,8 +208,7 @@ def main():
         n_micro = per_rank // args.batch
         workload += f", global batch {args.global_batch} = {world} ranks x {n_micro} micro-batches x {args.batch}"
     eng = Engine(cfg, args.batch, training=True, world_size=world, seed=0,
-                 reserve_sms=args.reserve_sms if (world > 1 and args.overlap) else 0, pair_l2=args.pair_l2, stage_split=args.stage_split,
-                 zigzag=args.zigzag, l2_hints=args.l2_hints, l2_prefetch=args.l2_prefetch)
+                 reserve_sms=args.reserve_sms if (world > 1 and args.overlap) else 0, pair_l2=args.pair_l2, stage_split=args.stage_split)
     img, loc, ori = synth_batch(cfg, args.batch, seed=rank)
     h_img, h_loc, h_ori = img.pin_memory(), loc.pin_memory(), ori.pin_memory()
     eng.img_u8.copy_(h_img)

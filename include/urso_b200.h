@@ -35,25 +35,8 @@ void urso_set_dry_run(int on);
 void urso_set_pdl(int on);
 /* Engine F launches planned while this is on (default) accumulate their addend (residual / gradient fan-in) on the tensor
  * core -- per 64-channel chunk one extra K step "addend tile x 64x64 identity" into the chunk's TMEM columns -- instead of
- * loading, unpacking and adding it in the epilogue warps; bit-exact products, fp32 accumulation.  0 = epilogue add,
- * 1 (default) = through a dedicated ring of addend tiles, 2 = launches with 2 or 4 K steps carry the addend chunks inside
- * their operand stages instead (half the barrier rounds per tile, but fewer bytes in flight: measured slower). */
+ * loading, unpacking and adding it in the epilogue warps; bit-exact products, fp32 accumulation.  0 = epilogue add. */
 void urso_set_residual_mma(int on);
-/* Tile order of the Engine-F launches planned from now on: 1 = the persistent CTAs walk the output tiles in DESCENDING
- * order.  A host that alternates the order from one launch of a dependent chain to the next makes every launch start on
- * the pixels its producer wrote LAST -- the part of that tensor still resident in the 126 MB L2.  Results are identical. */
-void urso_set_tile_reverse(int on);
-/* L2 eviction-priority hints on the operand loads of the Engine-F launches planned from now on (default 0 = none):
- * bit 0: activation and addend tiles evict_first (streamed once; they must not displace the freshly written output),
- * bit 1: weight tiles evict_last (re-read by every CTA). */
-void urso_set_l2_hints(int mask);
-/* Engine-F launches planned while on: the TMA producers also issue cp.async.bulk.prefetch.tensor (L2 only) for the
- * activation / addend tiles of the CTA's NEXT output tile, so that DRAM latency is not bounded by the depth of the
- * shared-memory ring (2-4 stages on the launches with large epilogue rings).  Scheduling only; results are identical. */
-void urso_set_l2_prefetch(int on);
-/* Addend ring of the tensor-core addend mode (urso_set_residual_mma(1)): 1 = shared memory the operand ring cannot use goes
- * to extra ring slots (4 = one tile .. 8), 0 (default) = always 4 slots (measured: no difference). */
-void urso_set_addend_ring_deep(int on);
 /* Engine W halo mode (default on): weight-gradient launches of multi-tap filters on one stride-1 view (3x3 convolutions, the
  * stem's four row taps) load ONE 8x8-pixel block + halo per 64-channel atom and K step and address every tap as a shifted
  * window of it, instead of one operand atom per tap.  0 = one atom per tap (A/B). */
@@ -128,10 +111,6 @@ int urso_convgemm_launch(urso_convgemm_t* h, void* stream);
 void urso_convgemm_destroy(urso_convgemm_t* h);
 /* plan introspection (tests / profiling): out9 = {block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid} */
 int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9);
-/* writes {addend mode (0 epilogue, 1 tensor core via its own ring, 2 riding in the operand stages), ring slots (mode 1) or
- * addend chunks per stage (mode 2),
- * epilogue input ring depth, output slabs per warp, tile order reversed, next-tile L2 prefetch} */
-int urso_convgemm_plan_extra(const urso_convgemm_t* h, int32_t* out6);
 
 /* ---- Engine W: weight-gradient GEMM on tcgen05 (replaces Conv2DBackpropFilter of TF autodiff).
  *   G[t][p, q] (+)= sum_pixels  P_t[pixel + (dh_t,dw_t), p] * Q[pixel, q]        t = 0..n_seg-1
@@ -207,7 +186,6 @@ int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream);
 int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream);
 void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h);
 int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9); /* see urso_convgemm_plan_info */
-int urso_conv2d_fwd_plan_extra(const urso_conv2d_fwd_t* h, int32_t* out6); /* see urso_convgemm_plan_extra */
 /* the staging work of this operator as a job of urso_stage_weights_multi (declared below) */
 int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* stage_job_out);
 

@@ -9,38 +9,28 @@ import torch
 from oracle import ursonet_oracle as O
 
 pytestmark = pytest.mark.gpu
-DEFAULT_RESIDUAL_MMA = 1      # the library's default (urso_set_residual_mma)
 DEV = "cuda"
 
 
-@pytest.fixture(params=[(0, 0, 0), (3, 0, 0), (3, 1, 3)], autouse=True, ids=["all_sms", "3_ctas", "3_ctas_reversed_l2hints"])
+@pytest.fixture(params=[0, 3], autouse=True, ids=["all_sms", "3_ctas"])
 def cta_limit(request):
     """Every case also runs with the persistent grids limited to 3 CTAs (urso_set_max_ctas): each CTA then works through a
     long queue of tiles, so the two operand pipelines, their ring wrap-arounds and the accumulator-stage phase flips are
-    exercised even at these small shapes.  Third variant: tiles walked in descending order (urso_set_tile_reverse) and the
-    operand loads carrying L2 eviction hints (urso_set_l2_hints), next-tile L2 prefetch on (urso_set_l2_prefetch) -- results
-    must not change."""
+    exercised even at these small shapes."""
     from ursonet_b200 import lib
-    n, rev, hints = request.param
-    lib.load().urso_set_max_ctas(n)
-    lib.load().urso_set_tile_reverse(rev)
-    lib.load().urso_set_l2_hints(hints)
-    lib.load().urso_set_l2_prefetch(rev)
+    lib.load().urso_set_max_ctas(request.param)
     yield
     lib.load().urso_set_max_ctas(0)
-    lib.load().urso_set_tile_reverse(0)
-    lib.load().urso_set_l2_hints(0)
-    lib.load().urso_set_l2_prefetch(0)
 
 
-@pytest.fixture(params=[2, 1, 0], ids=["addend_mma_in_stage", "addend_mma_ring", "addend_epilogue"])
+@pytest.fixture(params=[1, 0], ids=["addend_mma", "addend_epilogue"])
 def residual_mma(request):
     """Launches with an addend run both ways: accumulated on the tensor core as an extra identity K step (default), or
     loaded and added by the epilogue warps (urso_set_residual_mma)."""
     from ursonet_b200 import lib
     lib.load().urso_set_residual_mma(request.param)
     yield request.param
-    lib.load().urso_set_residual_mma(DEFAULT_RESIDUAL_MMA)
+    lib.load().urso_set_residual_mma(1)
 
 
 def bf16_exact(*shape, scale=1.0, seed=0):

@@ -9,7 +9,6 @@ from tests import emulator as E
 from ursonet_b200 import convplan as P
 
 pytestmark = pytest.mark.gpu
-DEFAULT_RESIDUAL_MMA = 1      # the library's default (urso_set_residual_mma)
 DEV = "cuda"
 
 
@@ -24,14 +23,14 @@ def cta_limit(request):
     lib.load().urso_set_max_ctas(0)
 
 
-@pytest.fixture(params=[2, 1, 0], ids=["addend_mma_in_stage", "addend_mma_ring", "addend_epilogue"])
+@pytest.fixture(params=[1, 0], ids=["addend_mma", "addend_epilogue"])
 def residual_mma(request):
     """Launches with an addend run both ways: accumulated on the tensor core as an extra identity K step (default), or
     loaded and added by the epilogue warps (urso_set_residual_mma)."""
     from ursonet_b200 import lib
     lib.load().urso_set_residual_mma(request.param)
     yield request.param
-    lib.load().urso_set_residual_mma(DEFAULT_RESIDUAL_MMA)
+    lib.load().urso_set_residual_mma(1)
 
 
 def bf16_exact(*shape, scale=1.0, seed=0):

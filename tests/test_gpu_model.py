@@ -291,29 +291,3 @@ def test_split_backward_for_overlapped_allreduce(use_graph):
     # amplifies that noise) only have to agree loosely -- a double-counted accumulation would be off by far more
     assert (p0 - p1).abs().max().item() <= 2e-6 * p0.abs().max().item() + 1e-7
     assert torch.allclose(l0, l1, rtol=3e-2, atol=1e-3)
-
-
-def test_zigzag_tile_order_and_l2_hints_leave_results_bit_identical():
-    """Engine(zigzag=3, l2_hints=15, l2_prefetch=3): consecutive conv launches walk their tiles in opposite directions and their operand
-    loads carry L2 eviction hints -- scheduling only.  Every activation and every activation gradient must be bit-identical
-    to the default engine's (those launches contain no atomics on the tensors compared)."""
-    from ursonet_b200.engine import Engine
-    cfg = make_cfg("resnet50", True)
-    B = 2
-    p64 = O.init_weights(cfg, seed=2, pretrained_like=True)
-    img, gt_loc, gt_ori = make_batch(cfg, B, seed=3)
-    engs = []
-    for kw in (dict(), dict(zigzag=3, l2_hints=15, l2_prefetch=3)):
-        eng = Engine(cfg, B, training=True, **kw)
-        load_oracle_weights(eng, p64)
-        eng.img_u8.copy_(img)
-        eng.gt_loc.copy_(gt_loc)
-        eng.gt_ori.copy_(gt_ori)
-        eng._phase_train()
-        torch.cuda.synchronize()
-        engs.append(eng)
-    a, b = engs
-    for name in a.act:
-        assert torch.equal(a.act[name], b.act[name]), name
-    for name in a.dact:
-        assert torch.equal(a.dact[name], b.dact[name]), name

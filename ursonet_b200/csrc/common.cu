@@ -30,19 +30,10 @@ int num_sms() {
 
 static int g_pdl = 1;
 static int g_residual_mma = 1;
-static int g_tile_reverse = 0;
-static int g_l2_hints = 0;
-static int g_l2_prefetch = 0;
-static int g_radd_deep = 0;
 static int g_wgrad_halo = 1;
 bool pdl_enabled() { return g_pdl != 0; }
-bool tile_reverse() { return g_tile_reverse != 0; }
-int l2_hints() { return g_l2_hints; }
-bool l2_prefetch() { return g_l2_prefetch != 0; }
-bool radd_deep() { return g_radd_deep != 0; }
 bool wgrad_halo_enabled() { return g_wgrad_halo != 0; }
 bool residual_mma_enabled() { return g_residual_mma != 0; }
-int residual_mma_mode() { return g_residual_mma; }
 static int g_max_ctas = 0;
 bool dry_run() { return g_dry_run != 0; }
 int max_ctas() {
@@ -112,10 +103,6 @@ void urso_set_max_ctas(int n) { urso::g_max_ctas = n; }
 void urso_set_dry_run(int on) { urso::g_dry_run = on; }
 void urso_set_pdl(int on) { urso::g_pdl = on; }
 void urso_set_residual_mma(int on) { urso::g_residual_mma = on; }
-void urso_set_tile_reverse(int on) { urso::g_tile_reverse = on; }
-void urso_set_l2_hints(int mask) { urso::g_l2_hints = mask; }
-void urso_set_l2_prefetch(int on) { urso::g_l2_prefetch = on; }
-void urso_set_addend_ring_deep(int on) { urso::g_radd_deep = on; }
 void urso_set_wgrad_halo(int on) { urso::g_wgrad_halo = on; }
 int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
 int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }

@@ -14,11 +14,6 @@ void set_error(const char* fmt, ...);
 int num_sms();
 bool pdl_enabled();   // urso_set_pdl: launch the tcgen05 engines with programmatic stream serialization (default on)
 bool residual_mma_enabled();   // urso_set_residual_mma: Engine F accumulates the addend on the tensor core (default on)
-bool tile_reverse();   // urso_set_tile_reverse: Engine-F launches planned while on walk their tiles in DESCENDING order
-int l2_hints();        // urso_set_l2_hints: bit 0 = activation / addend loads evict_first, bit 1 = weight loads evict_last
-bool l2_prefetch();    // urso_set_l2_prefetch: Engine-F producers prefetch the next tile's activation tiles into L2
-int residual_mma_mode();   // 0 = epilogue add, 1 = tensor core through a dedicated addend ring, 2 = addend chunks ride in the operand stages where K allows
-bool radd_deep();      // urso_set_addend_ring_deep: left-over shared memory deepens the addend ring of Engine F (default off)
 bool wgrad_halo_enabled();   // urso_set_wgrad_halo: Engine W reads the taps of a 3x3 / stem filter from one box + halo (default on)
 bool dry_run();   // urso_set_dry_run(1): create-calls plan only (CPU-side tests of the planners)
 int max_ctas();   // num_sms() or the urso_set_max_ctas() limit: grid size of the persistent Engine-F kernels

@@ -81,9 +81,6 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   FastDiv fd_ntn, fd_tw, fd_th;
   int ncols;
-  int rev;           // 1: tiles are walked in descending order (urso_set_tile_reverse)
-  unsigned long long pol_a, pol_b;   // L2 eviction-priority hints of the activation / weight tile loads (0 = none)
-  int l2pf;          // 1: producers prefetch the activation (and addend) tiles of the CTA's NEXT tile into L2 (urso_set_l2_prefetch)
   int npipe;         // 1 or 2 producer -> MMA pipelines working on alternate tiles
   int stages;        // per pipeline: stream mode = ring of (A, B) stages; halo mode = ring of B tiles (unless resident)
   int kpack;         // stream mode: K steps (of 64) per stage / barrier round
@@ -98,11 +95,6 @@ struct ConvGemmParams {
                      // The epilogue then has no input stream at all (no ring, no unpack, no add).  One pipeline only
                      // (BLOCK_N = 256): producer warp 3 feeds the addend tiles through their own ring of kRaddStages
                      // (barriers: the halo mode's A-ring pair), producer warp 0 owns every operand round.
-                     // radd == 2 (K steps divide the 4 chunks: 2 or 4 K steps): no separate ring -- every operand stage also
-                     // carries radd_cps = 4 / ksteps addend chunks, consumed in the same barrier round (half the rounds
-                     // per tile, and the addend no longer sits serially behind the operand rounds).
-  int radd_cps, r_ring_off;
-  int radd_stages;   // radd == 1: slots of the addend ring (>= one tile = 4, more where shared memory is left over)
   int ident_off, radd_off;
   int epi_tma;       // 1: TMA epilogue, 0: legacy register epilogue
   int has_add, has_mask;
@@ -135,7 +127,6 @@ constexpr int kRaddStages = 4;                      // addend ring: one BLOCK_N 
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, int& n_tile, int& img, int& h0,
                                             int& w0) {
-  if (p.rev) tile = p.total_tiles - 1 - tile;
   const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntn);
   n_tile = tile - (int)m_tile * p.n_tiles_n;
   const uint32_t rest = fdiv(m_tile, p.fd_tw);
@@ -148,7 +139,6 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& p, int tile, i
 }
 
 __device__ __forceinline__ int fdiv_ntile(const ConvGemmParams& p, int tile) {
-  if (p.rev) tile = p.total_tiles - 1 - tile;
   return tile - (int)fdiv((uint32_t)tile, p.fd_ntn) * p.n_tiles_n;
 }
 
@@ -164,17 +154,6 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
-}
-
-// operand tile loads with an optional L2 eviction-priority hint (warp-uniform branch, one elected lane issues)
-__device__ __forceinline__ void load_a(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                       unsigned long long pol) {
-  if (pol) tma_load_4d_hint(dst, m, bar, c0, c1, c2, c3, pol);
-  else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
-}
-__device__ __forceinline__ void load_b(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, unsigned long long pol) {
-  if (pol) tma_load_2d_hint(dst, m, bar, c0, c1, pol);
-  else tma_load_2d(dst, m, bar, c0, c1);
 }
 
 // Position of an epilogue warp in its stream of 64-channel chunks (tiles of this CTA x chunks per tile).
@@ -313,7 +292,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (elect_one()) {
           mbar_arrive_expect_tx(bres_bar, p.ksteps * kBTileBytes);
           for (int ks = 0; ks < p.ksteps; ++ks)
-            load_b(smem + p.bres_off + ks * kBTileBytes, &p.b_map, bres_bar, ks * kBlockK, 0, p.pol_b);
+            tma_load_2d(smem + p.bres_off + ks * kBTileBytes, &p.b_map, bres_bar, ks * kBlockK, 0);
         }
         __syncwarp();
       }
@@ -323,18 +302,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
         decode_tile(p, wk, n_tile, img, h0, w0);
-        const int wk_nx = wk + npipe * (int)gridDim.x;
-        const bool pf_on = p.l2pf && a_mine && wk_nx < p.total_tiles;
-        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
-        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         for (int c = 0; c < c_chunks; ++c) {
           if (a_mine) {
             mbar_wait(&aemptyb[a_stage], a_phase ^ 1);
             if (elect_one()) {
-              if (pf_on) tma_prefetch_4d(&p.a_halo_map, c * kBlockK, nx_w0 + p.halo_dw_min, nx_h0 + p.halo_dh_min, nx_img);
               mbar_arrive_expect_tx(&afullb[a_stage], p.halo_bytes);
-              load_a(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afullb[a_stage], c * kBlockK, w0 + p.halo_dw_min,
-                     h0 + p.halo_dh_min, img, p.pol_a);
+              tma_load_4d(sA + a_stage * p.a_stage_bytes, &p.a_halo_map, &afullb[a_stage], c * kBlockK,
+                          w0 + p.halo_dw_min, h0 + p.halo_dh_min, img);
             }
             __syncwarp();
           }
@@ -348,8 +322,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 mbar_wait(&emptyb[stage], phase ^ 1);
                 if (elect_one()) {
                   mbar_arrive_expect_tx(&fullb[stage], kBTileBytes);
-                  load_b(sB + stage * kBTileBytes, &p.b_map, &fullb[stage], (s * c_chunks + c) * kBlockK, n_tile * BLOCK_N,
-                         p.pol_b);
+                  tma_load_2d(sB + stage * kBTileBytes, &p.b_map, &fullb[stage], (s * c_chunks + c) * kBlockK,
+                              n_tile * BLOCK_N);
                 }
                 __syncwarp();
               }
@@ -361,7 +335,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
-    } else if (p.radd == 1 && pw == 1) {
+    } else if (p.radd && pw == 1) {
       // addend ring (one pipeline): a whole tile's 64-channel chunks ahead of the MMA warp, which consumes them after the
       // tile's operand rounds
       int slot = 0;
@@ -372,21 +346,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         decode_tile(p, wk, n_tile, img, h0, w0);
         const int n0 = n_tile * BLOCK_N;
         const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
-        // (the ring holds one tile: the loads below already run a tile ahead; the prefetch reaches two tiles further)
-        const int wk_nx = wk + 2 * (int)gridDim.x;
-        const bool pf_on = p.l2pf && wk_nx < p.total_tiles;
-        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
-        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         for (int r = 0; r < rn; ++r) {
           mbar_wait(&aempty_bar[slot], rphase ^ 1);
           if (elect_one()) {
-            if (pf_on && nx_n * BLOCK_N + r * kBlockK < p.ncols)
-              tma_prefetch_4d(&p.radd_map, nx_n * BLOCK_N + r * kBlockK, nx_w0, nx_h0, nx_img);
             mbar_arrive_expect_tx(&afull_bar[slot], kATileBytes);
-            load_a(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img, p.pol_a);
+            tma_load_4d(ring + slot * kATileBytes, &p.radd_map, &afull_bar[slot], n0 + r * kBlockK, w0, h0, img);
           }
           __syncwarp();
-          if (++slot == p.radd_stages) {
+          if (++slot == kRaddStages) {
             slot = 0;
             rphase ^= 1;
           }
@@ -395,9 +362,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     } else {
       // stream mode: a stage holds kpack K steps (A tile + B tile each); the owning producer arms the barrier once
       // with the bytes of the whole round and issues its tile loads
-      const bool own_all = npipe == 2 || p.radd == 1;      // (with an addend ring producer 0 issues every operand round)
-      const int cps = p.radd == 2 ? p.radd_cps : 0;        // addend chunks riding in every operand stage
-      uint8_t* sR = pbase + p.r_ring_off;
+      const bool own_all = npipe == 2 || p.radd != 0;      // (with an addend ring producer 0 issues every operand round)
       int stage = 0, gg = 0;
       uint32_t phase = 0;
       const int kp = p.kpack;
@@ -405,12 +370,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
         int n_tile, img, h0, w0;
         decode_tile(p, wk, n_tile, img, h0, w0);
-        const int wk_nx = wk + npipe * (int)gridDim.x;
-        const bool pf_on = p.l2pf && wk_nx < p.total_tiles;
-        int nx_n = 0, nx_img = 0, nx_h0 = 0, nx_w0 = 0;
-        if (pf_on) decode_tile(p, wk_nx, nx_n, nx_img, nx_h0, nx_w0);
         int kcol = 0, ks = 0, slot = 0;
-        const int rn_tile = (p.ncols - n_tile * BLOCK_N < BLOCK_N ? p.ncols - n_tile * BLOCK_N : BLOCK_N) >> 6;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
           for (int c = 0; c < sg.c_chunks; ++c, ++ks) {
@@ -419,20 +379,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               if (elect_one()) {
                 if (slot == 0) {
                   const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
-                  int n_r = rn_tile - ks * cps;                                // valid addend chunks of this round
-                  n_r = n_r < 0 ? 0 : (n_r > cps ? cps : n_r);
-                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes) + n_r * kATileBytes);
+                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes));
                 }
-                load_a(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK, w0 + sg.dw,
-                       h0 + sg.dh, img, p.pol_a);
-                if (pf_on) tma_prefetch_4d(&p.a_maps[sg.map_id], c * kBlockK, nx_w0 + sg.dw, nx_h0 + sg.dh, nx_img);
-                load_b(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N, p.pol_b);
-                for (int i = 0; i < cps; ++i) {
-                  const int r = ks * cps + i;
-                  if (r < rn_tile)
-                    load_a(sR + (stage * cps + i) * kATileBytes, &p.radd_map, &fullb[stage], n_tile * BLOCK_N + r * kBlockK, w0,
-                           h0, img, p.pol_a);
-                }
+                tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK,
+                            w0 + sg.dw, h0 + sg.dh, img);
+                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N);
               }
               __syncwarp();
             }
@@ -534,10 +485,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       int stage = 0, rslot = 0;
       uint32_t phase = 0, rphase = 0;
       const uint32_t radd_base = smem_u32(smem + p.radd_off);
-      const uint32_t r_base = a_base + p.r_ring_off;
-      const int cps = p.radd == 2 ? p.radd_cps : 0;
-      constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 64, 0, 0);
-      const uint64_t ident_d = kDescHiB | (smem_u32(smem + p.ident_off) >> 4);
       const int kp = p.kpack;
       const int ksteps = p.ksteps;
       int li = 0;
@@ -546,11 +493,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         mbar_wait(&temptyb[as], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (pipe * 2 + as) * BLOCK_N;
-        int rn_tile = 0;
-        if (cps) {
-          const int n0 = fdiv_ntile(p, wk) * BLOCK_N;
-          rn_tile = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
-        }
         for (int ks = 0; ks < ksteps; ks += kp) {
           const int n = ksteps - ks < kp ? ksteps - ks : kp;
           mbar_wait(&fullb[stage], phase);
@@ -563,14 +505,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
             }
-            for (int i = 0; i < cps; ++i) {      // D[:, 64r .. 64r+63] += addend chunk r x I (after this tile's first MMA)
-              const int r = ks * cps + i;
-              if (r < rn_tile) {
-                const uint64_t ad = kDescHiB | ((r_base + (stage * cps + i) * kATileBytes) >> 4);
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d_tmem + r * 64, ad + 2 * k, ident_d + 2 * k, idesc64, 1u);
-              }
-            }
             umma_commit(&emptyb[stage]);   // one commit per barrier round
           }
           __syncwarp();
@@ -579,8 +513,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             phase ^= 1;
           }
         }
-        if (p.radd == 1) {       // D[:, 64r .. 64r+63] += addend chunk r x I
-          const uint64_t bd = ident_d;
+        if (p.radd) {       // D[:, 64r .. 64r+63] += addend chunk r x I
+          constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 64, 0, 0);
+          const uint64_t bd = kDescHiB | (smem_u32(smem + p.ident_off) >> 4);
           const int n0 = fdiv_ntile(p, wk) * BLOCK_N;
           const int rn = (p.ncols - n0 < BLOCK_N ? p.ncols - n0 : BLOCK_N) >> 6;
           for (int r = 0; r < rn; ++r) {
@@ -593,7 +528,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               umma_commit(&aempty_bar[rslot]);
             }
             __syncwarp();
-            if (++rslot == p.radd_stages) {
+            if (++rslot == kRaddStages) {
               rslot = 0;
               rphase ^= 1;
             }
@@ -642,7 +577,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         uint8_t* dst = ei + slot * slot_bytes;
         mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
         const int c = pf.n_tile * BLOCK_N + pf.j * 64;
-        if (p.has_add) load_a(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img, p.pol_a);
+        if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         if (p.has_mask)
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         pf.next(p);
@@ -1017,12 +952,11 @@ static int make_pix_map(CUtensorMap* out, const urso_pix& px, int C, int W, int 
 namespace {
 struct PipePlan {
   int npipe, stages, kpack, a_stages, bres;
-  int pipe_bytes, b_ring_off, bres_bytes, r_ring_off;
+  int pipe_bytes, b_ring_off, bres_bytes;
 };
 
-bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, int r_step_bytes, long long tiles_per_cta,
-                 PipePlan* pl) {
-  const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2 + r_step_bytes;   // + addend chunks riding in the stage
+bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, long long tiles_per_cta, PipePlan* pl) {
+  const int step_bytes = urso::kATileBytes + bn * urso::kBlockK * 2;
   // preference order: two pipelines (hides the issue-side cost of a barrier round, the bound of the N <= 128 launches),
   // two K steps per round where the ring still gets >= 2 stages per pipeline
   const bool dual_ok = bn <= 128 && tiles_per_cta >= 2;
@@ -1041,7 +975,6 @@ bool plan_stream(int avail, int bn, int ksteps, bool epi_inputs, bool radd, int 
     if (np == 2 && kp == 1 && stages < 3 && avail / step_bytes >= 3) continue;   // prefer one deeper ring over two shallow ones
     pl->npipe = np; pl->kpack = kp; pl->stages = stages; pl->a_stages = 0; pl->bres = 0; pl->bres_bytes = 0;
     pl->b_ring_off = stages * kp * urso::kATileBytes;
-    pl->r_ring_off = stages * kp * (urso::kATileBytes + bn * urso::kBlockK * 2);
     pl->pipe_bytes = stages * kp * step_bytes;
     return true;
   }
@@ -1135,9 +1068,6 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   // pipeline (BLOCK_N = 256), short K loops -- the store-bound launches, whose epilogue warps are the bottleneck.  (With
   // >= 8 K steps the third operand stage that the addend ring displaces is worth more: res5x_2c 54 -> 67 us measured.)
   p.radd = (residual_mma_enabled() && d->addend.ptr != nullptr && p.epi_tma && !d->halo && bn == 256 && ksteps <= 4) ? 1 : 0;
-  // 2 or 4 K steps: the addend chunks ride in the operand stages (radd == 2) instead of a ring of their own
-  if (p.radd && residual_mma_mode() >= 2 && (ksteps == 2 || ksteps == 4) && d->b_rows % 256 == 0) p.radd = 2;
-  p.radd_cps = p.radd == 2 ? 4 / ksteps : 0;
   p.shift_bytes = (p.epi_tma && d->shift != nullptr) ? ((d->b_rows * 4 + 1023) / 1024) * 1024 : 0;
   const int kColAcc = kColAccOnly + p.shift_bytes;     // everything between the control block and the epilogue rings
   if ((d->relu_bits.ptr != nullptr || d->mask_bits.ptr != nullptr) && !p.epi_tma) {
@@ -1154,8 +1084,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   for (const int bn_asked = bn;; p.radd = 0, bn = bn_asked) {       // second pass: the addend ring did not fit
     p.has_add = d->addend.ptr != nullptr && !p.radd;
     n_in = p.has_add + p.has_mask;
-    radd_bytes = p.radd == 1 ? 8192 + kRaddStages * kATileBytes : (p.radd == 2 ? 8192 : 0);   // identity tile (+ addend ring)
-    const int r_step = p.radd_cps * kATileBytes;
+    radd_bytes = p.radd ? 8192 + kRaddStages * kATileBytes : 0;     // identity tile + addend ring
     if (p.epi_tma) {
       // per-warp private rings (8 epilogue warps): input slots (prefetch depth) and output slabs (stores in flight).
       // Launches with a long K loop visit the epilogue rarely: minimal rings, smem goes to the operand pipelines.  Launches
@@ -1164,8 +1093,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       const bool heavy = ksteps >= 4;
       const bool epi_bound = ksteps <= 6;
       p.ei_depth = (heavy || n_in == 2) ? 1 : 2;
-      p.eo_depth = (heavy || n_in == 2 || p.radd == 1) ? 1 : 2;
-      if (p.radd == 2) p.eo_depth = 2;      // store-bound launches: two output slabs per warp where they fit (checked below)
+      p.eo_depth = (heavy || n_in == 2 || p.radd) ? 1 : 2;
       if (n_in > 0 && epi_bound) p.ei_depth = 2;
       epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
       const int room = kSmemBudget - kCtrlBytes - kColAcc - radd_bytes;
@@ -1175,16 +1103,11 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
         epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
       }
       const int min_stages = ((n_in > 0 && epi_bound) || p.radd) ? 2 : 3;
-      if (p.radd == 2 && p.eo_depth == 2 && room - epi_bytes < 2 * (kATileBytes + 256 * kBlockK * 2 + r_step)) {
-        p.eo_depth = 1;
-        epi_bytes = 8 * p.ei_depth * n_in * kSlabBytes + 8 * p.eo_depth * kSlabBytes;
-      }
-      if (bn == 256 && room - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2 + r_step)) bn = 128;
+      if (bn == 256 && room - epi_bytes < min_stages * (kATileBytes + 256 * kBlockK * 2)) bn = 128;
     } else {
       epi_bytes = kLegacyScratchBytes;
     }
     if (!p.radd || bn == 256) break;
-    p.radd_cps = 0;
   }
   h->block_n = bn;
   p.n_tiles_n = (d->b_rows + bn - 1) / bn;
@@ -1201,7 +1124,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   if (sms <= 0) sms = 148;
   h->grid = p.total_tiles < sms ? p.total_tiles : sms;
   const long long tiles_per_cta = (total + h->grid - 1) / h->grid;
-  PipePlan pl = {};
+  PipePlan pl;
   bool planned = false;
   int halo_w = 0, halo_h = 0, dw_min = 0, dh_min = 0;
   if (d->halo) {
@@ -1246,7 +1169,7 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
         continue;
       }   // else: not enough shared memory for the halo rings -> plain stream mode on the same patch
     }
-    planned = plan_stream(avail, bn, ksteps, n_in > 0, p.radd != 0, p.radd_cps * kATileBytes, tiles_per_cta, &pl);
+    planned = plan_stream(avail, bn, ksteps, n_in > 0, p.radd != 0, tiles_per_cta, &pl);
   }
   if (!planned) {
     set_error("not enough shared memory for 2 pipeline stages (BLOCK_N=%d)", bn);
@@ -1266,21 +1189,10 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
   p.bres = pl.bres;
   p.pipe_bytes = pl.pipe_bytes;
   p.b_ring_off = pl.b_ring_off;
-  p.r_ring_off = pl.r_ring_off;
   p.bres_off = pl.npipe * pl.pipe_bytes;
   p.ident_off = p.bres_off + pl.bres_bytes;
   p.radd_off = p.ident_off + (p.radd ? 8192 : 0);
-  p.radd_stages = kRaddStages;
-  if (p.radd == 1 && radd_deep()) {
-    // shared memory the operand ring could not use (less than one more stage) goes to the addend ring: these launches
-    // are bound by the bytes they keep in flight (measured: time follows ring bytes), so every 16 KB slot counts
-    const int used = p.radd_off + kRaddStages * kATileBytes + (kCtrlBytes + kColAcc + 1023) / 1024 * 1024 + epi_bytes;
-    int extra = (kSmemBudget - used) / kATileBytes;
-    if (extra < 0) extra = 0;
-    if (extra > 8 - kRaddStages) extra = 8 - kRaddStages;       // afull / aempty barrier arrays hold 8
-    p.radd_stages = kRaddStages + extra;
-  }
-  p.ctrl_off = p.radd_off + (p.radd == 1 ? p.radd_stages * kATileBytes : 0);
+  p.ctrl_off = p.radd_off + (p.radd ? kRaddStages * kATileBytes : 0);
   const int fixed = p.ctrl_off + kCtrlBytes + kColAcc;
   if (p.epi_tma) {
     p.ei_off = (fixed + 1023) / 1024 * 1024;
@@ -1309,10 +1221,6 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
       return rc;
     }
   }
-  p.rev = tile_reverse() ? 1 : 0;
-  p.l2pf = l2_prefetch() ? 1 : 0;
-  p.pol_a = (l2_hints() & 1) ? kL2EvictFirst : 0ull;
-  p.pol_b = (l2_hints() & 2) ? kL2EvictLast : 0ull;
   p.n_seg = d->n_seg;
   p.OW = d->OW; p.OH = d->OH; p.NB = d->NB;
   p.TW = d->TW; p.TH = d->TH;
@@ -1360,14 +1268,5 @@ extern "C" int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9) 
   const urso::ConvGemmParams& p = h->params;
   const int32_t v[9] = {h->block_n, p.npipe, p.stages, p.kpack, p.halo, p.bres, p.a_stages, h->smem_bytes, h->grid};
   for (int i = 0; i < 9; ++i) out9[i] = v[i];
-  return 0;
-}
-
-/* more plan introspection: writes {radd mode, addend chunks per stage, ei_depth, eo_depth, tile order reversed, L2 prefetch} */
-extern "C" int urso_convgemm_plan_extra(const urso_convgemm_t* h, int32_t* out6) {
-  URSO_REQUIRE(h != nullptr && out6 != nullptr, "null argument");
-  const urso::ConvGemmParams& p = h->params;
-  const int32_t v[6] = {p.radd, p.radd == 1 ? p.radd_stages : p.radd_cps, p.ei_depth, p.eo_depth, p.rev, p.l2pf};
-  for (int i = 0; i < 6; ++i) out6[i] = v[i];
   return 0;
 }

@@ -320,10 +320,6 @@ extern "C" int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* ou
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_plan_info(h->plan, out9);
 }
-extern "C" int urso_conv2d_fwd_plan_extra(const urso_conv2d_fwd_t* h, int32_t* out6) {
-  URSO_REQUIRE(h != nullptr, "null handle");
-  return urso_convgemm_plan_extra(h->plan, out6);
-}
 extern "C" void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h) {
   if (h == nullptr) return;
   urso_convgemm_destroy(h->plan);

@@ -127,37 +127,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
-// Same with an L2 eviction-priority hint (policy = a createpolicy.fractional encoding, fraction 1.0).  Streaming operands
-// (an activation that no later launch of the phase re-reads) are loaded evict_first so that they do not displace the output
-// the NEXT launch is about to read back; the small weight operand every CTA re-reads is loaded evict_last.
-constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d_hint(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                                 uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(smem_u32(smem)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_hint(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
-                                                 int c3, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, "
-      "%6}], [%2], %7;" ::"r"(smem_u32(smem)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
-      : "memory");
-}
-
-// TMA prefetch of a tile into L2 only (no shared-memory destination, no completion to wait for): lets a producer run
-// further ahead of the tensor core than its shared-memory ring is deep -- the DRAM latency is then paid by the prefetch,
-// the ring load that follows hits L2.
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-
 __device__ __forceinline__ void tma_load_4d_u32(uint32_t smem_addr, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1,
                                                 int c2, int c3) {
   asm volatile(

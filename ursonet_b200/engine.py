@@ -11,7 +11,6 @@ Memory layout (HBM):
   gradients of activations (du)    : bf16 NHWC, masked by the consumer's ReLU at production time
   staged GEMM operands             : bf16 K-major weight matrices with the frozen-BN scale folded in (rebuilt per step)
 """
-import contextlib
 import math
 import re
 from typing import Dict, List, Optional
@@ -144,8 +143,7 @@ class Engine:
 
     def __init__(self, cfg, batch_size: int, training: bool, device="cuda", world_size: int = 1, seed: int = 0,
                  parity=None, reserve_sms: int = 0, lanes: bool = True, wgrad_lanes: int = 1, sparse_bwd: bool = True,
-                 mask_bits: bool = True, pair_l2: bool = False, stage_split: int = 4, zigzag: int = 0,
-                 l2_hints: int = 0, l2_prefetch: int = 0):
+                 mask_bits: bool = True, pair_l2: bool = False, stage_split: int = 4):
         lib.load()   # fail loudly if the CUDA extension is missing: there is no other path
         if not torch.cuda.is_available():
             raise lib.UrsoError("a CUDA device is required (no CPU fallback)")
@@ -167,12 +165,6 @@ class Engine:
         # does not wait for the operands of all layers at the start of a step (0 = one table)
         self.stage_split = int(stage_split)
         self._pair = {}
-        # zigzag (bit 0: forward, bit 1: input-gradient chain): consecutive Engine-F launches of the dependent chain walk
-        # their tiles in OPPOSITE directions, so each one starts on the pixels its producer wrote last -- the part of that
-        # tensor still in L2 (126 MB against 79..629 MB tensors).  l2_hints (bits 0-1: forward, bits 2-3: gradient chain;
-        # see urso_set_l2_hints): eviction priorities that keep the freshly written output ahead of the streamed inputs.
-        # l2_prefetch (bit 0: forward, bit 1: gradient chain; urso_set_l2_prefetch): producers prefetch the next tile into L2
-        self.zigzag, self.l2_hints, self.l2_prefetch, self._zz = int(zigzag), int(l2_hints), int(l2_prefetch), 0
         self.graph: Graph = build_graph(cfg)
         # Lanes (CUDA streams -> graph branches).  Lane 0 is the dependent chain (forward convs, heads, losses, dgrad
         # chain); the weight-gradient launches run on their own lane(s) (wgrad of a layer only needs the du its dgrad
@@ -359,8 +351,7 @@ class Engine:
             bits = None
             if self.training and self.use_mask_bits and c.relu and c.dst in g.relu_buffers and c.dst != g.pool_src:
                 bits = self.relu_bits[c.dst] = torch.zeros((B, oh, ow, c.cout // 32), dtype=torch.int32, device=self.device)
-            with self._tile_policy(self._zigzag_next(1), self.l2_hints & 3, self.l2_prefetch & 1):
-                op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu, relu_bits=bits)
+            op = lib.Conv2dFwd(shape, x, w, sc, sh, out, addend=addend, relu=c.relu, relu_bits=bits)
             self.fwd_ops[c.name] = op
             staged = self._stage_op_a if c.name in self._early_layers else self._stage_op
             if c.stem:
@@ -657,11 +648,9 @@ class Engine:
         op = self._add(self.ops_bwd, OpRec(lambda: box["p"].launch(), "conv_dgrad", X, fl, nbytes,
                                            after=self._bwd_deps() + [stage_op] + ([pair] if pair is not None else [])))
 
-        rev = self._zigzag_next(2)
-
         def bind():
             cs = self._zero_view(key) if key else None
-            with self._cta_limit(op, half=pair is not None), self._tile_policy(rev, (self.l2_hints >> 2) & 3, self.l2_prefetch & 2):
+            with self._cta_limit(op, half=pair is not None):
                 box["p"] = lib.Conv2dDgrad(shapes, dys, ws, scs, dX, mask=mask, addend=addend, colsum=cs,
                                            dy_sparse=sparse_in, mask_bits=mask_bits)
             op.launches = box["p"].n_launches
@@ -674,29 +663,11 @@ class Engine:
         if self.sparse_bwd and not adds and only_phase0 and h % 2 == 0 and w % 2 == 0:
             self.sparse.add(X)
 
-    def _zigzag_next(self, bit):
-        if not (self.zigzag & bit):
-            return 0
-        self._zz ^= 1
-        return self._zz
-
-    @contextlib.contextmanager
-    def _tile_policy(self, reverse, hints, prefetch):
-        """Plan the Engine-F launches created inside with this tile order / L2 hints / L2 prefetch (library-global knobs)."""
-        L = lib.load()
-        L.urso_set_tile_reverse(int(reverse))
-        L.urso_set_l2_hints(int(hints))
-        L.urso_set_l2_prefetch(1 if prefetch else 0)
-        try:
-            yield
-        finally:
-            L.urso_set_tile_reverse(0)
-            L.urso_set_l2_hints(0)
-            L.urso_set_l2_prefetch(0)
-
     def _cta_limit(self, op, half=False):
         """Context manager: plan the operator of a second-segment backward op with `reserve_sms` SMs left free, or (half)
         on half of the SMs (an L2-sharing pair)."""
+        import contextlib
+
         @contextlib.contextmanager
         def cm():
             n_sm = lib.load().urso_num_sms()

@@ -98,10 +98,6 @@ SIGNATURES = {
     "urso_set_dry_run": [_i32],
     "urso_set_pdl": [_i32],
     "urso_set_residual_mma": [_i32],
-    "urso_set_tile_reverse": [_i32],
-    "urso_set_l2_hints": [_i32],
-    "urso_set_l2_prefetch": [_i32],
-    "urso_set_addend_ring_deep": [_i32],
     "urso_set_wgrad_halo": [_i32],
     "urso_sizeof_convgemm_desc": [],
     "urso_sizeof_wgrad_desc": [],
@@ -109,7 +105,6 @@ SIGNATURES = {
     "urso_convgemm_launch": [_vp, _vp],
     "urso_convgemm_destroy": [_vp],
     "urso_convgemm_plan_info": [_vp, C.POINTER(_i32)],
-    "urso_convgemm_plan_extra": [_vp, C.POINTER(_i32)],
     "urso_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(_vp)],
     "urso_wgrad_launch": [_vp, _vp],
     "urso_wgrad_destroy": [_vp],
@@ -123,7 +118,6 @@ SIGNATURES = {
     "urso_conv2d_fwd_launch": [_vp, _vp],
     "urso_conv2d_fwd_destroy": [_vp],
     "urso_conv2d_fwd_plan_info": [_vp, C.POINTER(_i32)],
-    "urso_conv2d_fwd_plan_extra": [_vp, C.POINTER(_i32)],
     "urso_conv2d_dgrad_workspace_bytes": [C.POINTER(Conv2dDgradDesc)],
     "urso_conv2d_dgrad_create": [C.POINTER(Conv2dDgradDesc), C.POINTER(_vp)],
     "urso_conv2d_dgrad_stage_weights": [_vp, _vp],
@@ -177,8 +171,7 @@ SIGNATURES = {
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
-             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_set_tile_reverse": None,
-             "urso_set_l2_hints": None, "urso_set_l2_prefetch": None, "urso_set_addend_ring_deep": None, "urso_set_wgrad_halo": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_set_wgrad_halo": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
              "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
              "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
