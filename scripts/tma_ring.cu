@@ -14,17 +14,20 @@ using namespace urso;
 struct RingParams {
   CUtensorMap a_map, b_map;      // a: [rows_a, 1024] bf16, box {64, 128};  b: [256, 1024] bf16, box {64, brows}
   int stages, na, brows, ksteps, tiles_per_cta, delay, a_wrap_tiles;
+  int a_stages;      // > 0: SPLIT rings -- the activation boxes get their own ring of a_stages slots (own barriers, own producer warp)
 };
 
 __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ RingParams p, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full_bar[16], empty_bar[16];
+  __shared__ uint64_t full_bar[16], empty_bar[16], afull_bar[16], aempty_bar[16];
   const int warp = threadIdx.x >> 5;
   const int stage_bytes = p.na * 16384 + p.brows * 128;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 16; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.a_map);
@@ -32,7 +35,59 @@ __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ Ri
   }
   __syncthreads();
   const long long t0 = clock64();
-  if (warp == 0) {
+  if (p.a_stages > 0) {
+    // split rings: [a_stages x na x 16 KB][stages x brows x 128 B]
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + p.a_stages * p.na * 16384;
+    const int n = p.tiles_per_cta * p.ksteps;
+    if (warp == 0) {            // activation producer
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < p.tiles_per_cta; ++t) {
+        const int row0 = ((int)blockIdx.x * p.tiles_per_cta + t) * 128 * p.na;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          mbar_wait(&aempty_bar[st], ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull_bar[st], p.na * 16384);
+            for (int a = 0; a < p.na; ++a)
+              tma_load_2d(a_ring + (st * p.na + a) * 16384, &p.a_map, &afull_bar[st], ks * 64, row0 + a * 128);
+          }
+          __syncwarp();
+          if (++st == p.a_stages) { st = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 2) {     // weight producer
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < n; ++i) {
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[st], p.brows * 128);
+          tma_load_2d(b_ring + st * p.brows * 128, &p.b_map, &full_bar[st], (i % p.ksteps) * 64, 0);
+        }
+        __syncwarp();
+        if (++st == p.stages) { st = 0; ph ^= 1; }
+      }
+    } else if (warp == 1) {     // consumer
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int i = 0; i < n; ++i) {
+        mbar_wait(&afull_bar[sa], pa);
+        mbar_wait(&full_bar[sb], pb);
+        if (p.delay > 0) {
+          const long long t = clock64();
+          while (clock64() - t < p.delay) {}
+        }
+        if (threadIdx.x == 32) {
+          mbar_arrive(&aempty_bar[sa]);
+          mbar_arrive(&empty_bar[sb]);
+        }
+        __syncwarp();
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        if (++sb == p.stages) { sb = 0; pb ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < p.tiles_per_cta; ++t) {
@@ -115,7 +170,7 @@ int main() {
   printf("%d SMs, %d MHz nominal; per K step: na x 16 KB activation boxes (DRAM stream unless 'L2') + brows x 128 B weight box (L2)\n", sms,
          khz / 1000);
   printf("%-26s %6s %7s %9s %10s %10s %9s\n", "stage", "stages", "delay", "ring KB", "B/clk/SM", "GB/s/SM", "TB/s all");
-  struct Cfg { int na, brows, stages, delay, wrap; };
+  struct Cfg { int na, brows, stages, delay, wrap, a_stages; };
   const Cfg cfgs[] = {
       {1, 256, 2, 0, 0}, {1, 256, 3, 0, 0}, {1, 256, 4, 0, 0},                       // Engine F stream stage: 48 KB
       {1, 256, 4, 512, 0},                                                             // + the MMAs' time (512 cycles per K step)
@@ -124,6 +179,10 @@ int main() {
       {1, 0, 4, 0, 0}, {1, 0, 8, 0, 0}, {1, 0, 12, 0, 0},                            // activation stream only: 16 KB boxes
       {2, 0, 6, 0, 0},                                                                 // 32 KB of activations per stage
       {1, 256, 4, 0, 2}, {1, 256, 2, 0, 2}, {1, 128, 6, 0, 2}, {1, 0, 12, 0, 2},     // everything L2 resident
+      // consumer time of the real kernel (~316 cycles of issue overhead + 512 of MMAs): joint ring vs SPLIT rings (the DRAM
+      // stream of activations gets more slots than the L2-resident weight tiles)
+      {1, 256, 4, 830, 0, 0}, {1, 256, 4, 830, 0, 6}, {1, 256, 3, 830, 0, 8}, {1, 256, 4, 512, 0, 6}, {1, 256, 4, 0, 0, 6},
+      {1, 256, 4, 1100, 0, 0}, {1, 256, 4, 1100, 0, 6},
   };
   for (const Cfg& c : cfgs) {
     RingParams p;
@@ -131,8 +190,9 @@ int main() {
     make_map(enc, &p.b_map, b, 256, c.brows ? c.brows : 128);
     p.stages = c.stages; p.na = c.na; p.brows = c.brows; p.ksteps = ksteps; p.tiles_per_cta = tiles; p.delay = c.delay;
     p.a_wrap_tiles = c.wrap;
+    p.a_stages = c.a_stages;
     const int stage_bytes = c.na * 16384 + c.brows * 128;
-    const int smem = c.stages * stage_bytes;
+    const int smem = c.a_stages > 0 ? c.a_stages * c.na * 16384 + c.stages * c.brows * 128 : c.stages * stage_bytes;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
       cudaEvent_t e0, e1;
@@ -155,7 +215,8 @@ int main() {
     for (int i = 0; i < sms; ++i) avg += (double)hc[i] / sms;
     const double bytes_sm = (double)tiles * ksteps * stage_bytes;
     char name[64];
-    snprintf(name, sizeof(name), "%dx16KB A + %2d KB B%s", c.na, c.brows * 128 / 1024, c.wrap ? " (L2)" : "");
+    snprintf(name, sizeof(name), "%dx16KB A + %2d KB B%s%s", c.na, c.brows * 128 / 1024, c.wrap ? " (L2)" : "", c.a_stages ? " SPLIT" : "");
+    if (c.a_stages) printf("  (next line: %d activation slots + %d weight slots)\n", c.a_stages, c.stages);
     printf("%-26s %6d %7d %9d %10.1f %10.1f %9.2f\n", name, c.stages, c.delay, smem / 1024, bytes_sm / avg,
            bytes_sm / (best * 1e-3) / 1e9, bytes_sm * sms / (best * 1e-3) / 1e12);
   }
