@@ -14,6 +14,8 @@ using namespace urso;
 struct RingParams {
   CUtensorMap a_map, b_map;      // a: [rows_a, 1024] bf16, box {64, 128};  b: [256, 1024] bf16, box {64, brows}
   int stages, na, brows, ksteps, tiles_per_cta, delay, a_wrap_tiles;
+  int mma;           // 1: the consumer is the real thing -- 4 tcgen05.mma (M = 128, N = 256, K = 16) per K step on the stage's tiles and a
+                     // tcgen05.commit that releases the stage when they have completed (na = 1, brows = 256, joint ring)
   int a_stages;      // > 0: SPLIT rings -- the activation boxes get their own ring of a_stages slots (own barriers, own producer warp)
 };
 
@@ -33,9 +35,38 @@ __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ Ri
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
   }
+  __shared__ uint32_t tmem_slot;
+  if (p.mma && warp == 3) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   const long long t0 = clock64();
-  if (p.a_stages > 0) {
+  if (p.mma && warp == 1) {
+    // real consumer: descriptor = constant high word | (smem address >> 4); K advance of 16 elements = +2
+    constexpr uint64_t kHi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 16) | (1ull << 46) | (2ull << 61);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
+    const uint32_t d_tmem = tmem_slot;
+    const uint32_t base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int n = p.tiles_per_cta * p.ksteps;
+    for (int i = 0; i < n; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = kHi | ((base + stage * stage_bytes) >> 4);
+        const uint64_t bd = kHi | ((base + stage * stage_bytes + 16384) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) != 0);
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (p.a_stages > 0) {
     // split rings: [a_stages x na x 16 KB][stages x brows x 128 B]
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + p.a_stages * p.na * 16384;
@@ -109,7 +140,7 @@ __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ Ri
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !p.mma) {
     int stage = 0;
     uint32_t phase = 0;
     const int n = p.tiles_per_cta * p.ksteps;
@@ -129,6 +160,22 @@ __global__ void __launch_bounds__(128, 1) ring_kernel(const __grid_constant__ Ri
   }
   __syncthreads();
   if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+  if (p.mma) {
+    // drain: every MMA has completed once the last stages were released; one more commit + wait keeps it simple
+    __shared__ uint64_t done_bar;
+    if (threadIdx.x == 32) {
+      mbar_init(&done_bar, 1);
+      fence_barrier_init();
+      umma_commit(&done_bar);
+      mbar_wait(&done_bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+      tc_fence_after();
+      tmem_dealloc(tmem_slot, 256);
+    }
+  }
 }
 
 typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -170,7 +217,7 @@ int main() {
   printf("%d SMs, %d MHz nominal; per K step: na x 16 KB activation boxes (DRAM stream unless 'L2') + brows x 128 B weight box (L2)\n", sms,
          khz / 1000);
   printf("%-26s %6s %7s %9s %10s %10s %9s\n", "stage", "stages", "delay", "ring KB", "B/clk/SM", "GB/s/SM", "TB/s all");
-  struct Cfg { int na, brows, stages, delay, wrap, a_stages; };
+  struct Cfg { int na, brows, stages, delay, wrap, a_stages, mma; };
   const Cfg cfgs[] = {
       {1, 256, 2, 0, 0}, {1, 256, 3, 0, 0}, {1, 256, 4, 0, 0},                       // Engine F stream stage: 48 KB
       {1, 256, 4, 512, 0},                                                             // + the MMAs' time (512 cycles per K step)
@@ -183,6 +230,8 @@ int main() {
       // stream of activations gets more slots than the L2-resident weight tiles)
       {1, 256, 4, 830, 0, 0}, {1, 256, 4, 830, 0, 6}, {1, 256, 3, 830, 0, 8}, {1, 256, 4, 512, 0, 6}, {1, 256, 4, 0, 0, 6},
       {1, 256, 4, 1100, 0, 0}, {1, 256, 4, 1100, 0, 6},
+      // the real consumer: tcgen05.mma + commit (no epilogue, one accumulator)
+      {1, 256, 4, 0, 0, 0, 1}, {1, 256, 3, 0, 0, 0, 1}, {1, 256, 2, 0, 0, 0, 1}, {1, 256, 4, 0, 2, 0, 1},
   };
   for (const Cfg& c : cfgs) {
     RingParams p;
@@ -191,6 +240,7 @@ int main() {
     p.stages = c.stages; p.na = c.na; p.brows = c.brows; p.ksteps = ksteps; p.tiles_per_cta = tiles; p.delay = c.delay;
     p.a_wrap_tiles = c.wrap;
     p.a_stages = c.a_stages;
+    p.mma = c.mma;
     const int stage_bytes = c.na * 16384 + c.brows * 128;
     const int smem = c.a_stages > 0 ? c.a_stages * c.na * 16384 + c.stages * c.brows * 128 : c.stages * stage_bytes;
     float best = 1e30f;
@@ -215,7 +265,7 @@ int main() {
     for (int i = 0; i < sms; ++i) avg += (double)hc[i] / sms;
     const double bytes_sm = (double)tiles * ksteps * stage_bytes;
     char name[64];
-    snprintf(name, sizeof(name), "%dx16KB A + %2d KB B%s%s", c.na, c.brows * 128 / 1024, c.wrap ? " (L2)" : "", c.a_stages ? " SPLIT" : "");
+    snprintf(name, sizeof(name), "%dx16KB A + %2d KB B%s%s", c.na, c.brows * 128 / 1024, c.wrap ? " (L2)" : "", c.a_stages ? " SPLIT" : (c.mma ? " MMA" : ""));
     if (c.a_stages) printf("  (next line: %d activation slots + %d weight slots)\n", c.a_stages, c.stages);
     printf("%-26s %6d %7d %9d %10.1f %10.1f %9.2f\n", name, c.stages, c.delay, smem / 1024, bytes_sm / avg,
            bytes_sm / (best * 1e-3) / 1e9, bytes_sm * sms / (best * 1e-3) / 1e12);
