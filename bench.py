@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--no-residual-mma", action="store_true", help="A/B: residual / fan-in addends added by the epilogue warps instead of the tensor core")
     ap.add_argument("--stage-split", type=int, default=4, help="A/B: leading convs whose weight operands get their own staging launch")
     ap.add_argument("--pair-l2", action="store_true", help="A/B: co-run the dgrad / wgrad launches that share a large gradient tensor")
+    ap.add_argument("--no-tail-split", action="store_true", help="A/B: no N-split of the last partial wave (urso_set_tail_split(0))")
     ap.add_argument("--no-wgrad-halo", action="store_true", help="A/B: Engine W loads one operand atom per filter tap (urso_set_wgrad_halo(0))")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch the engines without programmatic dependent launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -195,6 +196,8 @@ def main():
         _lib.load().urso_set_pdl(0)
     if args.no_residual_mma:
         _lib.load().urso_set_residual_mma(0)
+    if args.no_tail_split:
+        _lib.load().urso_set_tail_split(0)
     if args.no_wgrad_halo:
         _lib.load().urso_set_wgrad_halo(0)
     torch.cuda.set_device(local_rank)

@@ -41,6 +41,12 @@ void urso_set_residual_mma(int on);
  * stem's four row taps) load ONE 8x8-pixel block + halo per 64-channel atom and K step and address every tap as a shifted
  * window of it, instead of one operand atom per tap.  0 = one atom per tap (A/B). */
 void urso_set_wgrad_halo(int on);
+/* N-split tail of Engine F (default on).  A launch whose tile count is not a multiple of the CTA count ends with a partial
+ * wave in which most SMs idle.  K-heavy BLOCK_N = 256 launches in stream mode cut the tiles of that last wave along N into 2
+ * or 4 sub-tiles of 128 / 64 output channels, one per CTA: a sub-tile streams the same pixel tile but only its slice of the
+ * weight tile and issues narrower MMAs, so the last wave costs about half a wave; no reduction is involved and every output
+ * element is accumulated in the same order as before (bit-identical results).  0 = whole tiles only (A/B). */
+void urso_set_tail_split(int on);
 /* struct sizes, so that FFI bindings can verify their layout against this header */
 int urso_sizeof_convgemm_desc(void);
 int urso_sizeof_wgrad_desc(void);
@@ -111,6 +117,7 @@ int urso_convgemm_launch(urso_convgemm_t* h, void* stream);
 void urso_convgemm_destroy(urso_convgemm_t* h);
 /* plan introspection (tests / profiling): out9 = {block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid} */
 int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9);
+int urso_convgemm_tail_split(const urso_convgemm_t* h);   /* sub-tiles per tile of the last partial wave (1 = no N-split tail) */
 
 /* ---- Engine W: weight-gradient GEMM on tcgen05 (replaces Conv2DBackpropFilter of TF autodiff).
  *   G[t][p, q] (+)= sum_pixels  P_t[pixel + (dh_t,dw_t), p] * Q[pixel, q]        t = 0..n_seg-1
@@ -186,6 +193,7 @@ int urso_conv2d_fwd_stage_weights(urso_conv2d_fwd_t* h, void* stream);
 int urso_conv2d_fwd_launch(urso_conv2d_fwd_t* h, void* stream);
 void urso_conv2d_fwd_destroy(urso_conv2d_fwd_t* h);
 int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9); /* see urso_convgemm_plan_info */
+int urso_conv2d_fwd_tail_split(const urso_conv2d_fwd_t* h);                  /* see urso_convgemm_tail_split */
 /* the staging work of this operator as a job of urso_stage_weights_multi (declared below) */
 int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* stage_job_out);
 
@@ -224,6 +232,7 @@ int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream);
 int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h);
 int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h);
 int urso_conv2d_dgrad_plan_info(const urso_conv2d_dgrad_t* h, int32_t launch, int32_t* out9); /* see urso_convgemm_plan_info */
+int urso_conv2d_dgrad_tail_split(const urso_conv2d_dgrad_t* h, int32_t launch);                /* see urso_convgemm_tail_split */
 /* the staging work of this operator as jobs of urso_stage_weights_multi: writes up to max_jobs urso_stage_job structs,
  * returns how many the operator has (negative on error) */
 int urso_conv2d_dgrad_stage_jobs(const urso_conv2d_dgrad_t* h, void* stage_jobs_out, int32_t max_jobs);

@@ -402,3 +402,106 @@ def test_mask_bits_on_a_strided_dgrad_phase_grid():
         torch.cuda.synchronize()
         outs.append(dx.clone())
     assert torch.equal(outs[0], outs[1]) and outs[0].float().abs().sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------ N-split tail
+TAIL_CASES = [  # k, cin, cout, N, h, w, max_ctas (0 = all SMs), addend
+    (1, 512, 256, 4, 80, 120, 0, True),       # 300 tiles on 148 CTAs: 4 tail tiles x 4 sub-tiles; residual through the epilogue ring
+    (3, 256, 256, 8, 40, 60, 0, False),       # the stage-4 3x3 of the bench workload in small: 150 tiles, 2 tail tiles x 4
+    (1, 1024, 512, 8, 40, 60, 0, False),      # two N tiles per pixel tile: the sub-tiles of tail tiles with n_tile = 0 and 1
+    (1, 512, 256, 4, 80, 120, 13, False),     # 300 % 13 = 1 tail tile x 4 sub-tiles, 23 whole tiles per CTA before it
+    (1, 512, 256, 4, 80, 120, 11, True),      # 300 % 11 = 3 tail tiles: 4 x 3 > 11 -> 2 sub-tiles of 128 channels each
+    (1, 512, 256, 1, 37, 53, 0, False),       # 16 tiles: fewer tiles than CTAs -> no full wave, no tail split (plan check only)
+]
+
+
+@pytest.mark.parametrize("k,cin,cout,N,h,w,max_ctas,with_addend", TAIL_CASES)
+def test_tail_split_is_bit_identical_and_matches_oracle(k, cin, cout, N, h, w, max_ctas, with_addend):
+    """urso_set_tail_split(0 / 1): K-heavy BLOCK_N = 256 launches cut the tiles of their last partial wave along N into 2 or 4
+    sub-tiles (one per CTA).  No reduction is involved and every output element keeps its accumulation order, so outputs
+    and ReLU mask bits must be bit-identical to the whole-tile launch -- and match the fp64 oracle."""
+    from ursonet_b200 import lib
+    L = lib.load()
+    x = bf16_exact(N, h, w, cin, seed=171)
+    wk = bf16_exact(k, k, cin, cout, scale=0.03, seed=172)
+    scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+    shift = torch.randn(cout, dtype=torch.float64)
+    addend = bf16_exact(N, h, w, cout, seed=173) if with_addend else None
+    shape = lib.conv_shape(N, h, w, cin, cout, k, 1, "same" if k == 3 else "valid")
+    xd, wd = x.to(torch.bfloat16).to(DEV), wk.float().to(DEV)
+    sd, hd = scale.float().to(DEV), shift.float().to(DEV)
+    ad = addend.to(torch.bfloat16).to(DEV) if with_addend else None
+    outs = []
+    try:
+        L.urso_set_max_ctas(max_ctas)
+        for on in (0, 1):
+            L.urso_set_tail_split(on)
+            y = torch.full((N, h, w, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+            bits = torch.full((N, h, w, cout // 32), -1, dtype=torch.int32, device=DEV)
+            op = lib.Conv2dFwd(shape, xd, wd, sd, hd, y, addend=ad, relu=True, relu_bits=bits)
+            op.stage()
+            op.launch()
+            op.launch()
+            torch.cuda.synchronize()
+            outs.append((y, bits, op.plan_info()))
+    finally:
+        L.urso_set_tail_split(1)
+        L.urso_set_max_ctas(0)
+    info = outs[1][2]
+    tiles = -(-(N * h * w) // 128) * (cout // 256) if k == 1 else None
+    assert outs[0][2]["tail_split"] == 1
+    if tiles is not None:
+        grid = info["grid"]
+        R = tiles % grid if tiles > grid else 0
+        expect = 1 if R == 0 else (4 if 4 * R <= grid else (2 if 2 * R <= grid else 1))
+        assert info["tail_split"] == expect, (info, tiles)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), info
+    with torch.no_grad():
+        ref = O.conv2d(x, staged(wk, scale.float().double()), None, 1, "same" if k == 3 else "valid") + shift.float().double()
+        if with_addend:
+            ref = ref + addend
+        ref = torch.relu(ref)
+    assert relerr(outs[1][0].double().cpu(), ref) <= 6e-3, info
+
+
+def test_tail_split_dgrad_with_mask_bits_and_colsum(request):
+    """The input gradient of a 1x1 conv 256 -> 1024 (K = 1024, 16 K steps) with bit-packed ReLU mask and fused column sums,
+    300 tiles: the tail sub-tiles address their own 64-channel slice of the mask words and of the column sums."""
+    from ursonet_b200 import lib
+    L = lib.load()
+    N, h, w, cin, cout = 4, 80, 120, 256, 1024
+    shape = lib.conv_shape(N, h, w, cin, cout, 1, 1, "valid")
+    wk = bf16_exact(1, 1, cin, cout, scale=0.03, seed=181)
+    scale = 0.5 + torch.rand(cout, dtype=torch.float64)
+    dy = bf16_exact(N, h, w, cout, seed=182)
+    act = bf16_exact(N, h, w, cin, seed=183)
+    bits = torch.zeros(N, h, w, cin // 32, dtype=torch.int32)
+    pos = (act > 0)
+    for c in range(32):        # channel 32 g + c  <->  bit (7 - (c >> 2)) + 8 (c & 3) of word g   (see unpack_bits)
+        bit = (7 - (c >> 2)) + 8 * (c & 3)
+        word = pos.reshape(N, h, w, cin // 32, 32)[..., c].to(torch.int64) << bit
+        bits += torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
+    xr = torch.zeros(N, h, w, cin, dtype=torch.float64, requires_grad=True)
+    (gref,) = torch.autograd.grad(O.conv2d(xr, staged(wk, scale.float().double()), None, 1, "valid"), xr, dy)
+    gref = gref * pos
+    outs = []
+    try:
+        for on in (0, 1):
+            L.urso_set_tail_split(on)
+            dx = torch.zeros(N, h, w, cin, dtype=torch.bfloat16, device=DEV)
+            cs = torch.zeros(cin, dtype=torch.float32, device=DEV)
+            op = lib.Conv2dDgrad([shape], [dy.to(torch.bfloat16).to(DEV)], [wk.float().to(DEV)], [scale.float().to(DEV)], dx,
+                                 mask_bits=bits.to(DEV), colsum=cs)
+            op.stage()
+            op.launch()
+            torch.cuda.synchronize()
+            outs.append((dx, cs, L.urso_conv2d_dgrad_tail_split(op._h, 0)))
+    finally:
+        L.urso_set_tail_split(1)
+    grid = min(L.urso_num_sms(), 300) if request.node.callspec.params["cta_limit"] == 0 else request.node.callspec.params["cta_limit"]
+    R = 300 % grid
+    expect = 1 if R == 0 else (4 if 4 * R <= grid else (2 if 2 * R <= grid else 1))      # 148 CTAs: 4 tail tiles x 4 sub-tiles
+    assert outs[0][2] == 1 and outs[1][2] == expect, (outs[0][2], outs[1][2], grid)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-2)
+    assert relerr(outs[1][0].double().cpu(), gref) <= 6e-3

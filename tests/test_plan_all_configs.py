@@ -56,6 +56,7 @@ def plan_network(l, cfg, B):
         l.urso_conv2d_fwd_plan_info(h, v)
         infos[c.name] = dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem", "grid"), v))
         assert infos[c.name]["smem"] <= 227 * 1024
+        infos[c.name]["tail_split"] = l.urso_conv2d_fwd_tail_split(h)
         l.urso_conv2d_fwd_destroy(h)
         # weight gradient
         wd = lib.Conv2dWgradDesc()
@@ -90,6 +91,7 @@ def plan_network(l, cfg, B):
         v = (C.c_int32 * 9)()
         l.urso_conv2d_dgrad_plan_info(h, 0, v)
         infos["d:" + grp["X"]] = dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem", "grid"), v))
+        infos["d:" + grp["X"]]["tail_split"] = l.urso_conv2d_dgrad_tail_split(h, 0)
         l.urso_conv2d_dgrad_destroy(h)
     return g, infos, n_dgrad, sparse
 
@@ -134,6 +136,11 @@ def test_bench_workload_gets_the_intended_modes(dry):
         assert infos[name]["halo"] == 1 and infos[name]["stages"] >= 5, (name, infos[name])
     assert infos["w:res2a_branch2b"]["units"] == 5 and infos["w:res2a_branch2b"]["groups"] == 1      # all 9 taps in one CTA
     assert infos["w:res4b_branch2b"]["halo"] == 0 and infos["w:res5b_branch2b"]["halo"] == 0
+    # N-split tail: the K-heavy BLOCK_N = 256 launches of stages 4 and 5 cut the tiles of their partial last wave along N
+    # (600 tiles on 148 CTAs: 8 tail tiles x 4 sub-tiles; 640 tiles: 48 tail tiles x 2)
+    assert infos["res4b_branch2a"]["tail_split"] == 4 and infos["res4b_branch2b"]["tail_split"] == 2
+    assert infos["res5b_branch2b"]["tail_split"] == 4 and infos["d:res4b_branch2b"]["tail_split"] == 4
+    assert infos["res2a_branch2c"]["tail_split"] == 1 and infos["res3a_branch2b"]["tail_split"] == 1
     for name, i in infos.items():
         if name.startswith("w:"):
             continue

@@ -31,8 +31,10 @@ int num_sms() {
 static int g_pdl = 1;
 static int g_residual_mma = 1;
 static int g_wgrad_halo = 1;
+static int g_tail_split = 1;
 bool pdl_enabled() { return g_pdl != 0; }
 bool wgrad_halo_enabled() { return g_wgrad_halo != 0; }
+bool tail_split_enabled() { return g_tail_split != 0; }
 bool residual_mma_enabled() { return g_residual_mma != 0; }
 static int g_max_ctas = 0;
 bool dry_run() { return g_dry_run != 0; }
@@ -104,6 +106,7 @@ void urso_set_dry_run(int on) { urso::g_dry_run = on; }
 void urso_set_pdl(int on) { urso::g_pdl = on; }
 void urso_set_residual_mma(int on) { urso::g_residual_mma = on; }
 void urso_set_wgrad_halo(int on) { urso::g_wgrad_halo = on; }
+void urso_set_tail_split(int on) { urso::g_tail_split = on; }
 int urso_sizeof_convgemm_desc(void) { return (int)sizeof(urso_convgemm_desc); }
 int urso_sizeof_wgrad_desc(void) { return (int)sizeof(urso_wgrad_desc); }
 }

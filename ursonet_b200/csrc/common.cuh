@@ -15,6 +15,7 @@ int num_sms();
 bool pdl_enabled();   // urso_set_pdl: launch the tcgen05 engines with programmatic stream serialization (default on)
 bool residual_mma_enabled();   // urso_set_residual_mma: Engine F accumulates the addend on the tensor core (default on)
 bool wgrad_halo_enabled();   // urso_set_wgrad_halo: Engine W reads the taps of a 3x3 / stem filter from one box + halo (default on)
+bool tail_split_enabled();   // urso_set_tail_split: Engine F cuts the tiles of a partial last wave along N (default on)
 bool dry_run();   // urso_set_dry_run(1): create-calls plan only (CPU-side tests of the planners)
 int max_ctas();   // num_sms() or the urso_set_max_ctas() limit: grid size of the persistent Engine-F kernels
 

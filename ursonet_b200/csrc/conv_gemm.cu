@@ -81,6 +81,15 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   FastDiv fd_ntn, fd_tw, fd_th;
   int ncols;
+  // N-SPLIT TAIL.  A launch whose tile count is not a multiple of the CTA count ends with a partial wave in which most SMs
+  // idle (600 tiles on 148 CTAs: 4.05 waves of work in 5 waves of time).  For K-heavy BLOCK_N = 256 launches in stream mode
+  // the R tiles of that last wave are cut along N into tail_nsub (2 or 4) sub-tiles of 128 / 64 output channels, one per CTA:
+  // a sub-tile streams the same pixel tile but only its slice of the weight tile (16 + 8 KB per K step instead of 48) and
+  // issues N = 64 / 128 MMAs, so the last wave costs about half a wave -- and, unlike a split along K, needs no reduction.
+  // Units 0 .. tail_first-1 are whole tiles (tail_first = the full waves, a multiple of the grid); unit tail_first + u is
+  // sub-tile u % tail_nsub of tile tail_first + u / tail_nsub.  Off: tail_first = n_units = total_tiles, tail_nsub = 1.
+  int tail_first, tail_nsub, n_units;
+  CUtensorMap b_sub_map;   // box {64, BLOCK_N / tail_nsub}
   int npipe;         // 1 or 2 producer -> MMA pipelines working on alternate tiles
   int stages;        // per pipeline: stream mode = ring of (A, B) stages; halo mode = ring of B tiles (unless resident)
   int kpack;         // stream mode: K steps (of 64) per stage / barrier round
@@ -142,6 +151,18 @@ __device__ __forceinline__ int fdiv_ntile(const ConvGemmParams& p, int tile) {
   return tile - (int)fdiv((uint32_t)tile, p.fd_ntn) * p.n_tiles_n;
 }
 
+// work unit -> tile and N sub-tile (q = 0 for whole tiles)
+__device__ __forceinline__ int unit_tile(const ConvGemmParams& p, int wk, int& q) {
+  if (wk < p.tail_first) {
+    q = 0;
+    return wk;
+  }
+  const int u = wk - p.tail_first;
+  const int t = p.tail_nsub == 4 ? (u >> 2) : (u >> 1);
+  q = u - t * p.tail_nsub;
+  return p.tail_first + t;
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -160,13 +181,21 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
 template <int BLOCK_N>
 struct ChunkIter {
   int wk, j, nch, n_tile, img, h0, w0;
+  int jb;        // first 64-channel chunk of this unit within its tile (N-split tail: sub-tile q starts at chunk q * nch)
   bool valid;
   __device__ __forceinline__ void load(const ConvGemmParams& p) {
-    valid = wk < p.total_tiles;
+    valid = wk < p.n_units;
     if (valid) {
-      decode_tile(p, wk, n_tile, img, h0, w0);
+      int q;
+      const int tile = unit_tile(p, wk, q);
+      decode_tile(p, tile, n_tile, img, h0, w0);
       const int rem = p.ncols - n_tile * BLOCK_N;
       nch = (rem < BLOCK_N ? rem : BLOCK_N) >> 6;
+      jb = 0;
+      if (wk >= p.tail_first) {       // (only planned when every tile is BLOCK_N channels wide)
+        nch = (BLOCK_N / 64) / p.tail_nsub;
+        jb = q * nch;
+      }
     }
   }
   __device__ __forceinline__ void init(const ConvGemmParams& p) {
@@ -367,9 +396,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       uint32_t phase = 0;
       const int kp = p.kpack;
       const int ksteps = p.ksteps;
-      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x) {
-        int n_tile, img, h0, w0;
-        decode_tile(p, wk, n_tile, img, h0, w0);
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.n_units; wk += npipe * (int)gridDim.x) {
+        int n_tile, img, h0, w0, q;
+        decode_tile(p, unit_tile(p, wk, q), n_tile, img, h0, w0);
+        // N-split tail unit: only rows [q * BLOCK_N / nsub, ...) of the weight tile
+        const bool sub = wk >= p.tail_first;
+        const int b_bytes = sub ? kBTileBytes / p.tail_nsub : kBTileBytes;
+        const int b_row0 = n_tile * BLOCK_N + (sub ? q * (BLOCK_N / p.tail_nsub) : 0);
+        const CUtensorMap* bmap = sub ? &p.b_sub_map : &p.b_map;
         int kcol = 0, ks = 0, slot = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const SegDev sg = p.seg[s];
@@ -379,11 +413,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               if (elect_one()) {
                 if (slot == 0) {
                   const int n_grp = ksteps - ks < kp ? ksteps - ks : kp;      // K steps in this barrier round
-                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + kBTileBytes));
+                  mbar_arrive_expect_tx(&fullb[stage], n_grp * (kATileBytes + b_bytes));
                 }
                 tma_load_4d(sA + (stage * kp + slot) * kATileBytes, &p.a_maps[sg.map_id], &fullb[stage], c * kBlockK,
                             w0 + sg.dw, h0 + sg.dh, img);
-                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, &p.b_map, &fullb[stage], kcol, n_tile * BLOCK_N);
+                tma_load_2d(sB + (stage * kp + slot) * kBTileBytes, bmap, &fullb[stage], kcol, b_row0);
               }
               __syncwarp();
             }
@@ -488,11 +522,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       const int kp = p.kpack;
       const int ksteps = p.ksteps;
       int li = 0;
-      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.total_tiles; wk += npipe * (int)gridDim.x, ++li) {
+      for (int wk = (int)blockIdx.x + pipe * (int)gridDim.x; wk < p.n_units; wk += npipe * (int)gridDim.x, ++li) {
         const int as = li & 1;
         mbar_wait(&temptyb[as], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (pipe * 2 + as) * BLOCK_N;
+        // N-split tail unit: the same A tile against BLOCK_N / nsub rows of the weight tile (narrower MMAs)
+        constexpr uint32_t idesc_h = umma_idesc_bf16(kBlockM, BLOCK_N >= 64 ? BLOCK_N / 2 : 32, 0, 0);
+        constexpr uint32_t idesc_q = umma_idesc_bf16(kBlockM, BLOCK_N >= 128 ? BLOCK_N / 4 : 32, 0, 0);
+        const uint32_t idesc_u = wk < p.tail_first ? idesc : (p.tail_nsub == 4 ? idesc_q : idesc_h);
         for (int ks = 0; ks < ksteps; ks += kp) {
           const int n = ksteps - ks < kp ? ksteps - ks : kp;
           mbar_wait(&fullb[stage], phase);
@@ -501,9 +539,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             for (int j = 0; j < n; ++j) {
               const uint64_t ad = kDescHiB | ((a_base + (stage * kp + j) * kATileBytes) >> 4);
               const uint64_t bd = kDescHiB | ((b_base + (stage * kp + j) * kBTileBytes) >> 4);
-              umma_bf16(d_tmem, ad, bd, idesc, (ks + j) != 0);
+              umma_bf16(d_tmem, ad, bd, idesc_u, (ks + j) != 0);
 #pragma unroll
-              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              for (int k = 1; k < kBlockK / 16; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc_u, 1u);
             }
             umma_commit(&emptyb[stage]);   // one commit per barrier round
           }
@@ -576,7 +614,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (++pf_slot == kEiDepth) pf_slot = 0;
         uint8_t* dst = ei + slot * slot_bytes;
         mbar_arrive_expect_tx(&my_bar[slot], slot_bytes);
-        const int c = pf.n_tile * BLOCK_N + pf.j * 64;
+        const int c = pf.n_tile * BLOCK_N + (pf.jb + pf.j) * 64;
         if (p.has_add) tma_load_4d(dst, &p.add_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
         if (p.has_mask)
           tma_load_4d(dst + p.has_add * kSlabBytes, &p.mask_map, &my_bar[slot], c, pf.w0 + slab_w, pf.h0 + slab_h, pf.img);
@@ -594,7 +632,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if (ci.valid && (ci.h0 + rh < p.OH) && (ci.w0 + rw < p.OW) && (ci.img < p.NB)) {
           const char* a = static_cast<const char*>(p.mask_bits.ptr) + (long long)ci.img * p.mask_bits.sn +
                           (long long)(ci.h0 + rh) * p.mask_bits.sh + (long long)(ci.w0 + rw) * p.mask_bits.sw +
-                          ((ci.n_tile * BLOCK_N + ci.j * 64) >> 3);
+                          ((ci.n_tile * BLOCK_N + (ci.jb + ci.j) * 64) >> 3);
           r = __ldg(reinterpret_cast<const uint2*>(a));
         }
         return r;
@@ -607,7 +645,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       uint32_t in_phase = 0;
       int it = 0;            // tiles of this CTA visited
       // every tile of the CTA is visited by BOTH warp sets (each must release the accumulator stage exactly once)
-      for (int wk = blockIdx.x; wk < p.total_tiles; wk += gridDim.x, ++it) {
+      for (int wk = blockIdx.x; wk < p.n_units; wk += gridDim.x, ++it) {
         const int li = it >> pshift;                         // index of the tile within its pipeline
         const int as = ((it & pshift) << 1) | (li & 1);      // accumulator stage: 2 per pipeline
         const uint32_t aphase = (li >> 1) & 1;
@@ -615,7 +653,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         tc_fence_after();
         while (cur.valid && cur.wk == wk) {
           const int j = cur.j;
-          const int col0 = cur.n_tile * BLOCK_N + j * 64;
+          const int col0 = cur.n_tile * BLOCK_N + (cur.jb + j) * 64;     // (TMEM columns below: j, the unit's own accumulator)
           const uint8_t* in_slab = ei + in_slot * slot_bytes;
           uint8_t* out_slab = eo + out_slot * kSlabBytes;
           // rows outside the image are clipped by the TMA store; they only have to be zeroed for the column sums
@@ -1210,6 +1248,24 @@ extern "C" int urso_convgemm_create(const urso_convgemm_desc* d, urso_convgemm_t
     delete h;
     return rc;
   }
+  // ---- N-split tail (see ConvGemmParams::tail_*): K-heavy BLOCK_N = 256 launches in stream mode with a partial last wave
+  p.tail_first = p.n_units = p.total_tiles;
+  p.tail_nsub = 1;
+  if (tail_split_enabled() && bn == 256 && !p.halo && !p.radd && p.epi_tma && pl.npipe == 1 && pl.kpack == 1 && ksteps >= 8 &&
+      d->b_rows % 256 == 0 && p.total_tiles > h->grid) {
+    const int full = p.total_tiles / h->grid * h->grid;
+    const int R = p.total_tiles - full;
+    const int nsub = R == 0 ? 1 : (4 * R <= h->grid ? 4 : (2 * R <= h->grid ? 2 : 1));
+    if (nsub > 1) {
+      p.tail_first = full;
+      p.tail_nsub = nsub;
+      p.n_units = full + R * nsub;
+      if (int rc = make_mat_map(&p.b_sub_map, d->b, d->b_rows, d->b_k, bn / nsub)) {
+        delete h;
+        return rc;
+      }
+    }
+  }
   if (p.epi_tma) {
     const int bw = d->TW < 32 ? d->TW : 32, bh = 32 / bw;
     int rc = make_pix_map(&p.out_map, d->out, d->b_rows, d->OW, d->OH, d->NB, bw, bh);
@@ -1270,3 +1326,6 @@ extern "C" int urso_convgemm_plan_info(const urso_convgemm_t* h, int32_t* out9) 
   for (int i = 0; i < 9; ++i) out9[i] = v[i];
   return 0;
 }
+
+/* N-split tail of the launch: number of sub-tiles each tile of the last partial wave is cut into (1 = none) */
+extern "C" int urso_convgemm_tail_split(const urso_convgemm_t* h) { return h != nullptr ? h->params.tail_nsub : 0; }

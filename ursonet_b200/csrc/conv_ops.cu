@@ -316,6 +316,7 @@ extern "C" int urso_conv2d_fwd_stage_job(const urso_conv2d_fwd_t* h, void* out_)
   j->kind = 0; j->K = h->K; j->CO = h->cout; j->rows_out = h->cout; j->ld_out = h->K;
   return 0;
 }
+extern "C" int urso_conv2d_fwd_tail_split(const urso_conv2d_fwd_t* h) { return h != nullptr ? urso_convgemm_tail_split(h->plan) : 0; }
 extern "C" int urso_conv2d_fwd_plan_info(const urso_conv2d_fwd_t* h, int32_t* out9) {
   URSO_REQUIRE(h != nullptr, "null handle");
   return urso_convgemm_plan_info(h->plan, out9);
@@ -541,6 +542,9 @@ extern "C" int urso_conv2d_dgrad_launch(urso_conv2d_dgrad_t* h, void* stream) {
 extern "C" int urso_conv2d_dgrad_plan_info(const urso_conv2d_dgrad_t* h, int32_t launch, int32_t* out9) {
   URSO_REQUIRE(h != nullptr && launch >= 0 && launch < (int)h->phases.size(), "bad handle / launch index");
   return urso_convgemm_plan_info(h->phases[launch].plan, out9);
+}
+extern "C" int urso_conv2d_dgrad_tail_split(const urso_conv2d_dgrad_t* h, int32_t launch) {
+  return (h != nullptr && launch >= 0 && launch < (int)h->phases.size()) ? urso_convgemm_tail_split(h->phases[launch].plan) : 0;
 }
 extern "C" int urso_conv2d_dgrad_untouched_phases(const urso_conv2d_dgrad_t* h) { return h ? h->untouched : -1; }
 extern "C" int urso_conv2d_dgrad_num_launches(const urso_conv2d_dgrad_t* h) { return h ? (int)h->phases.size() : -1; }

@@ -99,6 +99,10 @@ SIGNATURES = {
     "urso_set_pdl": [_i32],
     "urso_set_residual_mma": [_i32],
     "urso_set_wgrad_halo": [_i32],
+    "urso_set_tail_split": [_i32],
+    "urso_convgemm_tail_split": [_vp],
+    "urso_conv2d_fwd_tail_split": [_vp],
+    "urso_conv2d_dgrad_tail_split": [_vp, _i32],
     "urso_sizeof_convgemm_desc": [],
     "urso_sizeof_wgrad_desc": [],
     "urso_convgemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(_vp)],
@@ -171,7 +175,7 @@ SIGNATURES = {
     "urso_colsum_bf16": [_vp, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"urso_last_error": C.c_char_p, "urso_convgemm_destroy": None, "urso_wgrad_destroy": None,
-             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_set_wgrad_halo": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
+             "urso_same_pad": None, "urso_set_max_ctas": None, "urso_set_dry_run": None, "urso_set_pdl": None, "urso_set_residual_mma": None, "urso_set_wgrad_halo": None, "urso_set_tail_split": None, "urso_stem_grad_row_map": None, "urso_conv2d_fwd_destroy": None,
              "urso_conv2d_dgrad_destroy": None, "urso_conv2d_wgrad_destroy": None,
              "urso_conv2d_fwd_workspace_bytes": C.c_int64, "urso_conv2d_dgrad_workspace_bytes": C.c_int64}
 
@@ -395,7 +399,9 @@ class Conv2dFwd:
         """Planned Engine-F launch: dict(block_n, npipe, stages, kpack, halo, bres, a_stages, smem_bytes, grid)."""
         v = (_i32 * 9)()
         check(load().urso_conv2d_fwd_plan_info(self._h, v), "urso_conv2d_fwd_plan_info")
-        return dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem_bytes", "grid"), v))
+        d = dict(zip(("block_n", "npipe", "stages", "kpack", "halo", "bres", "a_stages", "smem_bytes", "grid"), v))
+        d["tail_split"] = int(load().urso_conv2d_fwd_tail_split(self._h))
+        return d
 
     def launch(self):
         check(load().urso_conv2d_fwd_launch(self._h, stream_ptr()), "urso_conv2d_fwd_launch")
